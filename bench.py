@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- GP joint Thompson samples/s of the MTS posterior-sampling step.
+
+Workload (BASELINE.json configs[4], SURVEY.md 8d "sweep"): per trial n=1024
+observations, m=8192 candidates (T=64 tasks x A=128 actions, task-major),
+d=6, S=256 Thompson draws, fp64, SE-ARD kernel at fixed hyper-parameters.
+One "step" = the whole hot path (Gram -> chol -> alpha -> mean -> cross-cov ->
+trsm -> Sigma -> chol(Sigma) -> Philox Z -> mu + L Z -> per-task argmax -> pick)
+for ``streams x batch`` independent trials on every GPU.
+
+  python bench.py --gpus N --steps K --warmup W           (our arm)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+      (the reference's CPU path: numpy/LAPACK restatement in oracle/, one trial
+       per step on rank 0's host cores; the reference itself has no GPU path)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OBS, N_TASK, N_ACT, N_DRAW, DIM = 1024, 64, 128, 256, 6
+METRIC = 'GP joint Thompson samples/sec (m=8192 grid, fp64)'
+UNIT = 'samples/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=6)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--streams', type=int, default=4, help='concurrent trial groups per GPU')
+    ap.add_argument('--batch', type=int, default=1, help='trials per kernel launch (grid.z)')
+    ap.add_argument('--cpu-trials', type=int, default=2, help='trials timed for cpu_baseline')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-peaks', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name():
+    return ('sweep: n=%d obs, m=%d candidates (T=%d x A=%d), d=%d, S=%d draws/trial, SE-ARD '
+            'bw ctx 0.25 / act 0.05, scale 1, noise 1e-2, mu0 0'
+            % (N_OBS, N_TASK * N_ACT, N_TASK, N_ACT, DIM, N_DRAW))
+
+
+# --------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get('num_threads') for p in threadpool_info() if p.get('user_api') == 'blas']
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_step_seconds(trial):
+    """One full-size trial-step of the CPU restatement (numpy + LAPACK, all BLAS threads)."""
+    from oracle import sweep_step
+    from ocbo_b200.sweep import make_trial_inputs
+    X, y, Xs = make_trial_inputs(trial, N_OBS, N_TASK, N_ACT)
+    np.random.seed(trial)
+    t0 = time.perf_counter()
+    sweep_step.step(X, y, Xs, N_TASK, N_DRAW)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm for this path on the host
+    cores (oracle port -- Dragonfly, which holds it, is not installable here)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    for w in range(args.warmup):
+        cpu_step_seconds(w)
+    t = [cpu_step_seconds(args.warmup + k) for k in range(args.steps)]
+    total = float(np.sum(t))
+    value = N_DRAW * args.steps / total
+    cores = cpu_threads()
+    sample = '%d steps x 1 full-size trial (n=%d, m=%d, S=%d) per step' % (
+        args.steps, N_OBS, N_TASK * N_ACT, N_DRAW)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': workload_name(), 'trials_per_step': 1,
+                   'note': 'numpy/LAPACK restatement of the Dragonfly path (oracle/), host cores only'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def measure_fp64_peaks(torch, lib_call, dev):
+    """FP64 denominators (MEASURED_PEAKS.json has no FP64 row):
+    cuBLAS DGEMM 8192^3 via torch.matmul, the raw DMMA.8x8x4 / DFMA issue rate and
+    this library's own DMMA tile core on a plain 8192^3 NT GEMM."""
+    out = {}
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    out['cublas_dgemm_tflops'] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    blocks, iters = 148 * 8, 4000
+    for name, per_thread_flops in (('ocbo_probe_dmma', None), ('ocbo_probe_dfma', 16 * 2)):
+        lib_call(name, ctypes.c_void_p(sink.data_ptr()), blocks, 10, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib_call(name, ctypes.c_void_p(sink.data_ptr()), blocks, iters, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if per_thread_flops is None:
+            flops = blocks * 8 * iters * 16 * 512.0  # 8 warps x 16 DMMA(8x8x4 = 512 flop)
+        else:
+            flops = blocks * 256 * iters * float(per_thread_flops)
+        out[name.replace('ocbo_probe_', '') + '_issue_tflops'] = flops / (ms * 1e-3) / 1e12
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib_call('ocbo_probe_dgemm_nt', ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                 ctypes.c_void_p(c.data_ptr()), n, st)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    out['own_dgemm_nt_tflops'] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    del a, b, c
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ocbo_b200 import engine, sweep
+    from ocbo_b200._lib import call as lib_call
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    G, B = args.streams, args.batch
+    trials_per_step = G * B
+    m = N_TASK * N_ACT
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    groups = [sweep.SweepStep(N_OBS, N_TASK, N_ACT, N_DRAW, DIM, batch=B, stream=s) for s in streams]
+
+    def trial_id(step, g, b):  # trial r lives on rank r mod W
+        return ((step * G + g) * B + b) * world + rank
+
+    total_steps = args.warmup + args.steps
+    pool = {}
+    for step in range(total_steps):
+        for g in range(G):
+            for b in range(B):
+                t = trial_id(step, g, b)
+                pool[t] = sweep.make_trial_inputs(t, N_OBS, N_TASK, N_ACT)
+
+    def ids(step, g):
+        return [trial_id(step, g, b) for b in range(B)]
+
+    # ---- (1) device-resident throughput: inputs already in HBM -----------------
+    for g, grp in enumerate(groups):
+        grp.set_inputs_device(ids(0, g), [pool[t] for t in ids(0, g)])
+    main = torch.cuda.current_stream()
+
+    def run_resident(nsteps):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record(main)
+        for s in streams:
+            s.wait_event(start)
+        for _ in range(nsteps):
+            for grp in groups:
+                grp.run()
+        for s in streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+        end.record(main)
+        barrier()
+        return start.elapsed_time(end)
+
+    run_resident(args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = engine.LAUNCHES[0]
+    ms_resident = run_resident(args.steps)
+    launches = engine.LAUNCHES[0] - launches0
+    clocks = sampler.stop()
+
+    # ---- (2) end to end: host buffers in, picks out, every step ----------------
+    def run_e2e(first_step, nsteps):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        start.record(main)
+        for s in streams:
+            s.wait_event(start)
+        picks = []
+        for k in range(nsteps):
+            step = first_step + k
+            for g, grp in enumerate(groups):
+                if k > 0:
+                    picks.append(grp.result_host())  # D2H result of the previous step
+                grp.submit_host(ids(step, g), [pool[t] for t in ids(step, g)])
+        for grp in groups:
+            picks.append(grp.result_host())
+        for s in streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+        end.record(main)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(start.elapsed_time(end), wall), picks
+
+    run_e2e(0, args.warmup)
+    ms_e2e, picks = run_e2e(args.warmup, args.steps)
+    checksum = int(sum(int(p[0].sum()) + int(p[1].sum()) for p in picks))
+
+    # ---- max over ranks ---------------------------------------------------------
+    times = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_resident, ms_e2e = [float(x) for x in times.tolist()]
+    samples_per_step = world * trials_per_step * N_DRAW
+    value = samples_per_step * args.steps / (ms_resident * 1e-3)
+    e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- single NCCL gather of the picks -----------------------------
+    if world > 1:
+        last = torch.from_numpy(np.stack([picks[-1][0], picks[-1][1]])).to(dev)
+        gathered = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
+        dist.gather(last, gathered, dst=0)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: Cholesky trailing update (DMMA) ------
+        grp = groups[0]
+        grp.run()
+        torch.cuda.synchronize()
+        st = ctypes.c_void_p(grp.stream.cuda_stream)
+        # re-assemble Sigma (the factorisation above overwrote it) and time its kernels
+        lib_call('ocbo_post_cov', grp.kind, DIM, ctypes.c_void_p(grp.Xs.data_ptr()), m,
+                 grp.Xs.stride(0), None, ctypes.c_void_p(grp.V.data_ptr()), N_OBS, m, grp.V.stride(0),
+                 ctypes.c_void_p(grp.theta.data_ptr()), grp.theta.stride(0),
+                 ctypes.c_void_p(grp.Sigma.data_ptr()), m, grp.Sigma.stride(0), 1, B, st)
+        grp.info.zero_()
+        torch.cuda.synchronize()
+        ms3 = (ctypes.c_float * 3)()
+        lib_call('ocbo_potrf_profile', ctypes.c_void_p(grp.Sigma.data_ptr()), m, m,
+                 grp.Sigma.stride(0), ctypes.c_void_p(grp.invdS.data_ptr()),
+                 ctypes.c_void_p(grp.info[1].data_ptr()), B, st, ms3)
+        nt = m // 128
+        # algorithmic flops of the trailing updates: lower triangle incl. diagonal of the
+        # (r*128)^2 trailing block, rank-128 update, 2 flops per multiply-add
+        alg = sum(((r * 128) * (r * 128 + 1) / 2.0) * 2.0 * 128 for r in range(1, nt)) * B
+        trailing_tflops = alg / (ms3[2] * 1e-3) / 1e12 if ms3[2] > 0 else None
+        peaks = {} if args.no_peaks else measure_fp64_peaks(torch, lib_call, dev)
+        peak = peaks.get('cublas_dgemm_tflops')
+        step_tflops = sweep.step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
+            / (ms_resident * 1e-3) / 1e12
+        roof = {
+            'bound': 'tensor', 'kernel': 'gemm_nt_kernel (Cholesky trailing update, DMMA.8x8x4 fp64)',
+            'achieved': trailing_tflops, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': (trailing_tflops / peak) if (peak and trailing_tflops) else None,
+            'traffic': None,
+            'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
+                           'MEASURED_PEAKS.json has no FP64 row',
+            'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'trailing': ms3[2]},
+            'step_tflops_per_gpu': step_tflops / world,
+            'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
+            'fp64_probes_tflops': peaks,
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu_step_seconds(0)  # warm BLAS threads
+            ts = [cpu_step_seconds(1 + k) for k in range(args.cpu_trials)]
+            cpu = {'value': N_DRAW * len(ts) / float(np.sum(ts)), 'unit': UNIT,
+                   'cores': cpu_threads(), 'kind': 'port',
+                   'sample': '%d full-size trials (n=%d, m=%d, S=%d), numpy+LAPACK oracle, '
+                             '1 warm-up trial' % (len(ts), N_OBS, m, N_DRAW)}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_resident / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(), 'trials_per_step_per_gpu': trials_per_step,
+                       'streams': G, 'batch': B, 'parallelism': 'trials sharded r mod W, no collective '
+                       'inside the step, one gather of picks',
+                       'l2': 'working set per trial (Sigma 512 MiB) exceeds the 126 MB L2; no flush needed',
+                       'rng': 'device Philox4x32-10 keyed (seed, trial)'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT,
+                    'h2d_bytes_per_step': sum(g.h2d_bytes for g in groups),
+                    'd2h_bytes_per_step': sum(g.d2h_bytes for g in groups),
+                    'ms_per_step': ms_e2e / args.steps, 'picks_checksum': checksum},
+            'gpu_launches': launches,
+            'roofline': roof,
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,199 @@
+/*
+ * libocbo_b200 -- C ABI of the B200-native GP posterior + Thompson-sampling
+ * path behind OCBO's Multi-task Thompson Sampling (MTS).
+ *
+ * The reference (fusion-ml/OCBO) has no FFI: its boundary for this path is the
+ * Python GP interface in src/gp/gp_interface.py.  Each entry point below names
+ * the reference call it replaces (file:line under /root/reference); the Python
+ * binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - matrices are row-major fp64 with an explicit leading dimension (elements)
+ *     and a batch stride (elements); `batch` problems are processed per call
+ *     (grid.z), a stride of 0 shares the operand between problems;
+ *   - dimensions that feed the DMMA tiles (n, m, nrhs) must be multiples of
+ *     OCBO_TILE (128); callers pad.  Padding is exact: padded rows/cols of a
+ *     Gram matrix are identity, of a cross-covariance zero, so results on the
+ *     valid part are unchanged (DESIGN.md "padding");
+ *   - theta[b] = { scale, noise_var, mu0, bw_1 .. bw_D } (stride `s_theta`);
+ *   - calls are asynchronous on `stream`, never synchronise, never allocate;
+ *   - return 0 on success, -k if argument k (1-based) is invalid,
+ *     1000 + cudaError_t on a CUDA failure (see ocbo_last_error_string);
+ *   - numerical failure of a Cholesky is reported per problem in `info[b]`
+ *     (device int32): 0 ok, k>0 = first non-positive / NaN pivot at column k,
+ *     LAPACK dpotrf convention, so the host can walk Dragonfly's jitter ladder
+ *     (SURVEY.md Appendix A stable_cholesky).
+ */
+#ifndef OCBO_B200_H
+#define OCBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCBO_TILE 128
+#define OCBO_MAX_DIM 16
+
+/* kernel kinds: SE and Matern nu = 1/2, 3/2, 5/2 */
+#define OCBO_KERNEL_SE 0
+#define OCBO_KERNEL_MATERN12 1
+#define OCBO_KERNEL_MATERN32 2
+#define OCBO_KERNEL_MATERN52 3
+
+/* ocbo_gram flags */
+#define OCBO_GRAM_SYM 1        /* X1 == X2: pad diagonal = 1, symmetric semantics   */
+#define OCBO_GRAM_LOWER 2      /* with SYM: only tiles on/below the diagonal written */
+#define OCBO_GRAM_ADD_NOISE 4  /* with SYM: add theta.noise_var to valid diagonal    */
+
+typedef void* ocbo_stream_t; /* cudaStream_t */
+
+const char* ocbo_last_error_string(void);
+int ocbo_version(void);
+
+/* Workspace (bytes) for the inverse diagonal blocks that ocbo_potrf writes and
+ * ocbo_trsm_lower / ocbo_solve_vec read: batch * (n/128) * 128*128 doubles. */
+int64_t ocbo_invdiag_elems(int n);
+
+/* K[b][i][j] = scale_b * phi(|| (x1_i - x2_j) / bw_b ||) for i < nv1[b], j < nv2[b];
+ * padding per the conventions above.  nv1/nv2 may be NULL (= n1/n2).
+ * Replaces gp_core.kernel(A, B)  (src/gp/gp_interface.py:113-117) and the Gram
+ * assembly inside Dragonfly's build_posterior / eval. */
+int ocbo_gram(int kind, int dim,
+              const double* X1, int n1, int64_t s_x1, const int32_t* nv1,
+              const double* X2, int n2, int64_t s_x2, const int32_t* nv2,
+              const double* theta, int64_t s_theta,
+              double* K, int ldk, int64_t s_k,
+              int batch, int flags, ocbo_stream_t stream);
+
+/* A[b][i][i] += val[b] for i < nv[b] (jitter ladder step). */
+int ocbo_add_diag(double* A, int n, int lda, int64_t s_a, const int32_t* nv,
+                  const double* val, int batch, ocbo_stream_t stream);
+
+/* out[b] = max_i A[b][i][i], i < nv[b]  (the ladder's max(diag M)). */
+int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* nv,
+                  double* out, int batch, ocbo_stream_t stream);
+
+/* In-place lower Cholesky A = L L^T (row-major, lower triangle referenced and
+ * overwritten; the strictly upper part of the diagonal 128-blocks is zeroed,
+ * blocks above the diagonal are not touched).  Also writes inv(L_jj) of every
+ * diagonal block to invdiag.  info must be zeroed by the caller.
+ * Replaces np.linalg.cholesky inside stable_cholesky
+ * (GP.build_posterior / draw_gaussian_samples; src/gp/gp_interface.py:78,87-88,132). */
+int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
+               double* invdiag, int32_t* info, int batch, ocbo_stream_t stream);
+
+/* ocbo_potrf with CUDA events around every launch, summed per kernel class into
+ * ms_host[3] = { diagonal-block, panel-solve, trailing-update } milliseconds.
+ * Synchronises the stream; used by bench.py's roofline leg only. */
+int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a,
+                       double* invdiag, int32_t* info, int batch, ocbo_stream_t stream,
+                       float* ms_host);
+
+/* B <- L^{-1} B  (left, lower, non-transposed), B is n x nrhs row-major.
+ * Replaces solve_lower_triangular(L, K(X*, X)^T)  (src/gp/gp_interface.py:116,118;
+ * Dragonfly eval 'covar'). */
+int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l,
+                    const double* invdiag,
+                    double* B, int nrhs, int ldb, int64_t s_b,
+                    const int32_t* info, int batch, ocbo_stream_t stream);
+
+/* alpha = L^{-T} L^{-1} (y - mu0) on the nv[b] valid rows (0 elsewhere) and
+ * lml[b] = -1/2 (y-mu0)^T alpha - sum log L_ii - nv/2 log 2 pi.
+ * Either output may be NULL.  Replaces the alpha solve of build_posterior and
+ * the LML evaluator behind fit_gp (src/gp/gp_interface.py:87-88,123-125). */
+int ocbo_solve_alpha_lml(const double* L, int n, int ldl, int64_t s_l,
+                         const double* invdiag,
+                         const double* y, int64_t s_y, const int32_t* nv,
+                         const double* theta, int64_t s_theta,
+                         double* alpha, int64_t s_alpha, double* lml,
+                         const int32_t* info, int batch, ocbo_stream_t stream);
+
+/* mean[b][i] = mu0 + sum_j k(xs_i, x_j) alpha_j, i < mv[b] (0 on padding).
+ * Replaces the mean half of GP.eval (src/gp/gp_interface.py:69-74). */
+int ocbo_post_mean(int kind, int dim,
+                   const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                   const double* X, int n, int64_t s_x, const int32_t* nv,
+                   const double* theta, int64_t s_theta,
+                   const double* alpha, int64_t s_alpha,
+                   double* mean, int64_t s_mean, int batch, ocbo_stream_t stream);
+
+/* Sigma = K(Xs, Xs) - V^T V with V = L^{-1} K(X, Xs) (n x m, from
+ * ocbo_trsm_lower).  lower_only != 0 writes tiles on/below the diagonal only
+ * (diagonal tiles full); padding rows/cols of Sigma are identity.
+ * Replaces the covariance half of GP.eval(X, 'covar') and the in-tree
+ * get_pt_relations (src/gp/gp_interface.py:72,112-119). */
+int ocbo_post_cov(int kind, int dim,
+                  const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                  const double* V, int n, int ldv, int64_t s_v,
+                  const double* theta, int64_t s_theta,
+                  double* Sigma, int lds, int64_t s_sigma,
+                  int lower_only, int batch, ocbo_stream_t stream);
+
+/* Cross form of the above for two point sets (get_pt_relations, :112-119):
+ * C = K(A, B) - V1^T V2, V1 (n x ma), V2 (n x mb). */
+int ocbo_post_cross_cov(int kind, int dim,
+                        const double* Xa, int ma, int64_t s_xa, const int32_t* mav,
+                        const double* Xb, int mb, int64_t s_xb, const int32_t* mbv,
+                        const double* V1, int ldv1, int64_t s_v1,
+                        const double* V2, int ldv2, int64_t s_v2, int n,
+                        const double* theta, int64_t s_theta,
+                        double* C, int ldc, int64_t s_c,
+                        int batch, ocbo_stream_t stream);
+
+/* Copy the lower triangle onto the upper one (full symmetric covar for eval). */
+int ocbo_symmetrize_lower(double* A, int n, int lda, int64_t s_a, int batch,
+                          ocbo_stream_t stream);
+
+/* Z[b] (m x S row-major, ld = ldz) <- standard normals from Philox4x32-10
+ * keyed by (seed, trial_ids[b]); layout contract in oracle/philox.py.
+ * Replaces np.random.normal(size=(m, S)) in draw_gaussian_samples. */
+int ocbo_philox_normal(double* Z, int m, int S, int ldz, int64_t s_z,
+                       uint64_t seed, const int32_t* trial_ids, int batch,
+                       ocbo_stream_t stream);
+
+/* F = mean + L Z  (m x S; S a multiple of 128 uses the DMMA path, S <= 8 the
+ * HBM-bound row-dot path).  Replaces (L.dot(U)).T + mu in
+ * draw_gaussian_samples (src/gp/gp_interface.py:76-79). */
+int ocbo_sample(const double* mean, int64_t s_mean,
+                const double* L, int m, int ldl, int64_t s_l,
+                const double* Z, int S, int ldz, int64_t s_z,
+                double* F, int ldf, int64_t s_f,
+                const int32_t* info, int batch, ocbo_stream_t stream);
+
+/* Segmented max / first-index argmax per sample column:
+ * seg_ptr[b][0..nseg] row offsets; out_max/out_arg are [batch][nseg][S]
+ * (arg relative to the segment start; empty segment -> -inf / -1).
+ * Replaces np.max / np.argmax in src/strategies/mts.py:37-38,
+ * joint_mts.py:46-53, src/cstrats/profile_cts.py:101-104. */
+int ocbo_segment_argmax(const double* F, int S, int ldf, int64_t s_f,
+                        const int32_t* seg_ptr, int nseg,
+                        double* out_max, int32_t* out_arg,
+                        int batch, ocbo_stream_t stream);
+
+/* Joint-MTS pick from the segment reductions (joint_mts.py:43-57):
+ * segments 0..T-1 are the old points per task (pass n_old_seg = 0 for the
+ * grid-only sweep: old best = 0), segments n_old_seg.. are the T new-point
+ * segments.  Per (b, s): task = first argmax_t (max new_t - max old_t),
+ * action = arg within new_t.  Outputs [batch][S]. */
+int ocbo_joint_pick(const double* seg_max, const int32_t* seg_arg, int nseg,
+                    int n_old_seg, int T, int S,
+                    int32_t* out_task, int32_t* out_action, double* out_gain,
+                    int batch, ocbo_stream_t stream);
+
+/* FP64 throughput probes used by bench.py to measure the DMMA / DFMA rate the
+ * roofline is quoted against (MEASURED_PEAKS.json has no FP64 row).
+ * Each thread block runs `iters` dependent-free DMMA.8x8x4 / DFMA chains. */
+int ocbo_probe_dmma(double* sink, int blocks, int iters, ocbo_stream_t stream);
+int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream);
+/* Plain C = A B^T DGEMM (n x n x n, multiples of 128) through the library's
+ * DMMA tile core -- the GEMM-shaped roofline reference for the core itself. */
+int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n,
+                        ocbo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCBO_B200_H */

@@ -1,0 +1,399 @@
+// extern "C" surface of libocbo_b200 (declared in include/ocbo_b200.h) and the
+// host-side blocked drivers (Cholesky, left triangular solve) that sequence the
+// tile kernels.  No allocation, no synchronisation, no global state besides
+// the per-kernel "max dynamic smem" opt-in done on first use.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace ocbo;
+
+static thread_local char g_err[256] = "ok";
+
+static int fail_arg(int k, const char* what) {
+  snprintf(g_err, sizeof(g_err), "invalid argument %d: %s", k, what);
+  return -k;
+}
+static int check(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return 1000 + (int)e;
+}
+#define CK(call, where)              \
+  do {                               \
+    int rc_ = check((call), where);  \
+    if (rc_) return rc_;             \
+  } while (0)
+
+static inline bool tile_ok(int n) { return n > 0 && n % TILE == 0; }
+
+extern "C" {
+
+const char* ocbo_last_error_string(void) { return g_err; }
+int ocbo_version(void) { return 100; }
+int64_t ocbo_invdiag_elems(int n) { return (int64_t)(n / TILE) * TILE * TILE; }
+
+int ocbo_gram(int kind, int dim, const double* X1, int n1, int64_t s_x1, const int32_t* nv1,
+              const double* X2, int n2, int64_t s_x2, const int32_t* nv2, const double* theta,
+              int64_t s_theta, double* K, int ldk, int64_t s_k, int batch, int flags,
+              ocbo_stream_t stream) {
+  if (kind < 0 || kind > 3) return fail_arg(1, "kernel kind");
+  if (dim < 1 || dim > MAXD) return fail_arg(2, "dim must be in [1, 16]");
+  if (!X1) return fail_arg(3, "X1 null");
+  if (n1 <= 0 || n1 % 64) return fail_arg(4, "n1 must be a positive multiple of 64");
+  if (!X2) return fail_arg(7, "X2 null");
+  if (n2 <= 0 || n2 % 64) return fail_arg(8, "n2 must be a positive multiple of 64");
+  if (!theta) return fail_arg(11, "theta null");
+  if (!K) return fail_arg(13, "K null");
+  if (ldk < n2 || (ldk & 1)) return fail_arg(14, "ldk must be even and >= n2");
+  if (batch <= 0) return fail_arg(16, "batch");
+  CK(launch_gram(kind, dim, X1, n1, s_x1, nv1, X2, n2, s_x2, nv2, theta, s_theta, K, ldk, s_k,
+                 batch, flags, (cudaStream_t)stream),
+     "ocbo_gram");
+  return 0;
+}
+
+int ocbo_add_diag(double* A, int n, int lda, int64_t s_a, const int32_t* nv, const double* val,
+                  int batch, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (n <= 0) return fail_arg(2, "n");
+  if (!val) return fail_arg(6, "val null");
+  if (batch <= 0) return fail_arg(7, "batch");
+  CK(launch_add_diag(A, n, lda, s_a, nv, val, batch, (cudaStream_t)stream), "ocbo_add_diag");
+  return 0;
+}
+
+int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* nv, double* out,
+                  int batch, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (n <= 0) return fail_arg(2, "n");
+  if (!out) return fail_arg(6, "out null");
+  if (batch <= 0) return fail_arg(7, "batch");
+  CK(launch_diag_max(A, n, lda, s_a, nv, out, batch, (cudaStream_t)stream), "ocbo_diag_max");
+  return 0;
+}
+
+int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info, int batch,
+               ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (lda < n || (lda & 1)) return fail_arg(3, "lda must be even and >= n");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!info) return fail_arg(6, "info null");
+  if (batch <= 0) return fail_arg(7, "batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nt = n / TILE;
+  const int64_t sInv = ocbo_invdiag_elems(n);
+  for (int j = 0; j < nt; ++j) {
+    CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "potrf_diag");
+    const int r = nt - 1 - j;
+    if (r == 0) break;
+    double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
+    NtParams p{};
+    // panel solve: X <- X inv(L_jj)^T, in place (each CTA owns its 128 rows)
+    p.P = panel; p.ldp = lda; p.sP = s_a;
+    p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
+    p.C = panel; p.ldc = lda; p.sC = s_a;
+    p.ntc = 1; p.ktiles = TILE / BK; p.row0 = 0; p.col0 = 0;
+    p.tri = 0; p.lower_skip = 0; p.mode = 0; p.info = info;
+    CK(launch_gemm_nt(p, r, batch, st), "potrf panel");
+    // trailing update: A22 -= L21 L21^T on the lower-triangular tiles
+    NtParams u{};
+    u.P = panel; u.ldp = lda; u.sP = s_a;
+    u.Q = panel; u.ldq = lda; u.sQ = s_a;
+    u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
+    u.ntc = r; u.ktiles = TILE / BK; u.row0 = 0; u.col0 = 0;
+    u.tri = 1; u.lower_skip = 0; u.mode = 1; u.info = info;
+    CK(launch_gemm_nt(u, r * (r + 1) / 2, batch, st), "potrf trailing");
+  }
+  return 0;
+}
+
+// Same factorisation, instrumented: CUDA events around every launch on `stream`,
+// summed per kernel class into ms_host[3] = {diag, panel, trailing}.  Synchronous
+// (bench.py's roofline leg only).
+int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
+                       int batch, ocbo_stream_t stream, float* ms_host) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (!invdiag || !info || !ms_host) return fail_arg(5, "null");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nt = n / TILE;
+  const int64_t sInv = ocbo_invdiag_elems(n);
+  const int nev = 3 * nt + 1;
+  cudaEvent_t* ev = new cudaEvent_t[nev];
+  for (int i = 0; i < nev; ++i) cudaEventCreate(&ev[i]);
+  int e = 0;
+  int rc = 0;
+  cudaEventRecord(ev[e++], st);
+  for (int j = 0; j < nt && !rc; ++j) {
+    rc = check(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "diag");
+    cudaEventRecord(ev[e++], st);
+    const int r = nt - 1 - j;
+    if (r == 0 || rc) break;
+    double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
+    NtParams p{};
+    p.P = panel; p.ldp = lda; p.sP = s_a;
+    p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
+    p.C = panel; p.ldc = lda; p.sC = s_a;
+    p.ntc = 1; p.ktiles = TILE / BK; p.mode = 0; p.info = info;
+    rc = check(launch_gemm_nt(p, r, batch, st), "panel");
+    cudaEventRecord(ev[e++], st);
+    NtParams u{};
+    u.P = panel; u.ldp = lda; u.sP = s_a;
+    u.Q = panel; u.ldq = lda; u.sQ = s_a;
+    u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
+    u.ntc = r; u.ktiles = TILE / BK; u.tri = 1; u.mode = 1; u.info = info;
+    if (!rc) rc = check(launch_gemm_nt(u, r * (r + 1) / 2, batch, st), "trailing");
+    cudaEventRecord(ev[e++], st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  ms_host[0] = ms_host[1] = ms_host[2] = 0.f;
+  if (!rc && se == cudaSuccess) {
+    for (int i = 1; i < e; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      ms_host[(i - 1) % 3] += ms;
+    }
+  }
+  for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  delete[] ev;
+  if (rc) return rc;
+  return check(se, "ocbo_potrf_profile sync");
+}
+
+int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* invdiag, double* B,
+                    int nrhs, int ldb, int64_t s_b, const int32_t* info, int batch,
+                    ocbo_stream_t stream) {
+  if (!L) return fail_arg(1, "L null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (ldl < n || (ldl & 1)) return fail_arg(3, "ldl");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!B) return fail_arg(6, "B null");
+  if (!tile_ok(nrhs)) return fail_arg(7, "nrhs must be a positive multiple of 128");
+  if (ldb < nrhs || (ldb & 1)) return fail_arg(8, "ldb");
+  if (batch <= 0) return fail_arg(11, "batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nt = n / TILE, ntc = nrhs / TILE;
+  const int64_t sInv = ocbo_invdiag_elems(n);
+  for (int I = 0; I < nt; ++I) {
+    double* BI = B + (size_t)I * TILE * ldb;
+    if (I > 0) {
+      NnParams u{};
+      u.P = L + (size_t)I * TILE * ldl; u.ldp = ldl; u.sP = s_l;
+      u.R = B; u.ldr = ldb; u.sR = s_b;
+      u.C = BI; u.ldc = ldb; u.sC = s_b;
+      u.ktiles = I * (TILE / BK); u.tri_k = 0; u.reverse_rows = 0; u.mode = 1; u.info = info;
+      CK(launch_gemm_nn(u, 1, ntc, batch, st), "trsm update");
+    }
+    NnParams m{};
+    m.P = invdiag + (size_t)I * TILE * TILE; m.ldp = TILE; m.sP = sInv;
+    m.R = BI; m.ldr = ldb; m.sR = s_b;
+    m.C = BI; m.ldc = ldb; m.sC = s_b;
+    m.ktiles = TILE / BK; m.tri_k = 0; m.reverse_rows = 0; m.mode = 0; m.info = info;
+    CK(launch_gemm_nn(m, 1, ntc, batch, st), "trsm diag");
+  }
+  return 0;
+}
+
+int ocbo_solve_alpha_lml(const double* L, int n, int ldl, int64_t s_l, const double* invdiag,
+                         const double* y, int64_t s_y, const int32_t* nv, const double* theta,
+                         int64_t s_theta, double* alpha, int64_t s_alpha, double* lml,
+                         const int32_t* info, int batch, ocbo_stream_t stream) {
+  if (!L) return fail_arg(1, "L null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (n > 24576) return fail_arg(2, "n too large for the single-CTA solve");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!y) return fail_arg(6, "y null");
+  if (!theta) return fail_arg(9, "theta null");
+  if (batch <= 0) return fail_arg(15, "batch");
+  CK(launch_solve_alpha_lml(L, n, ldl, s_l, invdiag, ocbo_invdiag_elems(n), y, s_y, nv, theta,
+                            s_theta, alpha, s_alpha, lml, info, batch, (cudaStream_t)stream),
+     "ocbo_solve_alpha_lml");
+  return 0;
+}
+
+int ocbo_post_mean(int kind, int dim, const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                   const double* X, int n, int64_t s_x, const int32_t* nv, const double* theta,
+                   int64_t s_theta, const double* alpha, int64_t s_alpha, double* mean,
+                   int64_t s_mean, int batch, ocbo_stream_t stream) {
+  if (kind < 0 || kind > 3) return fail_arg(1, "kernel kind");
+  if (dim < 1 || dim > MAXD) return fail_arg(2, "dim");
+  if (!Xs) return fail_arg(3, "Xs null");
+  if (m <= 0) return fail_arg(4, "m");
+  if (n < 0) return fail_arg(8, "n");
+  if (n > 0 && (!X || !alpha)) return fail_arg(7, "X/alpha null");
+  if (!theta) return fail_arg(11, "theta null");
+  if (!mean) return fail_arg(15, "mean null");
+  if (batch <= 0) return fail_arg(17, "batch");
+  CK(launch_post_mean(kind, dim, Xs, m, s_xs, mv, X, n, s_x, nv, theta, s_theta, alpha, s_alpha,
+                      mean, s_mean, batch, (cudaStream_t)stream),
+     "ocbo_post_mean");
+  return 0;
+}
+
+int ocbo_post_cov(int kind, int dim, const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                  const double* V, int n, int ldv, int64_t s_v, const double* theta,
+                  int64_t s_theta, double* Sigma, int lds, int64_t s_sigma, int lower_only,
+                  int batch, ocbo_stream_t stream) {
+  if (kind < 0 || kind > 3) return fail_arg(1, "kernel kind");
+  if (dim < 1 || dim > MAXD) return fail_arg(2, "dim");
+  if (!Xs) return fail_arg(3, "Xs null");
+  if (!tile_ok(m)) return fail_arg(4, "m must be a positive multiple of 128");
+  if (n < 0 || n % TILE) return fail_arg(8, "n must be a multiple of 128");
+  if (n > 0 && !V) return fail_arg(7, "V null");
+  if (n > 0 && (ldv < m || (ldv & 1))) return fail_arg(9, "ldv");
+  if (!theta) return fail_arg(11, "theta null");
+  if (!Sigma) return fail_arg(13, "Sigma null");
+  if (lds < m || (lds & 1)) return fail_arg(14, "lds");
+  if (batch <= 0) return fail_arg(17, "batch");
+  const int nt = m / TILE;
+  CovParams p{};
+  p.Xa = Xs; p.sXa = s_xs; p.ma = m; p.mav = mv;
+  p.Xb = Xs; p.sXb = s_xs; p.mb = m; p.mbv = mv;
+  p.V1 = V; p.ldv1 = ldv; p.sV1 = s_v;
+  p.V2 = V; p.ldv2 = ldv; p.sV2 = s_v;
+  p.theta = theta; p.sTheta = s_theta;
+  p.C = Sigma; p.ldc = lds; p.sC = s_sigma;
+  p.ntc = nt; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 1; p.tri = lower_only ? 1 : 0;
+  CK(launch_postcov(p, lower_only ? nt * (nt + 1) / 2 : nt * nt, batch, (cudaStream_t)stream),
+     "ocbo_post_cov");
+  return 0;
+}
+
+int ocbo_post_cross_cov(int kind, int dim, const double* Xa, int ma, int64_t s_xa,
+                        const int32_t* mav, const double* Xb, int mb, int64_t s_xb,
+                        const int32_t* mbv, const double* V1, int ldv1, int64_t s_v1,
+                        const double* V2, int ldv2, int64_t s_v2, int n, const double* theta,
+                        int64_t s_theta, double* C, int ldc, int64_t s_c, int batch,
+                        ocbo_stream_t stream) {
+  if (kind < 0 || kind > 3) return fail_arg(1, "kernel kind");
+  if (dim < 1 || dim > MAXD) return fail_arg(2, "dim");
+  if (!Xa || !Xb) return fail_arg(3, "Xa/Xb null");
+  if (!tile_ok(ma)) return fail_arg(4, "ma must be a positive multiple of 128");
+  if (!tile_ok(mb)) return fail_arg(8, "mb must be a positive multiple of 128");
+  if (n < 0 || n % TILE) return fail_arg(17, "n must be a multiple of 128");
+  if (n > 0 && (!V1 || !V2)) return fail_arg(11, "V1/V2 null");
+  if (!theta) return fail_arg(18, "theta null");
+  if (!C) return fail_arg(20, "C null");
+  if (ldc < mb || (ldc & 1)) return fail_arg(21, "ldc");
+  if (batch <= 0) return fail_arg(23, "batch");
+  CovParams p{};
+  p.Xa = Xa; p.sXa = s_xa; p.ma = ma; p.mav = mav;
+  p.Xb = Xb; p.sXb = s_xb; p.mb = mb; p.mbv = mbv;
+  p.V1 = V1; p.ldv1 = ldv1; p.sV1 = s_v1;
+  p.V2 = V2; p.ldv2 = ldv2; p.sV2 = s_v2;
+  p.theta = theta; p.sTheta = s_theta;
+  p.C = C; p.ldc = ldc; p.sC = s_c;
+  p.ntc = mb / TILE; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 0; p.tri = 0;
+  CK(launch_postcov(p, (ma / TILE) * (mb / TILE), batch, (cudaStream_t)stream),
+     "ocbo_post_cross_cov");
+  return 0;
+}
+
+int ocbo_symmetrize_lower(double* A, int n, int lda, int64_t s_a, int batch,
+                          ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (n <= 0 || n % 32) return fail_arg(2, "n must be a positive multiple of 32");
+  if (batch <= 0) return fail_arg(5, "batch");
+  CK(launch_symmetrize(A, n, lda, s_a, batch, (cudaStream_t)stream), "ocbo_symmetrize_lower");
+  return 0;
+}
+
+int ocbo_philox_normal(double* Z, int m, int S, int ldz, int64_t s_z, uint64_t seed,
+                       const int32_t* trial_ids, int batch, ocbo_stream_t stream) {
+  if (!Z) return fail_arg(1, "Z null");
+  if (m <= 0) return fail_arg(2, "m");
+  if (S <= 0) return fail_arg(3, "S");
+  if (ldz < S) return fail_arg(4, "ldz");
+  if (batch <= 0) return fail_arg(8, "batch");
+  CK(launch_philox_normal(Z, m, S, ldz, s_z, seed, trial_ids, batch, (cudaStream_t)stream),
+     "ocbo_philox_normal");
+  return 0;
+}
+
+int ocbo_sample(const double* mean, int64_t s_mean, const double* L, int m, int ldl, int64_t s_l,
+                const double* Z, int S, int ldz, int64_t s_z, double* F, int ldf, int64_t s_f,
+                const int32_t* info, int batch, ocbo_stream_t stream) {
+  if (!mean) return fail_arg(1, "mean null");
+  if (!L) return fail_arg(3, "L null");
+  if (m <= 0) return fail_arg(4, "m");
+  if (!Z) return fail_arg(7, "Z null");
+  if (S <= 0) return fail_arg(8, "S");
+  if (!F) return fail_arg(11, "F null");
+  if (batch <= 0) return fail_arg(15, "batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S <= 8) {
+    CK(launch_sample_rowdot(mean, s_mean, L, m, ldl, s_l, Z, S, ldz, s_z, F, ldf, s_f, info, batch,
+                            st),
+       "ocbo_sample rowdot");
+    return 0;
+  }
+  if (!tile_ok(m)) return fail_arg(4, "m must be a multiple of 128 on the DMMA path");
+  if (S % TILE) return fail_arg(8, "S must be <= 8 or a multiple of 128");
+  if ((ldz & 1) || (ldf & 1) || (ldl & 1)) return fail_arg(9, "leading dimensions must be even");
+  NnParams p{};
+  p.P = L; p.ldp = ldl; p.sP = s_l;
+  p.R = Z; p.ldr = ldz; p.sR = s_z;
+  p.C = F; p.ldc = ldf; p.sC = s_f;
+  p.rowvec = mean; p.sRowvec = s_mean;
+  p.ktiles = m / BK; p.tri_k = 1; p.reverse_rows = 1; p.mode = 2; p.info = info;
+  CK(launch_gemm_nn(p, m / TILE, S / TILE, batch, st), "ocbo_sample dmma");
+  return 0;
+}
+
+int ocbo_segment_argmax(const double* F, int S, int ldf, int64_t s_f, const int32_t* seg_ptr,
+                        int nseg, double* out_max, int32_t* out_arg, int batch,
+                        ocbo_stream_t stream) {
+  if (!F) return fail_arg(1, "F null");
+  if (S <= 0) return fail_arg(2, "S");
+  if (!seg_ptr) return fail_arg(5, "seg_ptr null");
+  if (nseg <= 0) return fail_arg(6, "nseg");
+  if (!out_max || !out_arg) return fail_arg(7, "outputs null");
+  if (batch <= 0) return fail_arg(9, "batch");
+  CK(launch_segment_argmax(F, S, ldf, s_f, seg_ptr, nseg, out_max, out_arg, batch,
+                           (cudaStream_t)stream),
+     "ocbo_segment_argmax");
+  return 0;
+}
+
+int ocbo_joint_pick(const double* seg_max, const int32_t* seg_arg, int nseg, int n_old_seg, int T,
+                    int S, int32_t* out_task, int32_t* out_action, double* out_gain, int batch,
+                    ocbo_stream_t stream) {
+  if (!seg_max || !seg_arg) return fail_arg(1, "inputs null");
+  if (T <= 0 || n_old_seg + T > nseg) return fail_arg(5, "T / n_old_seg inconsistent with nseg");
+  if (n_old_seg != 0 && n_old_seg != T) return fail_arg(4, "n_old_seg must be 0 or T");
+  if (S <= 0) return fail_arg(6, "S");
+  if (!out_task || !out_action || !out_gain) return fail_arg(7, "outputs null");
+  if (batch <= 0) return fail_arg(10, "batch");
+  CK(launch_joint_pick(seg_max, seg_arg, nseg, n_old_seg, T, S, out_task, out_action, out_gain,
+                       batch, (cudaStream_t)stream),
+     "ocbo_joint_pick");
+  return 0;
+}
+
+int ocbo_probe_dmma(double* sink, int blocks, int iters, ocbo_stream_t stream) {
+  if (!sink) return fail_arg(1, "sink null");
+  CK(launch_probe_dmma(sink, blocks, iters, (cudaStream_t)stream), "ocbo_probe_dmma");
+  return 0;
+}
+int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream) {
+  if (!sink) return fail_arg(1, "sink null");
+  CK(launch_probe_dfma(sink, blocks, iters, (cudaStream_t)stream), "ocbo_probe_dfma");
+  return 0;
+}
+int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n, ocbo_stream_t stream) {
+  if (!A || !B || !C) return fail_arg(1, "null");
+  if (!tile_ok(n)) return fail_arg(4, "n must be a multiple of 128");
+  NtParams p{};
+  p.P = A; p.ldp = n; p.sP = 0;
+  p.Q = B; p.ldq = n; p.sQ = 0;
+  p.C = C; p.ldc = n; p.sC = 0;
+  p.ntc = n / TILE; p.ktiles = n / BK; p.tri = 0; p.lower_skip = 0; p.mode = 0; p.info = nullptr;
+  CK(launch_gemm_nt(p, (n / TILE) * (n / TILE), 1, (cudaStream_t)stream), "ocbo_probe_dgemm_nt");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Internal launch interface between the kernel translation units and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ocbo {
+
+struct NtParams {  // C (=|-=) P Q^T ; all pointers pre-offset to the region origin
+  const double* P; int ldp; int64_t sP;
+  const double* Q; int ldq; int64_t sQ;
+  double* C; int ldc; int64_t sC;
+  int ntc;         // column tiles of a rectangular region
+  int ktiles;      // k extent / 16
+  int row0, col0;  // global element coordinates of the region origin (diagonal test)
+  int tri;         // grid.x enumerates the lower-triangular tiles of a square region
+  int lower_skip;  // rectangular region: skip tiles entirely above the diagonal
+  int mode;        // 0: C = acc, 1: C -= acc
+  const int32_t* info;
+};
+
+struct NnParams {  // C (=|-=|= rowvec +) P R
+  const double* P; int ldp; int64_t sP;
+  const double* R; int ldr; int64_t sR;
+  double* C; int ldc; int64_t sC;
+  const double* rowvec; int64_t sRowvec;
+  int ktiles;
+  int tri_k;         // k stops at the diagonal block of the row tile (L lower)
+  int reverse_rows;  // heavy row tiles first
+  int mode;          // 0 set, 1 sub, 2 rowvec + acc
+  const int32_t* info;
+};
+
+struct CovParams {  // C = K(Xa, Xb) - V1^T V2
+  const double* Xa; int64_t sXa; int ma; const int32_t* mav;
+  const double* Xb; int64_t sXb; int mb; const int32_t* mbv;
+  const double* V1; int ldv1; int64_t sV1;
+  const double* V2; int ldv2; int64_t sV2;
+  const double* theta; int64_t sTheta;
+  double* C; int ldc; int64_t sC;
+  int ntc, ktiles, dim, kind, sym, tri;
+};
+
+cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st);
+cudaError_t launch_gemm_nn(const NnParams& p, int ntr, int ntc, int batch, cudaStream_t st);
+cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st);
+
+cudaError_t launch_gram(int kind, int dim, const double* X1, int n1, int64_t sX1, const int32_t* nv1,
+                        const double* X2, int n2, int64_t sX2, const int32_t* nv2,
+                        const double* theta, int64_t sTheta, double* K, int ldk, int64_t sK,
+                        int batch, int flags, cudaStream_t st);
+cudaError_t launch_add_diag(double* A, int n, int lda, int64_t sA, const int32_t* nv,
+                            const double* val, int batch, cudaStream_t st);
+cudaError_t launch_diag_max(const double* A, int n, int lda, int64_t sA, const int32_t* nv,
+                            double* out, int batch, cudaStream_t st);
+cudaError_t launch_symmetrize(double* A, int n, int lda, int64_t sA, int batch, cudaStream_t st);
+
+// factor the 128x128 diagonal block at (j0, j0) of every problem, write inv(L_jj)
+cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
+                              int64_t sInv, int32_t* info, int batch, cudaStream_t st);
+cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,
+                                   const double* invdiag, int64_t sInv, const double* y, int64_t sY,
+                                   const int32_t* nv, const double* theta, int64_t sTheta,
+                                   double* alpha, int64_t sAlpha, double* lml,
+                                   const int32_t* info, int batch, cudaStream_t st);
+cudaError_t launch_post_mean(int kind, int dim, const double* Xs, int m, int64_t sXs,
+                             const int32_t* mv, const double* X, int n, int64_t sX,
+                             const int32_t* nv, const double* theta, int64_t sTheta,
+                             const double* alpha, int64_t sAlpha, double* mean, int64_t sMean,
+                             int batch, cudaStream_t st);
+
+cudaError_t launch_philox_normal(double* Z, int m, int S, int ldz, int64_t sZ, uint64_t seed,
+                                 const int32_t* trial_ids, int batch, cudaStream_t st);
+cudaError_t launch_sample_rowdot(const double* mean, int64_t sMean, const double* L, int m, int ldl,
+                                 int64_t sL, const double* Z, int S, int ldz, int64_t sZ,
+                                 double* F, int ldf, int64_t sF, const int32_t* info, int batch,
+                                 cudaStream_t st);
+cudaError_t launch_segment_argmax(const double* F, int S, int ldf, int64_t sF,
+                                  const int32_t* seg_ptr, int nseg, double* out_max,
+                                  int32_t* out_arg, int batch, cudaStream_t st);
+cudaError_t launch_joint_pick(const double* seg_max, const int32_t* seg_arg, int nseg,
+                              int n_old_seg, int T, int S, int32_t* out_task, int32_t* out_action,
+                              double* out_gain, int batch, cudaStream_t st);
+cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st);
+
+}  // namespace ocbo

@@ -1,0 +1,307 @@
+"""Host-side engine: padded, batched GP posteriors on one B200.
+
+PyTorch is plumbing only (device memory, streams, pinned staging); every
+floating-point operation of the path runs in ``libocbo_b200.so``.  There is no
+CPU fallback: constructing anything here without CUDA raises.
+
+Layout in HBM (all fp64, row-major, one slab per batched quantity):
+  X      [B, n_pad, D]        training inputs, rows >= nv[b] are padding
+  y      [B, n_pad]
+  theta  [B, 3 + D]           scale, noise_var, mu0, bandwidths
+  L      [B, n_pad, n_pad]    lower Cholesky factor of K + noise I (+ jitter)
+  invd   [B, n_pad/128, 128, 128]  inverted diagonal blocks of L
+  alpha  [B, n_pad]
+with n_pad a multiple of 128.  Padding is exact (see include/ocbo_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TILE, call
+
+F64 = torch.float64
+I32 = torch.int32
+
+KIND_OF = {'se': _lib.KERNEL_SE, 'default': _lib.KERNEL_SE,
+           ('matern', 0.5): _lib.KERNEL_MATERN12, ('matern', 1.5): _lib.KERNEL_MATERN32,
+           ('matern', 2.5): _lib.KERNEL_MATERN52}
+
+
+def kernel_kind(kernel_type, matern_nu=2.5):
+    kt = str(kernel_type).lower()
+    if kt in ('se', 'default'):
+        return _lib.KERNEL_SE
+    if kt == 'matern':
+        try:
+            return KIND_OF[('matern', float(matern_nu))]
+        except KeyError:
+            raise ValueError('Matern nu must be 0.5, 1.5 or 2.5.')
+    raise ValueError('Unknown kernel_type %s' % kernel_type)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('ocbo_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.')
+
+
+def device():
+    require_cuda()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def pad_to(n, mult=TILE):
+    return max(mult, ((int(n) + mult - 1) // mult) * mult)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _h2d(arr, dtype=F64):
+    """Host ndarray -> device tensor through a pinned staging buffer."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.pin_memory().to(device(), non_blocking=True)
+
+
+LAUNCHES = [0]  # kernels launched by this process (bench.py reports it)
+
+
+def _count(k):
+    LAUNCHES[0] += k
+
+
+# ---------------------------------------------------------------------------
+# thin wrappers over the C ABI on torch tensors
+# ---------------------------------------------------------------------------
+def gram(kind, X1, nv1, X2, nv2, theta, out, flags):
+    """out[b] = K(X1[b], X2[b]); X: [B, n_pad, D]; out: [B, n1_pad, ld]."""
+    B, n1, D = X1.shape
+    n2 = X2.shape[1]
+    call('ocbo_gram', kind, D, _p(X1), n1, X1.stride(0), _p(nv1), _p(X2), n2, X2.stride(0), _p(nv2),
+         _p(theta), theta.stride(0), _p(out), out.stride(1), out.stride(0), B, flags, _stream())
+    _count(1)
+
+
+def potrf(A, invd, info):
+    B, n, _ = A.shape
+    call('ocbo_potrf', _p(A), n, A.stride(1), A.stride(0), _p(invd), _p(info), B, _stream())
+    _count(3 * (n // TILE) - 2)
+
+
+def trsm_lower(L, invd, Bm, info):
+    B, n, _ = L.shape
+    call('ocbo_trsm_lower', _p(L), n, L.stride(1), L.stride(0), _p(invd), _p(Bm), Bm.shape[2],
+         Bm.stride(1), Bm.stride(0), _p(info), B, _stream())
+    _count(2 * (n // TILE) - 1)
+
+
+def chol_with_ladder(assemble, A, invd, info, nv_dev, nv_host):
+    """Dragonfly's stable_cholesky on a batch: factor once;
+    every problem whose plain factorisation fails is re-assembled and retried
+    alone with jitter 10^p * max(diag) for p = -11 .. 4, then ValueError.
+    ``assemble(b0, b1)`` must (re)write A[b0:b1].  Returns the jitter exponent
+    used per problem (None = none needed)."""
+    B = A.shape[0]
+    info.zero_()
+    potrf(A, invd, info)
+    status = info.cpu().numpy()
+    jit = [None] * B
+    if not status.any():
+        return jit
+    dmax = torch.empty(1, dtype=F64, device=A.device)
+    val = torch.empty(1, dtype=F64, device=A.device)
+    for b in np.nonzero(status)[0]:
+        b = int(b)
+        Ab, ib, inf_b = A[b:b + 1], invd[b:b + 1], info[b:b + 1]
+        nvb = nv_dev[b:b + 1] if nv_dev is not None else None
+        n = A.shape[1]
+        done = False
+        for p in range(-11, 5):
+            assemble(b, b + 1)
+            call('ocbo_diag_max', _p(Ab), n, Ab.stride(1), Ab.stride(0), _p(nvb), _p(dmax), 1, _stream())
+            val.copy_(dmax * (10.0 ** p))
+            call('ocbo_add_diag', _p(Ab), n, Ab.stride(1), Ab.stride(0), _p(nvb), _p(val), 1, _stream())
+            _count(2)
+            inf_b.zero_()
+            potrf(Ab, ib, inf_b)
+            if int(inf_b.item()) == 0:
+                jit[b] = p
+                done = True
+                break
+        if not done:
+            raise ValueError('stable_cholesky: matrix could not be made PD.')
+    return jit
+
+
+class DevicePosterior(object):
+    """B independent GP posteriors, padded to a common n_pad, resident in HBM."""
+
+    def __init__(self, X_list, y_list, thetas, kind, dim):
+        require_cuda()
+        self.B = len(X_list)
+        self.D = int(dim)
+        self.kind = int(kind)
+        if self.D < 1 or self.D > _lib.MAX_DIM:
+            raise ValueError('input dimension must be in [1, %d]' % _lib.MAX_DIM)
+        self.nv_host = [len(y) for y in y_list]
+        self.n_pad = pad_to(max(self.nv_host + [1]))
+        B, n_pad, D = self.B, self.n_pad, self.D
+        Xh = np.zeros((B, n_pad, D))
+        yh = np.zeros((B, n_pad))
+        for b in range(B):
+            nb = self.nv_host[b]
+            if nb:
+                Xh[b, :nb] = np.asarray(X_list[b], dtype=np.float64).reshape(nb, D)
+                yh[b, :nb] = np.asarray(y_list[b], dtype=np.float64).ravel()
+        self.X = _h2d(Xh)
+        self.y = _h2d(yh)
+        self.theta_host = np.asarray(thetas, dtype=np.float64).reshape(B, 3 + D)
+        self.theta = _h2d(self.theta_host)
+        self.nv = _h2d(np.asarray(self.nv_host, dtype=np.int32), I32)
+        dev = self.X.device
+        self.L = torch.empty((B, n_pad, n_pad), dtype=F64, device=dev)
+        self.invd = torch.empty((B, n_pad // TILE, TILE, TILE), dtype=F64, device=dev)
+        self.alpha = torch.empty((B, n_pad), dtype=F64, device=dev)
+        self.lml = torch.empty((B,), dtype=F64, device=dev)
+        self.info = torch.zeros((B,), dtype=I32, device=dev)
+        self.jitter = [None] * B
+        self.built = False
+
+    # -- build_posterior: K + noise I -> L -> alpha, LML  (gp_interface.py:85-88) --
+    def _assemble_K(self, b0, b1):
+        gram(self.kind, self.X[b0:b1], self.nv[b0:b1], self.X[b0:b1], self.nv[b0:b1],
+             self.theta[b0:b1], self.L[b0:b1],
+             _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE)
+
+    def build(self):
+        self._assemble_K(0, self.B)
+        self.jitter = chol_with_ladder(self._assemble_K, self.L, self.invd, self.info, self.nv,
+                                       self.nv_host)
+        call('ocbo_solve_alpha_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
+             _p(self.invd), _p(self.y), self.y.stride(0), _p(self.nv), _p(self.theta),
+             self.theta.stride(0), _p(self.alpha), self.alpha.stride(0), _p(self.lml), _p(self.info),
+             self.B, _stream())
+        _count(1)
+        self.built = True
+        return self
+
+    # -- candidates -------------------------------------------------------------
+    def upload_points(self, pts_list):
+        mv = [len(p) for p in pts_list]
+        m_pad = pad_to(max(mv + [1]))
+        Ph = np.zeros((self.B, m_pad, self.D))
+        for b, p in enumerate(pts_list):
+            if mv[b]:
+                Ph[b, :mv[b]] = np.asarray(p, dtype=np.float64).reshape(mv[b], self.D)
+        return _h2d(Ph), _h2d(np.asarray(mv, dtype=np.int32), I32), mv, m_pad
+
+    def mean(self, Xs, mv_dev):
+        B, m_pad, _ = Xs.shape
+        out = torch.empty((B, m_pad), dtype=F64, device=Xs.device)
+        call('ocbo_post_mean', self.kind, self.D, _p(Xs), m_pad, Xs.stride(0), _p(mv_dev), _p(self.X),
+             self.n_pad, self.X.stride(0), _p(self.nv), _p(self.theta), self.theta.stride(0),
+             _p(self.alpha), self.alpha.stride(0), _p(out), out.stride(0), B, _stream())
+        _count(1)
+        return out
+
+    def solve_cross(self, Xs, mv_dev):
+        """V = L^{-1} K(X, Xs)  [B, n_pad, m_pad]."""
+        B, m_pad, _ = Xs.shape
+        V = torch.empty((B, self.n_pad, m_pad), dtype=F64, device=Xs.device)
+        gram(self.kind, self.X, self.nv, Xs, mv_dev, self.theta, V, 0)
+        trsm_lower(self.L, self.invd, V, self.info)
+        return V
+
+    def cov(self, Xs, mv_dev, V, lower_only, out=None, b0=0, b1=None):
+        b1 = self.B if b1 is None else b1
+        Bn, m_pad = b1 - b0, Xs.shape[1]
+        if out is None:
+            out = torch.empty((self.B, m_pad, m_pad), dtype=F64, device=Xs.device)
+        o, Xv, Vv, mvv, th = out[b0:b1], Xs[b0:b1], V[b0:b1], mv_dev[b0:b1], self.theta[b0:b1]
+        call('ocbo_post_cov', self.kind, self.D, _p(Xv), m_pad, Xv.stride(0), _p(mvv), _p(Vv),
+             self.n_pad, Vv.stride(1), Vv.stride(0), _p(th), th.stride(0), _p(o), o.stride(1),
+             o.stride(0), 1 if lower_only else 0, Bn, _stream())
+        _count(1)
+        return out
+
+    def cross_cov(self, Xa, mav, Va, Xb, mbv, Vb):
+        B, ma, mb = self.B, Xa.shape[1], Xb.shape[1]
+        out = torch.empty((B, ma, mb), dtype=F64, device=Xa.device)
+        call('ocbo_post_cross_cov', self.kind, self.D, _p(Xa), ma, Xa.stride(0), _p(mav), _p(Xb), mb,
+             Xb.stride(0), _p(mbv), _p(Va), Va.stride(1), Va.stride(0), _p(Vb), Vb.stride(1),
+             Vb.stride(0), self.n_pad, _p(self.theta), self.theta.stride(0), _p(out), out.stride(1),
+             out.stride(0), B, _stream())
+        _count(1)
+        return out
+
+
+def factor_covariance(post_or_none, Sigma, mv_dev, mv_host, reassemble):
+    """stable_cholesky of a batch of (padded) covariance matrices, in place."""
+    B, m_pad, _ = Sigma.shape
+    invd = torch.empty((B, m_pad // TILE, TILE, TILE), dtype=F64, device=Sigma.device)
+    info = torch.zeros((B,), dtype=I32, device=Sigma.device)
+    jit = chol_with_ladder(reassemble, Sigma, invd, info, mv_dev, mv_host)
+    return invd, info, jit
+
+
+def sample_from_factor(mean, Lsig, Z, info=None):
+    """F = mean + L Z  -> [B, m_pad, S_pad] (mean [B, m_pad], Z [B, m_pad, S_pad])."""
+    B, m_pad, _ = Lsig.shape
+    S = Z.shape[2]
+    Fm = torch.empty((B, m_pad, S), dtype=F64, device=Lsig.device)
+    call('ocbo_sample', _p(mean), mean.stride(0), _p(Lsig), m_pad, Lsig.stride(1), Lsig.stride(0),
+         _p(Z), S, Z.stride(1), Z.stride(0), _p(Fm), Fm.stride(1), Fm.stride(0), _p(info), B, _stream())
+    _count(1)
+    return Fm
+
+
+def philox_normals(B, m_pad, S, seed, trial_ids, dev):
+    Z = torch.empty((B, m_pad, S), dtype=F64, device=dev)
+    tid = _h2d(np.asarray(trial_ids, dtype=np.int32), I32)
+    call('ocbo_philox_normal', _p(Z), m_pad, S, Z.stride(1), Z.stride(0),
+         ctypes.c_uint64(int(seed)), _p(tid), B, _stream())
+    _count(1)
+    return Z
+
+
+def segment_argmax(Fm, S, seg_ptr_host):
+    """seg_ptr_host: int array [B, nseg + 1] -> (max [B, nseg, S], arg [B, nseg, S])."""
+    seg = np.asarray(seg_ptr_host, dtype=np.int32)
+    B, nseg = seg.shape[0], seg.shape[1] - 1
+    seg_d = _h2d(seg, I32)
+    mx = torch.empty((B, nseg, S), dtype=F64, device=Fm.device)
+    ag = torch.empty((B, nseg, S), dtype=I32, device=Fm.device)
+    call('ocbo_segment_argmax', _p(Fm), S, Fm.stride(1), Fm.stride(0), _p(seg_d), nseg, _p(mx),
+         _p(ag), B, _stream())
+    _count(1)
+    return mx, ag
+
+
+def joint_pick(mx, ag, n_old_seg, T):
+    B, nseg, S = mx.shape
+    task = torch.empty((B, S), dtype=I32, device=mx.device)
+    act = torch.empty((B, S), dtype=I32, device=mx.device)
+    gain = torch.empty((B, S), dtype=F64, device=mx.device)
+    call('ocbo_joint_pick', _p(mx), _p(ag), nseg, n_old_seg, T, S, _p(task), _p(act), _p(gain), B,
+         _stream())
+    _count(1)
+    return task, act, gain
+
+
+def pad_normals(Z_list, mv, m_pad, S):
+    """Host normals [(m_b, S)] -> device [B, m_pad, S_pad] (zero padded)."""
+    S_pad = S if S <= 8 else pad_to(S)
+    Zh = np.zeros((len(Z_list), m_pad, S_pad))
+    for b, z in enumerate(Z_list):
+        Zh[b, :mv[b], :S] = np.asarray(z, dtype=np.float64).reshape(mv[b], S)
+    return _h2d(Zh)

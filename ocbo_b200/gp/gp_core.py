@@ -1,0 +1,234 @@
+"""B200 GP core: the object the reference reaches as ``gp_core``.
+
+Plays the role Dragonfly's ``EuclideanGP`` plays for the reference
+(/root/reference/src/gp/gp_interface.py:67-119, src/gp/gp_util.py:66-70): same
+constructor signature, same attributes (``X, Y, kernel, mean_func, noise_var,
+L, alpha``) and methods (``eval, draw_samples, add_data_single,
+build_posterior``), but every number is computed by ``libocbo_b200.so`` on the
+GPU.  Semantics follow SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib, engine, rng
+from ..engine import DevicePosterior, F64, TILE
+
+
+class _Kernel(object):
+    """scale * phi(||(x - x') / dim_bandwidths||); callable like Dragonfly's
+    kernel objects (gp_interface.py:113-117) with ``hyperparams`` (:107-110)."""
+    kernel_type = None
+
+    def __init__(self, dim, scale, dim_bandwidths):
+        self.dim = int(dim)
+        bws = np.asarray(dim_bandwidths, dtype=np.float64).ravel()
+        if bws.size == 1 and self.dim > 1:
+            bws = np.repeat(bws, self.dim)
+        if bws.size != self.dim:
+            raise ValueError('dim_bandwidths must have %d entries' % self.dim)
+        self.hyperparams = {'scale': float(scale), 'dim_bandwidths': bws}
+
+    @property
+    def kind(self):
+        raise NotImplementedError
+
+    def theta(self, noise_var=0.0, mu0=0.0):
+        return np.concatenate([[self.hyperparams['scale'], noise_var, mu0],
+                               self.hyperparams['dim_bandwidths']])
+
+    def __call__(self, X1, X2=None):
+        """Prior Gram matrix, evaluated on the GPU (ocbo_gram)."""
+        X1 = np.asarray(X1, dtype=np.float64).reshape(-1, self.dim)
+        X2 = X1 if X2 is None else np.asarray(X2, dtype=np.float64).reshape(-1, self.dim)
+        n1, n2 = len(X1), len(X2)
+        if n1 == 0 or n2 == 0:
+            return np.zeros((n1, n2))
+        p1, p2 = engine.pad_to(n1), engine.pad_to(n2)
+        A = np.zeros((1, p1, self.dim))
+        B = np.zeros((1, p2, self.dim))
+        A[0, :n1], B[0, :n2] = X1, X2
+        Ad, Bd = engine._h2d(A), engine._h2d(B)
+        th = engine._h2d(self.theta()[None, :])
+        out = torch.empty((1, p1, p2), dtype=F64, device=Ad.device)
+        nv1 = engine._h2d(np.asarray([n1], dtype=np.int32), engine.I32)
+        nv2 = engine._h2d(np.asarray([n2], dtype=np.int32), engine.I32)
+        engine.gram(self.kind, Ad, nv1, Bd, nv2, th, out, 0)
+        return out[0, :n1, :n2].cpu().numpy()
+
+
+class SEKernel(_Kernel):
+    kernel_type = 'se'
+
+    @property
+    def kind(self):
+        return _lib.KERNEL_SE
+
+
+class MaternKernel(_Kernel):
+    kernel_type = 'matern'
+
+    def __init__(self, dim, nu, scale, dim_bandwidths):
+        super(MaternKernel, self).__init__(dim, scale, dim_bandwidths)
+        self.nu = float(nu)
+        self.hyperparams['nu'] = self.nu
+        engine.kernel_kind('matern', self.nu)  # validates nu
+
+    @property
+    def kind(self):
+        return engine.kernel_kind('matern', self.nu)
+
+
+def make_kernel(kernel_type, dim, scale, dim_bandwidths, matern_nu=2.5):
+    kt = str(kernel_type).lower()
+    if kt in ('se', 'default'):
+        return SEKernel(dim, scale, dim_bandwidths)
+    if kt == 'matern':
+        return MaternKernel(dim, matern_nu, scale, dim_bandwidths)
+    raise ValueError('Unknown kernel_type %s' % kernel_type)
+
+
+class ConstMean(object):
+    def __init__(self, value):
+        self.value = float(value)
+
+    def __call__(self, X):
+        return np.full((len(X),), self.value, dtype=np.float64)
+
+
+class B200GPCore(object):
+    """One GP resident on the GPU (a DevicePosterior with batch 1)."""
+
+    def __init__(self, X, Y, kernel, mean_func, noise_var, build_posterior=True):
+        self.kernel = kernel
+        self.mean_func = mean_func
+        self.noise_var = float(noise_var)
+        self.dim = kernel.dim
+        self.X = [np.asarray(x, dtype=np.float64).ravel() for x in X]
+        self.Y = [float(y) for y in Y]
+        self._post = None
+        self.chol_jitter = None
+        if build_posterior:
+            self.build_posterior()
+
+    # -- attributes the reference reads -------------------------------------
+    @property
+    def num_tr_data(self):
+        return len(self.Y)
+
+    @property
+    def alpha(self):
+        if self._post is None:
+            return None
+        return self._post.alpha[0, :self.num_tr_data].cpu().numpy()
+
+    @property
+    def L(self):
+        if self._post is None:
+            return None
+        n = self.num_tr_data
+        return np.tril(self._post.L[0, :n, :n].cpu().numpy())
+
+    def _mu0(self):
+        return float(self.mean_func(np.zeros((1, self.dim)))[0])
+
+    def theta(self):
+        return self.kernel.theta(self.noise_var, self._mu0())
+
+    def __deepcopy__(self, memo):
+        # device state is rebuilt lazily (pre-tuned empty GPs are deep-copied:
+        # src/strategies/multi_opt.py:180-181)
+        from copy import deepcopy
+        new = B200GPCore([x.copy() for x in self.X], list(self.Y), deepcopy(self.kernel, memo),
+                         deepcopy(self.mean_func, memo), self.noise_var, build_posterior=False)
+        return new
+
+    # -- build_posterior / add_data_single (gp_interface.py:81-88) -----------
+    def build_posterior(self):
+        post = DevicePosterior([np.asarray(self.X).reshape(-1, self.dim)], [self.Y],
+                               self.theta()[None, :], self.kernel.kind, self.dim)
+        post.build()
+        self._post = post
+        self.chol_jitter = post.jitter[0]
+
+    def add_data_single(self, x, y):
+        self.X.append(np.asarray(x, dtype=np.float64).ravel())
+        self.Y.append(float(y))
+        self.build_posterior()
+
+    def compute_log_marginal_likelihood(self):
+        if self._post is None:
+            self.build_posterior()
+        return float(self._post.lml[0].item())
+
+    # -- eval (gp_interface.py:69-74) ----------------------------------------
+    def _posterior_at(self, X_test, want_cov, lower_only):
+        if self._post is None:
+            self.build_posterior()
+        post = self._post
+        Xs = np.asarray(X_test, dtype=np.float64).reshape(-1, self.dim)
+        Xd, mv_dev, mv, m_pad = post.upload_points([Xs])
+        mean = post.mean(Xd, mv_dev)
+        if not want_cov:
+            return Xd, mv_dev, mv, mean, None, None
+        V = post.solve_cross(Xd, mv_dev)
+        Sigma = post.cov(Xd, mv_dev, V, lower_only)
+        return Xd, mv_dev, mv, mean, V, Sigma
+
+    def eval(self, X_test, uncert_form='none'):
+        if uncert_form not in ('none', 'std', 'covar'):
+            raise ValueError('uncert_form must be none, std or covar.')
+        _, _, mv, mean, _, Sigma = self._posterior_at(X_test, uncert_form != 'none', False)
+        m = mv[0]
+        mu = mean[0, :m].cpu().numpy()
+        if uncert_form == 'none':
+            return mu, None
+        cov = Sigma[0, :m, :m].cpu().numpy()
+        if uncert_form == 'covar':
+            return mu, cov
+        return mu, np.sqrt(np.diag(cov))
+
+    # -- draw_samples (gp_interface.py:76-79) ---------------------------------
+    def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None):
+        """(S, m) joint samples: mu + L_Sigma z with Dragonfly's jitter ladder."""
+        S = int(num_samples)
+        if X_test is not None:
+            Xd, mv_dev, mv, mean, V, Sigma = self._posterior_at(X_test, True, True)
+            post = self._post
+
+            def reassemble(b0, b1):
+                post.cov(Xd, mv_dev, V, True, out=Sigma, b0=b0, b1=b1)
+        else:
+            mean_h = np.asarray(mean_vals, dtype=np.float64).ravel()
+            cov_h = np.asarray(covar, dtype=np.float64)
+            m = len(mean_h)
+            m_pad = engine.pad_to(m)
+            Sh = np.eye(m_pad)[None, :, :].copy()
+            Sh[0, :m, :m] = cov_h
+            Mh = np.zeros((1, m_pad))
+            Mh[0, :m] = mean_h
+            Sigma, mean = engine._h2d(Sh), engine._h2d(Mh)
+            mv = [m]
+            mv_dev = engine._h2d(np.asarray(mv, dtype=np.int32), engine.I32)
+            pinned = torch.from_numpy(Sh).pin_memory()
+
+            def reassemble(b0, b1):
+                Sigma.copy_(pinned, non_blocking=True)
+        m, m_pad = mv[0], Sigma.shape[1]
+        _, info, jit = engine.factor_covariance(None, Sigma, mv_dev, mv, reassemble)
+        self.last_sample_jitter = jit[0]
+        Z = engine.pad_normals([rng.normals((m, S))], mv, m_pad, S)
+        Fm = engine.sample_from_factor(mean, Sigma, Z, info)
+        return Fm[0, :m, :S].t().contiguous().cpu().numpy()
+
+    # -- get_pt_relations (gp_interface.py:112-119) ---------------------------
+    def cross_covariance(self, pts1, pts2):
+        if self._post is None:
+            self.build_posterior()
+        post = self._post
+        Xa, mav, ma, _ = post.upload_points([np.asarray(pts1, dtype=np.float64).reshape(-1, self.dim)])
+        Xb, mbv, mb, _ = post.upload_points([np.asarray(pts2, dtype=np.float64).reshape(-1, self.dim)])
+        Va, Vb = post.solve_cross(Xa, mav), post.solve_cross(Xb, mbv)
+        C = post.cross_cov(Xa, mav, Va, Xb, mbv, Vb)
+        return C[0, :ma[0], :mb[0]].cpu().numpy()

@@ -1,0 +1,160 @@
+"""GP model interface of the reference, B200 engine behind it.
+
+Mirrors /root/reference/src/gp/gp_interface.py: the abstract ``GPWrapper`` /
+``GPFitterWrapper`` (:9-65) are kept name for name so strategy code written
+against the reference runs unchanged; ``B200GP`` / ``B200GPFitter`` take the
+place of ``DragonflyGP`` / ``DragonflyGPFitter`` (:67-138).
+"""
+from copy import deepcopy
+
+import numpy as np
+
+from . import hp_search
+from .gp_core import B200GPCore, ConstMean, make_kernel
+from .. import engine
+
+
+class GPWrapper(object):
+    """Abstract GP (reference gp_interface.py:9-42)."""
+
+    def __init__(self, gp_core, options):
+        self.gp_core = gp_core
+        self.options = options
+
+    def eval(self, pts, include_covar=False):
+        raise NotImplementedError('Abstract Method')
+
+    def draw_sample(self, samp_pts=None, means=None, covar=None):
+        raise NotImplementedError('Abstract Method')
+
+    def add_data_single(self, pt, val):
+        raise NotImplementedError('Abstract Method')
+
+    def build_posterior(self):
+        raise NotImplementedError('Abstract Method')
+
+    def get_estimated_noise(self):
+        raise NotImplementedError('Abstract Method.')
+
+    def get_kernel_hps(self):
+        raise NotImplementedError('Abstract Method.')
+
+    def get_pt_relations(self, pt_set1, pt_set2):
+        raise NotImplementedError('Abstract Method.')
+
+
+class GPFitterWrapper(object):
+    """Abstract fitter (reference gp_interface.py:44-65)."""
+
+    def __init__(self, x_data, y_data, options):
+        self.x_data = x_data
+        self.y_data = y_data
+        self.options = options
+        self._init_gpf()
+
+    def fit_gp(self):
+        raise NotImplementedError('Abstract Method')
+
+    def get_next_gp(self):
+        raise NotImplementedError('Abstract Method')
+
+    def _init_gpf(self):
+        raise NotImplementedError('Abstract Method')
+
+
+class B200GP(GPWrapper):
+    """Drop-in for ``DragonflyGP`` (reference gp_interface.py:67-119)."""
+
+    def eval(self, pts, include_covar=False):
+        # :69-74 -- (mean[m], covar[m, m] or None)
+        if include_covar:
+            return self.gp_core.eval(pts, uncert_form='covar')
+        return self.gp_core.eval(pts)
+
+    def draw_sample(self, samp_pts=None, means=None, covar=None):
+        # :76-79 -- one joint sample, raveled to (m,)
+        return self.gp_core.draw_samples(1, X_test=samp_pts, mean_vals=means,
+                                         covar=covar).ravel()
+
+    def add_data_single(self, pt, val):
+        self.gp_core.add_data_single(pt, val)  # :81-83
+
+    def build_posterior(self):
+        if self.gp_core.alpha is None:  # :85-88, idempotent
+            self.gp_core.build_posterior()
+
+    def get_estimated_noise(self):
+        return self.gp_core.noise_var  # :90-92
+
+    def get_kernel_hps(self):
+        # :94-110 (additive kernels are out of scope)
+        if getattr(self.options, 'use_additive_gp', False):
+            raise NotImplementedError('additive GPs are outside the MTS hot path')
+        hps = deepcopy(self.gp_core.kernel.hyperparams)
+        hps['lengthscale'] = hps['dim_bandwidths']
+        hps.pop('dim_bandwidths', None)
+        return hps
+
+    def get_pt_relations(self, pt_set1, pt_set2):
+        # :112-119 -- k(A,B) - (L^-1 k(X,A))^T (L^-1 k(X,B)), fused on device
+        return self.gp_core.cross_covariance(pt_set1, pt_set2)
+
+
+class B200GPFitter(GPFitterWrapper):
+    """Drop-in for ``DragonflyGPFitter`` (reference gp_interface.py:121-138)."""
+
+    _fit_counter = 0
+
+    def _init_gpf(self):
+        X = [np.asarray(x, dtype=np.float64).ravel() for x in self.x_data]
+        self.dim = len(X[0]) if len(X) else int(self.options.dim)
+        self._X = np.asarray(X, dtype=np.float64).reshape(-1, self.dim)
+        self._Y = np.asarray(self.y_data, dtype=np.float64).ravel()
+        self.kind = engine.kernel_kind(self.options.kernel_type,
+                                       getattr(self.options, 'matern_nu', 2.5))
+        self.hp_list = []
+        self._next = 0
+        self.last_lmls = None
+        self.last_candidates = None
+
+    def _criterion(self):
+        crits = str(self.options.hp_tune_criterion).split('-')
+        crit = crits[B200GPFitter._fit_counter % len(crits)]
+        B200GPFitter._fit_counter += 1
+        return crit
+
+    def fit_gp(self):
+        """:123-125.  One batched device pass evaluates every candidate's LML."""
+        num_cand = int(getattr(self.options, 'hp_search_candidates', 64))
+        crit = self._criterion()
+        cands = hp_search.hp_candidates(self._X, self._Y, num_cand)
+        lmls, _ = hp_search.batched_lml(self._X, self._Y, self.kind, cands)
+        self.last_lmls, self.last_candidates = lmls, cands
+        idx = hp_search.select(lmls, crit, getattr(self.options, 'hp_samples', 0))
+        self.hp_list = [cands[i] for i in idx]
+        self._next = 0
+
+    def _make_core(self, theta, build):
+        D = self.dim
+        kern = make_kernel(self.options.kernel_type, D, theta[0], theta[3:3 + D],
+                           getattr(self.options, 'matern_nu', 2.5))
+        return B200GPCore(list(self._X), list(self._Y), kern, ConstMean(theta[2]), theta[1],
+                          build_posterior=build)
+
+    def get_next_gp(self):
+        """:127-133 -- next hyper-parameter draw, posterior built."""
+        theta = self.hp_list[self._next % len(self.hp_list)]
+        self._next += 1
+        return B200GP(self._make_core(theta, True), self.options)
+
+
+def make_gp(X, Y, kernel_type, scale, bandwidths, noise_var, mu0, matern_nu=2.5, options=None,
+            build=True):
+    """A B200GP at fixed hyper-parameters (pre-tuned mode, tests, benches)."""
+    from argparse import Namespace
+    X = np.asarray(X, dtype=np.float64)
+    D = X.shape[1] if X.ndim == 2 and X.size else len(np.atleast_1d(bandwidths))
+    kern = make_kernel(kernel_type, D, scale, bandwidths, matern_nu)
+    core = B200GPCore(list(X.reshape(-1, D)), list(np.asarray(Y, dtype=np.float64).ravel()), kern,
+                      ConstMean(mu0), noise_var, build_posterior=build)
+    return B200GP(core, options or Namespace(use_additive_gp=False))

@@ -1,0 +1,200 @@
+"""Joint-MTS posterior-sampling step for a batch of independent BO trials
+(BASELINE.json configs[4], SURVEY.md 8d "sweep").
+
+One step, per trial, is the whole hot path of ``JointMTS._find_best_query``
+(/root/reference/src/strategies/joint_mts.py:24-57) at fixed hyper-parameters:
+
+  K = k(X,X) + noise I -> L_K -> alpha            (build_posterior, a6)
+  mu = mu0 + k(Xs,X) alpha                        (eval mean, a4)
+  V = L_K^{-1} k(X,Xs); Sigma = k(Xs,Xs) - V^T V  (eval covar, a4)
+  L_S = chol(Sigma)                               (stable_cholesky, a5)
+  F = mu + L_S Z, Z ~ Philox(seed, trial)         (draw_samples, a5; S draws)
+  per draw: task = argmax_t max_a F[t,a], action  (the pick, a2)
+
+Everything is resident in HBM; a step only moves the trial inputs in and the
+picks out.  Trials are independent, so a step processes ``batch`` of them per
+kernel launch (grid.z) and several ``SweepStep`` objects may run on different
+CUDA streams to fill the latency-bound panel phases of one trial with the
+trailing updates of another.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import TILE, call
+from .engine import F64, I32, _p
+
+SEED = 100826730  # the reference's global seed (src/ocbo.py:74-75)
+# SE-ARD bandwidths of the sweep: 0.25 on the 4 context dims, 0.05 on the 2 action dims.
+# (SURVEY 8d quotes an isotropic 0.25 "to keep cond(Sigma) <~ 1e6"; measured, that choice gives
+# cond ~ 1e16 and fires the jitter ladder, so the action bandwidth is set to meet the stated
+# conditioning goal instead: cond(Sigma) ~ 1e4-1e5.  DESIGN.md "sweep configuration".)
+SWEEP_BANDWIDTHS = (0.25, 0.25, 0.25, 0.25, 0.05, 0.05)
+
+# algorithmic FLOPs of one trial-step
+def step_flops(n, m, S):
+    return (n ** 3 / 3.0 + float(n) ** 2 * m + float(n) * m ** 2 + m ** 3 / 3.0
+            + float(m) ** 2 * S + 2.0 * m * n + 2.0 * n ** 2)
+
+
+def hartmann6(x):
+    A = np.asarray([[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14],
+                    [3, 3.5, 1.7, 10, 17, 8], [17, 8, 0.05, 10, 0.1, 14]])
+    P = 1e-4 * np.asarray([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
+                           [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]])
+    alpha = np.asarray([1.0, 1.2, 3.0, 3.2])
+    x = np.atleast_2d(x)
+    e = -np.einsum('ij,nij->ni', A, (x[:, None, :] - P[None]) ** 2)
+    return (alpha * np.exp(e)).sum(axis=1)
+
+
+def make_trial_inputs(trial, n=1024, T=64, A=128, ctx_dim=4, act_dim=2):
+    """Synthetic inputs of trial ``trial``: X ~ U[0,1]^(n x 6),
+    y = hartmann6(X) + N(0, 1e-4), candidates = task-major grid of T task
+    locations ~ U[0,1]^4 times A actions ~ U[0,1]^2 (misc_util.py:104-116)."""
+    g = np.random.default_rng(trial)
+    D = ctx_dim + act_dim
+    X = g.uniform(size=(n, D))
+    y = (hartmann6(X) if D == 6 else np.sin(3.0 * X.sum(axis=1))) + 1e-2 * g.standard_normal(n)
+    locs = g.uniform(size=(T, ctx_dim))
+    acts = g.uniform(size=(T * A, act_dim))
+    Xs = np.hstack([np.repeat(locs, A, axis=0), acts])
+    return X, y, Xs
+
+
+class SweepStep(object):
+    """Pre-allocated device state + the kernel sequence for ``batch`` trials."""
+
+    def __init__(self, n=1024, T=64, A=128, S=256, dim=6, batch=1, kernel_type='se',
+                 scale=1.0, bandwidths=SWEEP_BANDWIDTHS, noise_var=1e-2, mu0=0.0, seed=SEED,
+                 stream=None):
+        engine.require_cuda()
+        if n % TILE or (T * A) % TILE:
+            raise ValueError('n and T*A must be multiples of %d' % TILE)
+        if S > 8 and S % TILE:
+            raise ValueError('S must be <= 8 or a multiple of %d' % TILE)
+        self.n, self.T, self.A, self.S, self.D, self.B = n, T, A, S, dim, batch
+        self.m = T * A
+        self.kind = engine.kernel_kind(kernel_type)
+        self.seed = seed
+        self.stream = stream or torch.cuda.current_stream()
+        dev = engine.device()
+        B, m, D = batch, self.m, dim
+        e = lambda *shape, dt=F64: torch.empty(shape, dtype=dt, device=dev)
+        self.X, self.y, self.Xs = e(B, n, D), e(B, n), e(B, m, D)
+        bws = np.broadcast_to(np.asarray(bandwidths, dtype=np.float64), (D,))
+        th = np.concatenate([[scale, noise_var, mu0], bws])
+        self.theta = torch.from_numpy(np.tile(th, (B, 1))).to(dev)
+        self.LK, self.invdK = e(B, n, n), e(B, n // TILE, TILE, TILE)
+        self.alpha, self.lml, self.mean = e(B, n), e(B), e(B, m)
+        self.V = e(B, n, m)
+        self.Sigma, self.invdS = e(B, m, m), e(B, m // TILE, TILE, TILE)
+        self.Z, self.F = e(B, m, S), e(B, m, S)
+        self.info = torch.zeros((2, B), dtype=I32, device=dev)
+        seg = np.tile((A * np.arange(T + 1)).astype(np.int32), (B, 1))
+        self.seg = torch.from_numpy(seg).to(dev)
+        self.seg_max, self.seg_arg = e(B, T, S), e(B, T, S, dt=I32)
+        self.task, self.action, self.gain = e(B, S, dt=I32), e(B, S, dt=I32), e(B, S)
+        self.trial_ids = torch.zeros((B,), dtype=I32, device=dev)
+        # pinned staging for the host-buffer API
+        pin = lambda *shape, dt=F64: torch.empty(shape, dtype=dt).pin_memory()
+        self.hX, self.hy, self.hXs = pin(B, n, D), pin(B, n), pin(B, m, D)
+        self.htrial = pin(B, dt=I32)
+        self.htask, self.haction = pin(B, S, dt=I32), pin(B, S, dt=I32)
+        self.hgain = pin(B, S)
+        self.hinfo = pin(2, B, dt=I32)
+        # kernels per run(): gram, potrf(n), solve, mean, gram, trsm, cov, potrf(m), philox,
+        # sample, segment, pick
+        self.launches_per_run = 1 + (3 * (n // TILE) - 2) + 1 + 1 + 1 + (2 * (n // TILE) - 1) + 1 \
+            + (3 * (self.m // TILE) - 2) + 1 + 1 + 1 + 1
+        self.h2d_bytes = B * (n * D + n + m * D) * 8 + B * 4
+        self.d2h_bytes = B * S * (8 + 8) + 2 * B * 4
+
+    # -- device-resident step -------------------------------------------------
+    def run(self):
+        """Launch the whole step on ``self.stream`` (asynchronous)."""
+        st = ctypes.c_void_p(self.stream.cuda_stream)
+        B, n, m, D, S, T = self.B, self.n, self.m, self.D, self.S, self.T
+        X, Xs, th = self.X, self.Xs, self.theta
+        infoK, infoS = self.info[0], self.info[1]
+        with torch.cuda.stream(self.stream):
+            self.info.zero_()
+        call('ocbo_gram', self.kind, D, _p(X), n, X.stride(0), None, _p(X), n, X.stride(0), None,
+             _p(th), th.stride(0), _p(self.LK), n, self.LK.stride(0), B,
+             _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE, st)
+        call('ocbo_potrf', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK), _p(infoK), B, st)
+        call('ocbo_solve_alpha_lml', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK),
+             _p(self.y), self.y.stride(0), None, _p(th), th.stride(0), _p(self.alpha),
+             self.alpha.stride(0), _p(self.lml), _p(infoK), B, st)
+        call('ocbo_post_mean', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(X), n, X.stride(0),
+             None, _p(th), th.stride(0), _p(self.alpha), self.alpha.stride(0), _p(self.mean),
+             self.mean.stride(0), B, st)
+        call('ocbo_gram', self.kind, D, _p(X), n, X.stride(0), None, _p(Xs), m, Xs.stride(0), None,
+             _p(th), th.stride(0), _p(self.V), m, self.V.stride(0), B, 0, st)
+        call('ocbo_trsm_lower', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK), _p(self.V), m,
+             m, self.V.stride(0), _p(infoK), B, st)
+        call('ocbo_post_cov', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
+             self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B, st)
+        call('ocbo_potrf', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(infoS), B, st)
+        call('ocbo_philox_normal', _p(self.Z), m, S, S, self.Z.stride(0),
+             ctypes.c_uint64(self.seed), _p(self.trial_ids), B, st)
+        call('ocbo_sample', _p(self.mean), self.mean.stride(0), _p(self.Sigma), m, m,
+             self.Sigma.stride(0), _p(self.Z), S, S, self.Z.stride(0), _p(self.F), S,
+             self.F.stride(0), _p(infoS), B, st)
+        call('ocbo_segment_argmax', _p(self.F), S, S, self.F.stride(0), _p(self.seg), T,
+             _p(self.seg_max), _p(self.seg_arg), B, st)
+        call('ocbo_joint_pick', _p(self.seg_max), _p(self.seg_arg), T, 0, T, S, _p(self.task),
+             _p(self.action), _p(self.gain), B, st)
+        engine._count(self.launches_per_run)
+
+    def set_inputs_device(self, trial_ids, inputs):
+        """Load trial inputs once (device-resident timing)."""
+        for b, (X, y, Xs) in enumerate(inputs):
+            self.hX[b].copy_(torch.from_numpy(X))
+            self.hy[b].copy_(torch.from_numpy(y))
+            self.hXs[b].copy_(torch.from_numpy(Xs))
+            self.htrial[b] = int(trial_ids[b])
+        self._upload()
+
+    def _upload(self):
+        with torch.cuda.stream(self.stream):
+            self.X.copy_(self.hX, non_blocking=True)
+            self.y.copy_(self.hy, non_blocking=True)
+            self.Xs.copy_(self.hXs, non_blocking=True)
+            self.trial_ids.copy_(self.htrial, non_blocking=True)
+
+    def _download(self):
+        with torch.cuda.stream(self.stream):
+            self.htask.copy_(self.task, non_blocking=True)
+            self.haction.copy_(self.action, non_blocking=True)
+            self.hgain.copy_(self.gain, non_blocking=True)
+            self.hinfo.copy_(self.info, non_blocking=True)
+
+    # -- host-buffer API (what bench.py's e2e leg times) ------------------------
+    def submit_host(self, trial_ids, inputs):
+        """Stage host inputs (pinned), H2D, run, D2H of the picks; asynchronous."""
+        for b, (X, y, Xs) in enumerate(inputs):
+            self.hX[b].copy_(torch.from_numpy(X))
+            self.hy[b].copy_(torch.from_numpy(y))
+            self.hXs[b].copy_(torch.from_numpy(Xs))
+            self.htrial[b] = int(trial_ids[b])
+        self._upload()
+        self.run()
+        self._download()
+
+    def result_host(self):
+        """Synchronise the stream and return (task[B,S], action[B,S], gain[B,S])."""
+        self.stream.synchronize()
+        info = self.hinfo.numpy()
+        if info.any():
+            raise ValueError('Cholesky failed in sweep step (info=%s); use the ladder path '
+                             '(B200GP.draw_sample) for this trial' % info.tolist())
+        return self.htask.numpy().copy(), self.haction.numpy().copy(), self.hgain.numpy().copy()
+
+    def step_host(self, trial_ids, inputs):
+        self.submit_host(trial_ids, inputs)
+        return self.result_host()
