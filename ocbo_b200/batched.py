@@ -1,0 +1,97 @@
+"""Batched posterior-sample-and-reduce over many GPs / many candidate sets.
+
+This is where the B200 design departs from the reference's Python ``for`` loops
+(src/strategies/mts.py:28, src/cstrats/profile_cts.py:31): every task (or
+context) becomes one problem of a strided batch and the whole
+posterior -> covariance -> Cholesky -> sample -> max/argmax chain is ONE
+sequence of batched kernel launches.  Normals are passed in (drawn by the
+caller in the reference's order) so a seeded run consumes the global numpy
+stream exactly like the reference.
+"""
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import engine
+from .engine import DevicePosterior, F64
+
+
+def _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post=False):
+    """Common tail: posterior at pts -> L_Sigma (ladder) -> mu + L z -> segment
+    max/argmax.  Returns (seg_max [B, nseg], seg_arg [B, nseg], mean dev, F dev, mv)."""
+    Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
+    mean = post.mean(Xd, mv_dev)
+    V = post.solve_cross(Xd, mv_dev)
+    Sigma = post.cov(Xd, mv_dev, V, True)
+
+    def reassemble(b0, b1):
+        post.cov(Xd, mv_dev, V, True, out=Sigma, b0=b0, b1=b1)
+
+    _, info, jit = engine.factor_covariance(post, Sigma, mv_dev, mv, reassemble)
+    Z = engine.pad_normals(Z_list, mv, m_pad, 1)
+    Fm = engine.sample_from_factor(mean, Sigma, Z, info)
+    seg = np.asarray(seg_lists, dtype=np.int32)
+    mx, ag = engine.segment_argmax(Fm, 1, seg)
+    return mx[:, :, 0].cpu().numpy(), ag[:, :, 0].cpu().numpy(), mean, Fm, mv, jit
+
+
+def mts_step(gps, samp_pts_list, n_old_list, Z_list):
+    """Independent-GP MTS reduction (src/strategies/mts.py:28-43) for all tasks
+    at once.  ``gps[f]`` are B200GP objects (only their data and hyper-parameters
+    are read: the batched posterior is rebuilt here, as ``get_next_gp`` would).
+    Returns per task (max_prev, best_new_idx_relative, best_new_val)."""
+    T = len(gps)
+    groups = defaultdict(list)
+    for f, gp in enumerate(gps):
+        core = gp.gp_core
+        groups[(core.dim, core.kernel.kind)].append(f)
+    out = [None] * T
+    for (D, kind), members in groups.items():
+        cores = [gps[f].gp_core for f in members]
+        post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
+                               np.asarray([c.theta() for c in cores]), kind, D).build()
+        pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
+        segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
+        mx, ag, _, _, _, jit = _sample_reduce(post, pts, [Z_list[f] for f in members], segs)
+        for k, f in enumerate(members):
+            out[f] = (float(mx[k, 0]), int(ag[k, 1]), float(mx[k, 1]))
+            gps[f].gp_core.last_sample_jitter = jit[k]
+    return out
+
+
+class SharedPosterior(object):
+    """View of ONE built posterior replicated (stride 0) over B candidate sets --
+    the continuous strategies evaluate the same GP at 50 contexts
+    (src/cstrats/profile_cts.py:26-37)."""
+
+    def __init__(self, post, B):
+        self.B, self.D, self.kind, self.n_pad = B, post.D, post.kind, post.n_pad
+        ex = lambda t: t.expand(B, *t.shape[1:])
+        self.X, self.y, self.theta, self.nv = ex(post.X), ex(post.y), ex(post.theta), ex(post.nv)
+        self.L, self.invd, self.alpha, self.info = ex(post.L), ex(post.invd), ex(post.alpha), ex(post.info)
+        self.nv_host = post.nv_host * B
+
+    upload_points = DevicePosterior.upload_points
+    mean = DevicePosterior.mean
+    solve_cross = DevicePosterior.solve_cross
+    cov = DevicePosterior.cov
+
+
+def profile_step(gp, act_sets, Z_list):
+    """Continuous MTS inner loop (src/cstrats/profile_cts.py:76-105) for all
+    contexts at once.  Returns (sample_max, sample_argmax, mean_max, mean_argmax,
+    sample_at_mean_argmax) as arrays over contexts."""
+    core = gp.gp_core
+    if core._post is None:
+        core.build_posterior()
+    B = len(act_sets)
+    post = SharedPosterior(core._post, B)
+    segs = [[0, len(a)] for a in act_sets]
+    mx, ag, mean, Fm, mv, jit = _sample_reduce(post, act_sets, Z_list, segs)
+    mmx, mag = engine.segment_argmax(mean.unsqueeze(2), 1, np.asarray(segs, dtype=np.int32))
+    mmx, mag = mmx[:, 0, 0].cpu().numpy(), mag[:, 0, 0].cpu().numpy()
+    idx = torch.from_numpy(mag.astype(np.int64)).to(Fm.device)
+    s_at = Fm[:, :, 0].gather(1, idx[:, None])[:, 0].cpu().numpy()
+    core.last_sample_jitter = jit
+    return mx[:, 0], ag[:, 0], mmx, mag, s_at
