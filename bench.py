@@ -273,9 +273,10 @@ def run_b200(args):
     run_resident(args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = engine.LAUNCHES[0]
+    from ocbo_b200._lib import LIB
+    launches0 = int(LIB.ocbo_launch_count())
     ms_resident = run_resident(args.steps)
-    launches = engine.LAUNCHES[0] - launches0
+    launches = int(LIB.ocbo_launch_count()) - launches0
     clocks = sampler.stop()
 
     # ---- (2) end to end: host buffers in, picks out, every step ----------------
@@ -337,27 +338,30 @@ def run_b200(args):
                  ctypes.c_void_p(grp.Sigma.data_ptr()), m, grp.Sigma.stride(0), 1, B, st)
         grp.info.zero_()
         torch.cuda.synchronize()
-        ms3 = (ctypes.c_float * 3)()
+        ms3 = (ctypes.c_float * 4)()
         lib_call('ocbo_potrf_profile', ctypes.c_void_p(grp.Sigma.data_ptr()), m, m,
                  grp.Sigma.stride(0), ctypes.c_void_p(grp.invdS.data_ptr()),
                  ctypes.c_void_p(grp.info[1].data_ptr()), B, st, ms3)
         nt = m // 128
-        # algorithmic flops of the trailing updates: lower triangle incl. diagonal of the
-        # (r*128)^2 trailing block, rank-128 update, 2 flops per multiply-add
-        alg = sum(((r * 128) * (r * 128 + 1) / 2.0) * 2.0 * 128 for r in range(1, nt)) * B
-        trailing_tflops = alg / (ms3[2] * 1e-3) / 1e12 if ms3[2] > 0 else None
+        # algorithmic flops of the DMMA update launches of one chol(Sigma): m^3/3 minus the
+        # diagonal-block factorisations (128^3/3 each) and the panel solves (rows * 128^2)
+        alg = (m ** 3 / 3.0 - nt * 128.0 ** 3 / 3.0
+               - sum(r * 128.0 * 128.0 ** 2 for r in range(1, nt))) * B
+        ms_upd = ms3[2] + ms3[3]
+        trailing_tflops = alg / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else None
         peaks = {} if args.no_peaks else measure_fp64_peaks(torch, lib_call, dev)
         peak = peaks.get('cublas_dgemm_tflops')
         step_tflops = sweep.step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
             / (ms_resident * 1e-3) / 1e12
         roof = {
-            'bound': 'tensor', 'kernel': 'gemm_nt_kernel (Cholesky trailing update, DMMA.8x8x4 fp64)',
+            'bound': 'tensor', 'kernel': 'gemm_nt_kernel (Cholesky rank-k updates of chol(Sigma), DMMA.8x8x4 fp64)',
             'achieved': trailing_tflops, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': (trailing_tflops / peak) if (peak and trailing_tflops) else None,
             'traffic': None,
             'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
                            'MEASURED_PEAKS.json has no FP64 row',
-            'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'trailing': ms3[2]},
+            'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],
+                         'outer_update': ms3[3], 'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 512))},
             'step_tflops_per_gpu': step_tflops / world,
             'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,

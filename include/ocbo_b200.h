@@ -52,6 +52,8 @@ typedef void* ocbo_stream_t; /* cudaStream_t */
 
 const char* ocbo_last_error_string(void);
 int ocbo_version(void);
+/* Kernel launches issued by this process through the library (statistics). */
+unsigned long long ocbo_launch_count(void);
 
 /* Workspace (bytes) for the inverse diagonal blocks that ocbo_potrf writes and
  * ocbo_trsm_lower / ocbo_solve_vec read: batch * (n/128) * 128*128 doubles. */
@@ -86,7 +88,8 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
                double* invdiag, int32_t* info, int batch, ocbo_stream_t stream);
 
 /* ocbo_potrf with CUDA events around every launch, summed per kernel class into
- * ms_host[3] = { diagonal-block, panel-solve, trailing-update } milliseconds.
+ * ms_host[4] = { diagonal-block, panel-solve, in-panel rank-128 update,
+ * outer rank-k trailing update } milliseconds.
  * Synchronises the stream; used by bench.py's roofline leg only. */
 int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a,
                        double* invdiag, int32_t* info, int batch, ocbo_stream_t stream,

@@ -13,6 +13,7 @@ _U64 = ctypes.c_uint64
 
 _PROTOS = {
     'ocbo_version': (ctypes.c_int, []),
+    'ocbo_launch_count': (ctypes.c_uint64, []),
     'ocbo_invdiag_elems': (_L, [_I]),
     'ocbo_gram': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _L, _VP, _I, _L, _I, _I, _VP]),
     'ocbo_add_diag': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP]),

@@ -4,12 +4,16 @@
 // the per-kernel "max dynamic smem" opt-in done on first use.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
 
 using namespace ocbo;
 
+namespace ocbo {
+unsigned long long g_launch_count = 0;
+}
 static thread_local char g_err[256] = "ok";
 
 static int fail_arg(int k, const char* what) {
@@ -31,6 +35,9 @@ static inline bool tile_ok(int n) { return n > 0 && n % TILE == 0; }
 
 extern "C" {
 
+unsigned long long ocbo_launch_count(void) {
+  return __atomic_load_n(&ocbo::g_launch_count, __ATOMIC_RELAXED);
+}
 const char* ocbo_last_error_string(void) { return g_err; }
 int ocbo_version(void) { return 100; }
 int64_t ocbo_invdiag_elems(int n) { return (int64_t)(n / TILE) * TILE * TILE; }
@@ -75,6 +82,82 @@ int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* n
   return 0;
 }
 
+// Two-level blocked right-looking Cholesky.  Outer panels of `outer` columns
+// (OCBO_POTRF_OUTER, default 512) are factored with 128-wide steps whose
+// rank-128 updates stay inside the panel (L2-resident); the trailing matrix is
+// then updated ONCE per outer panel with a rank-`outer` DMMA update, so the
+// bulk of the m^3/3 flops runs with long k and touches each C tile once per
+// outer panel instead of once per 128 columns.
+struct PotrfTimer {
+  cudaEvent_t* ev; int* cls; int n; int cap;
+  void mark(cudaStream_t st, int c) {
+    if (!ev || n >= cap) return;
+    cudaEventRecord(ev[n], st);
+    cls[n] = c;
+    ++n;
+  }
+};
+
+static int potrf_outer_tiles(int nt) {
+  static int outer = -1;
+  if (outer < 0) {
+    const char* e = getenv("OCBO_POTRF_OUTER");
+    int v = e ? atoi(e) : 512;
+    if (v < TILE) v = TILE;
+    outer = v / TILE;
+  }
+  return outer < nt ? outer : nt;
+}
+
+static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
+                     int batch, cudaStream_t st, PotrfTimer* tm) {
+  const int nt = n / TILE;
+  const int64_t sInv = ocbo_invdiag_elems(n);
+  const int NBO = potrf_outer_tiles(nt);
+  for (int J0 = 0; J0 < nt; J0 += NBO) {
+    const int J1 = (J0 + NBO < nt) ? J0 + NBO : nt;
+    for (int j = J0; j < J1; ++j) {
+      CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "potrf_diag");
+      if (tm) tm->mark(st, 0);
+      const int r = nt - 1 - j;
+      if (r == 0) break;
+      double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
+      NtParams p{};
+      // panel solve: X <- X inv(L_jj)^T, in place (each CTA owns its 128 rows)
+      p.P = panel; p.ldp = lda; p.sP = s_a;
+      p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
+      p.C = panel; p.ldc = lda; p.sC = s_a;
+      p.ntc = 1; p.ktiles = TILE / BK; p.mode = 0; p.info = info;
+      CK(launch_gemm_nt(p, r, batch, st), "potrf panel");
+      if (tm) tm->mark(st, 1);
+      // inner update: the remaining columns of this outer panel, all rows below
+      const int ncols = J1 - 1 - j;
+      if (ncols > 0) {
+        NtParams u{};
+        u.P = panel; u.ldp = lda; u.sP = s_a;
+        u.Q = panel; u.ldq = lda; u.sQ = s_a;
+        u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
+        u.ntc = ncols; u.ktiles = TILE / BK; u.row0 = (j + 1) * TILE; u.col0 = (j + 1) * TILE;
+        u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
+        CK(launch_gemm_nt(u, r * ncols, batch, st), "potrf inner update");
+        if (tm) tm->mark(st, 2);
+      }
+    }
+    const int R = nt - J1;
+    if (R > 0) {
+      // outer update: A[J1:, J1:] -= L[J1:, J0:J1] L[J1:, J0:J1]^T  (lower tiles)
+      NtParams u{};
+      u.P = A + (size_t)J1 * TILE * lda + (size_t)J0 * TILE; u.ldp = lda; u.sP = s_a;
+      u.Q = u.P; u.ldq = lda; u.sQ = s_a;
+      u.C = A + (size_t)J1 * TILE * lda + (size_t)J1 * TILE; u.ldc = lda; u.sC = s_a;
+      u.ntc = R; u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1; u.info = info;
+      CK(launch_gemm_nt(u, R * (R + 1) / 2, batch, st), "potrf outer update");
+      if (tm) tm->mark(st, 3);
+    }
+  }
+  return 0;
+}
+
 int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info, int batch,
                ocbo_stream_t stream) {
   if (!A) return fail_arg(1, "A null");
@@ -83,86 +166,41 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t*
   if (!invdiag) return fail_arg(5, "invdiag null");
   if (!info) return fail_arg(6, "info null");
   if (batch <= 0) return fail_arg(7, "batch");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int nt = n / TILE;
-  const int64_t sInv = ocbo_invdiag_elems(n);
-  for (int j = 0; j < nt; ++j) {
-    CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "potrf_diag");
-    const int r = nt - 1 - j;
-    if (r == 0) break;
-    double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
-    NtParams p{};
-    // panel solve: X <- X inv(L_jj)^T, in place (each CTA owns its 128 rows)
-    p.P = panel; p.ldp = lda; p.sP = s_a;
-    p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
-    p.C = panel; p.ldc = lda; p.sC = s_a;
-    p.ntc = 1; p.ktiles = TILE / BK; p.row0 = 0; p.col0 = 0;
-    p.tri = 0; p.lower_skip = 0; p.mode = 0; p.info = info;
-    CK(launch_gemm_nt(p, r, batch, st), "potrf panel");
-    // trailing update: A22 -= L21 L21^T on the lower-triangular tiles
-    NtParams u{};
-    u.P = panel; u.ldp = lda; u.sP = s_a;
-    u.Q = panel; u.ldq = lda; u.sQ = s_a;
-    u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
-    u.ntc = r; u.ktiles = TILE / BK; u.row0 = 0; u.col0 = 0;
-    u.tri = 1; u.lower_skip = 0; u.mode = 1; u.info = info;
-    CK(launch_gemm_nt(u, r * (r + 1) / 2, batch, st), "potrf trailing");
-  }
-  return 0;
+  return potrf_run(A, n, lda, s_a, invdiag, info, batch, (cudaStream_t)stream, nullptr);
 }
 
-// Same factorisation, instrumented: CUDA events around every launch on `stream`,
-// summed per kernel class into ms_host[3] = {diag, panel, trailing}.  Synchronous
-// (bench.py's roofline leg only).
+// Same factorisation, instrumented: CUDA events after every launch on `stream`,
+// summed per kernel class into ms_host[4] = {diag, panel, inner update, outer
+// update}.  Synchronous (bench.py's roofline leg only).
 int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
                        int batch, ocbo_stream_t stream, float* ms_host) {
   if (!A) return fail_arg(1, "A null");
   if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
   if (!invdiag || !info || !ms_host) return fail_arg(5, "null");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nt = n / TILE;
-  const int64_t sInv = ocbo_invdiag_elems(n);
-  const int nev = 3 * nt + 1;
-  cudaEvent_t* ev = new cudaEvent_t[nev];
-  for (int i = 0; i < nev; ++i) cudaEventCreate(&ev[i]);
-  int e = 0;
-  int rc = 0;
-  cudaEventRecord(ev[e++], st);
-  for (int j = 0; j < nt && !rc; ++j) {
-    rc = check(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "diag");
-    cudaEventRecord(ev[e++], st);
-    const int r = nt - 1 - j;
-    if (r == 0 || rc) break;
-    double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
-    NtParams p{};
-    p.P = panel; p.ldp = lda; p.sP = s_a;
-    p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
-    p.C = panel; p.ldc = lda; p.sC = s_a;
-    p.ntc = 1; p.ktiles = TILE / BK; p.mode = 0; p.info = info;
-    rc = check(launch_gemm_nt(p, r, batch, st), "panel");
-    cudaEventRecord(ev[e++], st);
-    NtParams u{};
-    u.P = panel; u.ldp = lda; u.sP = s_a;
-    u.Q = panel; u.ldq = lda; u.sQ = s_a;
-    u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
-    u.ntc = r; u.ktiles = TILE / BK; u.tri = 1; u.mode = 1; u.info = info;
-    if (!rc) rc = check(launch_gemm_nt(u, r * (r + 1) / 2, batch, st), "trailing");
-    cudaEventRecord(ev[e++], st);
-  }
+  const int cap = 4 * (n / TILE) + 2;
+  cudaEvent_t* ev = new cudaEvent_t[cap];
+  int* cls = new int[cap];
+  for (int i = 0; i < cap; ++i) cudaEventCreate(&ev[i]);
+  PotrfTimer tm{ev, cls, 0, cap};
+  tm.mark(st, -1);
+  int rc = potrf_run(A, n, lda, s_a, invdiag, info, batch, st, &tm);
   cudaError_t se = cudaStreamSynchronize(st);
-  ms_host[0] = ms_host[1] = ms_host[2] = 0.f;
+  for (int c = 0; c < 4; ++c) ms_host[c] = 0.f;
   if (!rc && se == cudaSuccess) {
-    for (int i = 1; i < e; ++i) {
+    for (int i = 1; i < tm.n; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      ms_host[(i - 1) % 3] += ms;
+      ms_host[cls[i]] += ms;
     }
   }
-  for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  for (int i = 0; i < cap; ++i) cudaEventDestroy(ev[i]);
   delete[] ev;
+  delete[] cls;
   if (rc) return rc;
   return check(se, "ocbo_potrf_profile sync");
 }
+
 
 int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* invdiag, double* B,
                     int nrhs, int ldb, int64_t s_b, const int32_t* info, int batch,

@@ -174,7 +174,7 @@ cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_
   }
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
   gemm_nt_kernel<<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 cudaError_t launch_gemm_nn(const NnParams& p, int ntr, int ntc, int batch, cudaStream_t st) {
@@ -187,7 +187,7 @@ cudaError_t launch_gemm_nn(const NnParams& p, int ntr, int ntc, int batch, cudaS
   }
   if (ntr <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
   gemm_nn_kernel<<<dim3(ntc, ntr, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
@@ -201,7 +201,7 @@ cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream
   }
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
   postcov_kernel<<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 }  // namespace ocbo

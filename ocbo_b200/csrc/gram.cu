@@ -91,7 +91,7 @@ cudaError_t launch_gram(int kind, int dim, const double* X1, int n1, int64_t sX1
   GramArgs a{X1, n1, sX1, nv1, X2, n2, sX2, nv2, theta, sTheta, K, ldk, sK, kind, dim, flags};
   dim3 grid(n2 / GT, n1 / GT, batch);
   gram_kernel<<<grid, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // --------------------------------------------------------------------------
@@ -106,7 +106,7 @@ __global__ void add_diag_kernel(double* A, int n, int lda, int64_t sA, const int
 cudaError_t launch_add_diag(double* A, int n, int lda, int64_t sA, const int32_t* nv,
                             const double* val, int batch, cudaStream_t st) {
   add_diag_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(A, n, lda, sA, nv, val);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 __global__ void diag_max_kernel(const double* A, int n, int lda, int64_t sA, const int32_t* nv,
@@ -130,7 +130,7 @@ __global__ void diag_max_kernel(const double* A, int n, int lda, int64_t sA, con
 cudaError_t launch_diag_max(const double* A, int n, int lda, int64_t sA, const int32_t* nv,
                             double* out, int batch, cudaStream_t st) {
   diag_max_kernel<<<batch, 256, 0, st>>>(A, n, lda, sA, nv, out);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // mirror the lower triangle onto the upper one, 32x32 tiles through smem
@@ -150,7 +150,7 @@ __global__ void symmetrize_kernel(double* A, int n, int lda, int64_t sA) {
 
 cudaError_t launch_symmetrize(double* A, int n, int lda, int64_t sA, int batch, cudaStream_t st) {
   symmetrize_kernel<<<dim3(n / 32, n / 32, batch), dim3(32, 8), 0, st>>>(A, n, lda, sA);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // --------------------------------------------------------------------------
@@ -211,7 +211,7 @@ cudaError_t launch_post_mean(int kind, int dim, const double* Xs, int m, int64_t
                              int batch, cudaStream_t st) {
   MeanArgs a{Xs, m, sXs, mv, X, n, sX, nv, theta, sTheta, alpha, sAlpha, mean, sMean, kind, dim};
   post_mean_kernel<<<dim3((m + 127) / 128, batch), 128, 0, st>>>(a);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 }  // namespace ocbo

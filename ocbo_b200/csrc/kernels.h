@@ -84,3 +84,13 @@ cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t 
 cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st);
 
 }  // namespace ocbo
+
+// process-wide count of kernel launches issued by the library (bench.py's
+// "gpu_launches"); statistics only, no behaviour depends on it
+namespace ocbo {
+extern unsigned long long g_launch_count;
+inline cudaError_t counted(cudaError_t e) {
+  __atomic_fetch_add(&g_launch_count, 1ULL, __ATOMIC_RELAXED);
+  return e;
+}
+}  // namespace ocbo

@@ -27,7 +27,7 @@ cudaError_t launch_philox_normal(double* Z, int m, int S, int ldz, int64_t sZ, u
   const uint64_t pairs = ((uint64_t)m * S + 1) / 2;
   const unsigned blocks = (unsigned)((pairs + 255) / 256);
   philox_normal_kernel<<<dim3(blocks, batch), 256, 0, st>>>(Z, m, S, ldz, sZ, seed, trial_ids);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // F[i][s] = mean_i + sum_{k<=i} L[i][k] Z[k][s] for S <= 8: one warp per row,
@@ -71,7 +71,7 @@ cudaError_t launch_sample_rowdot(const double* mean, int64_t sMean, const double
     sample_rowdot_kernel<1><<<grid, 256, 0, st>>>(mean, sMean, L, m, ldl, sL, Z, S, ldz, sZ, F, ldf, sF, info);
   else
     sample_rowdot_kernel<8><<<grid, 256, 0, st>>>(mean, sMean, L, m, ldl, sL, Z, S, ldz, sZ, F, ldf, sF, info);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // Per (problem, segment): max and FIRST argmax over rows [seg[j], seg[j+1]) of
@@ -131,7 +131,7 @@ cudaError_t launch_segment_argmax(const double* F, int S, int ldf, int64_t sF,
   while (CS * 2 <= S && CS < 256) CS *= 2;
   segment_argmax_kernel<<<dim3(nseg, batch), 256, 0, st>>>(F, S, ldf, sF, seg_ptr, nseg, out_max,
                                                            out_arg, CS);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // joint_mts.py:43-57 on the segment reductions; one thread per (problem, draw)
@@ -165,7 +165,7 @@ cudaError_t launch_joint_pick(const double* seg_max, const int32_t* seg_arg, int
   const int total = batch * S;
   joint_pick_kernel<<<(total + 127) / 128, 128, 0, st>>>(seg_max, seg_arg, nseg, n_old_seg, T, S,
                                                          out_task, out_action, out_gain, batch);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 // ------------------------------ rate probes --------------------------------
@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(double* sink, int iters
 
 cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st) {
   probe_dmma_kernel<<<blocks, 256, 0, st>>>(sink, iters);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st) {
   probe_dfma_kernel<<<blocks, 256, 0, st>>>(sink, iters);
-  return cudaGetLastError();
+  return counted(cudaGetLastError());
 }
 
 }  // namespace ocbo

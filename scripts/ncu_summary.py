@@ -1,0 +1,26 @@
+"""Summarise an .ncu-rep (ncu -i ... --page raw --csv) into the few counters we quote."""
+import csv, subprocess, sys
+WANT = [('gpu__time_duration.sum', 'dur'), ('launch__grid_size', 'grid'),
+        ('launch__registers_per_thread', 'regs'),
+        ('sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active', 'dmma_pct_active'),
+        ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct'),
+        ('dram__bytes_read.sum', 'dram_rd'), ('dram__bytes_write.sum', 'dram_wr'),
+        ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct'),
+        ('lts__t_sector_hit_rate.pct', 'l2_hit'),
+        ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ_pct'),
+        ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'st_long'),
+        ('smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'st_math'),
+        ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'st_bar'),
+        ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'st_short'),
+        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'st_wait')]
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h, u = rows[0], rows[1]
+ki = h.index('Kernel Name')
+for r in rows[2:]:
+    parts = ['%-28s' % r[ki].split('(')[0][:28]]
+    for name, short in WANT:
+        if name in h:
+            i = h.index(name)
+            parts.append('%s=%s%s' % (short, r[i][:9], u[i] if short in ('dur', 'dram_rd', 'dram_wr') else ''))
+    print('  '.join(parts))

@@ -290,6 +290,7 @@ def test_full_size_cholesky_backward_error(mods):
     torch, engine = mods['torch'], mods['engine']
     n, m, D = 1024, 8192, 6
     X, y, hp = problem(1, n, D, noise=1e-2, bw=0.25)
+    hp['bandwidths'] = np.asarray([0.25] * 4 + [0.05] * 2)  # sweep HPs: cond(Sigma) ~ 1e5
     bg = mods['gi'].make_gp(X, y, 'se', 1.0, hp['bandwidths'], 1e-2, 0.0)
     core = bg.gp_core
     rs = np.random.RandomState(2)
