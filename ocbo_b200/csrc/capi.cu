@@ -128,7 +128,7 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       p.Q = invdiag + (size_t)j * TILE * TILE; p.ldq = TILE; p.sQ = sInv;
       p.C = panel; p.ldc = lda; p.sC = s_a;
       p.ntc = 1; p.ktiles = TILE / BK; p.mode = 0; p.info = info;
-      CK(launch_gemm_nt(p, r, batch, st), "potrf panel");
+      CK(launch_gemm_nt(p, 2 * r, batch, st, 1), "potrf panel");  // 64-row tiles, full rows
       if (tm) tm->mark(st, 1);
       // inner update: the remaining columns of this outer panel, all rows below
       const int ncols = J1 - 1 - j;
@@ -137,9 +137,10 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.P = panel; u.ldp = lda; u.sP = s_a;
         u.Q = panel; u.ldq = lda; u.sQ = s_a;
         u.C = A + (size_t)(j + 1) * TILE * lda + (size_t)(j + 1) * TILE; u.ldc = lda; u.sC = s_a;
-        u.ntc = ncols; u.ktiles = TILE / BK; u.row0 = (j + 1) * TILE; u.col0 = (j + 1) * TILE;
+        u.ntc = ncols * (TILE / TN); u.ktiles = TILE / BK;
+        u.row0 = (j + 1) * TILE; u.col0 = (j + 1) * TILE;
         u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
-        CK(launch_gemm_nt(u, r * ncols, batch, st), "potrf inner update");
+        CK(launch_gemm_nt(u, r * u.ntc, batch, st), "potrf inner update");
         if (tm) tm->mark(st, 2);
       }
     }
@@ -150,8 +151,9 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       u.P = A + (size_t)J1 * TILE * lda + (size_t)J0 * TILE; u.ldp = lda; u.sP = s_a;
       u.Q = u.P; u.ldq = lda; u.sQ = s_a;
       u.C = A + (size_t)J1 * TILE * lda + (size_t)J1 * TILE; u.ldc = lda; u.sC = s_a;
-      u.ntc = R; u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1; u.info = info;
-      CK(launch_gemm_nt(u, R * (R + 1) / 2, batch, st), "potrf outer update");
+      u.ntc = R * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1;
+      u.info = info;
+      CK(launch_gemm_nt(u, R * (R + 1), batch, st), "potrf outer update");  // 2:1 lower tiles
       if (tm) tm->mark(st, 3);
     }
   }
@@ -214,7 +216,7 @@ int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* 
   if (ldb < nrhs || (ldb & 1)) return fail_arg(8, "ldb");
   if (batch <= 0) return fail_arg(11, "batch");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nt = n / TILE, ntc = nrhs / TILE;
+  const int nt = n / TILE, ntc = nrhs / TN;
   const int64_t sInv = ocbo_invdiag_elems(n);
   for (int I = 0; I < nt; ++I) {
     double* BI = B + (size_t)I * TILE * ldb;
@@ -223,14 +225,14 @@ int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* 
       u.P = L + (size_t)I * TILE * ldl; u.ldp = ldl; u.sP = s_l;
       u.R = B; u.ldr = ldb; u.sR = s_b;
       u.C = BI; u.ldc = ldb; u.sC = s_b;
-      u.ktiles = I * (TILE / BK); u.tri_k = 0; u.reverse_rows = 0; u.mode = 1; u.info = info;
+      u.ktiles = I * (TILE / BK); u.ntr = 1; u.tri_k = 0; u.pair_rows = 0; u.mode = 1; u.info = info;
       CK(launch_gemm_nn(u, 1, ntc, batch, st), "trsm update");
     }
     NnParams m{};
     m.P = invdiag + (size_t)I * TILE * TILE; m.ldp = TILE; m.sP = sInv;
     m.R = BI; m.ldr = ldb; m.sR = s_b;
     m.C = BI; m.ldc = ldb; m.sC = s_b;
-    m.ktiles = TILE / BK; m.tri_k = 0; m.reverse_rows = 0; m.mode = 0; m.info = info;
+    m.ktiles = TILE / BK; m.ntr = 1; m.tri_k = 0; m.pair_rows = 0; m.mode = 0; m.info = info;
     CK(launch_gemm_nn(m, 1, ntc, batch, st), "trsm diag");
   }
   return 0;
@@ -295,8 +297,8 @@ int ocbo_post_cov(int kind, int dim, const double* Xs, int m, int64_t s_xs, cons
   p.V2 = V; p.ldv2 = ldv; p.sV2 = s_v;
   p.theta = theta; p.sTheta = s_theta;
   p.C = Sigma; p.ldc = lds; p.sC = s_sigma;
-  p.ntc = nt; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 1; p.tri = lower_only ? 1 : 0;
-  CK(launch_postcov(p, lower_only ? nt * (nt + 1) / 2 : nt * nt, batch, (cudaStream_t)stream),
+  p.ntc = m / TN; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 1; p.tri = lower_only ? 1 : 0;
+  CK(launch_postcov(p, lower_only ? nt * (nt + 1) : nt * (m / TN), batch, (cudaStream_t)stream),
      "ocbo_post_cov");
   return 0;
 }
@@ -325,8 +327,8 @@ int ocbo_post_cross_cov(int kind, int dim, const double* Xa, int ma, int64_t s_x
   p.V2 = V2; p.ldv2 = ldv2; p.sV2 = s_v2;
   p.theta = theta; p.sTheta = s_theta;
   p.C = C; p.ldc = ldc; p.sC = s_c;
-  p.ntc = mb / TILE; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 0; p.tri = 0;
-  CK(launch_postcov(p, (ma / TILE) * (mb / TILE), batch, (cudaStream_t)stream),
+  p.ntc = mb / TN; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 0; p.tri = 0;
+  CK(launch_postcov(p, (ma / TILE) * (mb / TN), batch, (cudaStream_t)stream),
      "ocbo_post_cross_cov");
   return 0;
 }
@@ -370,15 +372,15 @@ int ocbo_sample(const double* mean, int64_t s_mean, const double* L, int m, int 
     return 0;
   }
   if (!tile_ok(m)) return fail_arg(4, "m must be a multiple of 128 on the DMMA path");
-  if (S % TILE) return fail_arg(8, "S must be <= 8 or a multiple of 128");
+  if (S % TN) return fail_arg(8, "S must be <= 8 or a multiple of 64");
   if ((ldz & 1) || (ldf & 1) || (ldl & 1)) return fail_arg(9, "leading dimensions must be even");
   NnParams p{};
   p.P = L; p.ldp = ldl; p.sP = s_l;
   p.R = Z; p.ldr = ldz; p.sR = s_z;
   p.C = F; p.ldc = ldf; p.sC = s_f;
   p.rowvec = mean; p.sRowvec = s_mean;
-  p.ktiles = m / BK; p.tri_k = 1; p.reverse_rows = 1; p.mode = 2; p.info = info;
-  CK(launch_gemm_nn(p, m / TILE, S / TILE, batch, st), "ocbo_sample dmma");
+  p.ktiles = m / BK; p.ntr = m / TILE; p.tri_k = 1; p.pair_rows = 1; p.mode = 2; p.info = info;
+  CK(launch_gemm_nn(p, (p.ntr + 1) / 2, S / TN, batch, st), "ocbo_sample dmma");
   return 0;
 }
 
@@ -429,8 +431,8 @@ int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n, ocbo
   p.P = A; p.ldp = n; p.sP = 0;
   p.Q = B; p.ldq = n; p.sQ = 0;
   p.C = C; p.ldc = n; p.sC = 0;
-  p.ntc = n / TILE; p.ktiles = n / BK; p.tri = 0; p.lower_skip = 0; p.mode = 0; p.info = nullptr;
-  CK(launch_gemm_nt(p, (n / TILE) * (n / TILE), 1, (cudaStream_t)stream), "ocbo_probe_dgemm_nt");
+  p.ntc = n / TN; p.ktiles = n / BK; p.tri = 0; p.lower_skip = 0; p.mode = 0; p.info = nullptr;
+  CK(launch_gemm_nt(p, (n / TILE) * (n / TN), 1, (cudaStream_t)stream), "ocbo_probe_dgemm_nt");
   return 0;
 }
 

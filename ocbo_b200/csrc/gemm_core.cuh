@@ -1,13 +1,20 @@
 // DMMA (FP64 tensor-core) tile GEMM core shared by every dense contraction on
-// the path: Cholesky trailing updates, panel / left triangular solves,
+// the path: Cholesky rank-k updates, panel / left triangular solves,
 // Sigma = K - V^T V, and the L*Z sampling product.
 //
-// One CTA (256 threads = 2 x 4 warps) computes a BM x BN tile; operands stream
-// through a 3-stage cp.async ring in shared memory, 16 k per stage.  Operand
-// tiles are stored in shared memory in the orientation they have in global
-// memory (no transposes); the leading dimensions (20 resp. R+4 doubles) are
-// == 4 (mod 16) so that the 16 lanes of a half-warp, reading the DMMA fragment
-// element (row = lane>>2, k = lane&3), hit 16 distinct 8-byte banks.
+// One CTA (256 threads = WARPS_M x WARPS_N warps) computes a BM x BN tile;
+// operands stream through a 3-stage cp.async ring in shared memory, 16 k per
+// stage.  The production shape is 128 x 64 with 32 x 32 warp tiles: 32 fp64
+// accumulators per thread keep the kernel under 128 registers so TWO CTAs are
+// resident per SM and the prologue / epilogue of one overlaps the DMMA main
+// loop of the other (ncu, round 1: a single 128 x 128 CTA per SM left the DMMA
+// pipe idle 21 % of the time at k = 512).
+//
+// Operand tiles are stored in shared memory in the orientation they have in
+// global memory (no transposes); the leading dimensions (20 resp. R+4 doubles)
+// are == 4 (mod 16) so that the 16 lanes of a half-warp, reading the DMMA
+// fragment element (row = lane>>2, k = lane&3), hit 16 distinct 8-byte banks
+// (ncu: 0 shared-memory bank conflicts).
 #pragma once
 #include "common.cuh"
 
@@ -49,44 +56,50 @@ struct OperandTile {
   }
 };
 
-template <int BM, int BN, bool A_KMAJ, bool B_KMAJ>
+template <int BM, int BN, bool A_KMAJ, bool B_KMAJ, int WARPS_M, int WARPS_N>
 struct Gemm {
+  static_assert(WARPS_M * WARPS_N * 32 == GEMM_THREADS, "8 warps per CTA");
   using TA = OperandTile<BM, A_KMAJ>;
   using TB = OperandTile<BN, B_KMAJ>;
   static constexpr int STAGE_DOUBLES = TA::SIZE + TB::SIZE;
   static constexpr int SMEM_DOUBLES = STAGES * STAGE_DOUBLES;
   static constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;
-  static constexpr int WM = BM / 2, WN = BN / 4;  // warp tile
-  static constexpr int MI = WM / 8, NI = WN / 8;  // 8x8 DMMA sub-tiles per warp
+  static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
+  static constexpr int MI = WM / 8, NI = WN / 8;              // 8x8 DMMA sub-tiles per warp
+  using Acc = double[MI][NI][2];
 
-  // acc += A(BM x 16*ktiles) * B(16*ktiles x BN).  A, B point at the tile origin.
-  __device__ __forceinline__ static void mainloop(const double* __restrict__ A, int lda,
-                                                  const double* __restrict__ B, int ldb,
-                                                  int ktiles, double* smem,
-                                                  double (&acc)[MI][NI][2]) {
+  __device__ __forceinline__ static void issue(const double* A, int lda, const double* B, int ldb,
+                                               int kt, double* smem, int tid) {
+    double* st = smem + (kt % STAGES) * STAGE_DOUBLES;
+    TA::load(st, TA::at_k(A, lda, kt), lda, tid);
+    TB::load(st + TA::SIZE, TB::at_k(B, ldb, kt), ldb, tid);
+  }
+
+  // Start the operand stream (first STAGES-1 k-tiles) -- callers issue this BEFORE
+  // loading the C tile so both latencies overlap.
+  __device__ __forceinline__ static void prologue(const double* A, int lda, const double* B,
+                                                  int ldb, int ktiles, double* smem) {
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    const int g = lane >> 2, t = lane & 3;
-
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < ktiles) {
-        double* st = smem + s * STAGE_DOUBLES;
-        TA::load(st, TA::at_k(A, lda, s), lda, tid);
-        TB::load(st + TA::SIZE, TB::at_k(B, ldb, s), ldb, tid);
-      }
+      if (s < ktiles) issue(A, lda, B, ldb, s, smem, tid);
       cp_async_commit();
     }
+  }
+
+  // acc += A(BM x 16*ktiles) * B(16*ktiles x BN); prologue() must have been called.
+  __device__ __forceinline__ static void mainloop(const double* __restrict__ A, int lda,
+                                                  const double* __restrict__ B, int ldb,
+                                                  int ktiles, double* smem, Acc& acc) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
     for (int kt = 0; kt < ktiles; ++kt) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       const int nk = kt + STAGES - 1;
-      if (nk < ktiles) {
-        double* st = smem + (nk % STAGES) * STAGE_DOUBLES;
-        TA::load(st, TA::at_k(A, lda, nk), lda, tid);
-        TB::load(st + TA::SIZE, TB::at_k(B, ldb, nk), ldb, tid);
-      }
+      if (nk < ktiles) issue(A, lda, B, ldb, nk, smem, tid);
       cp_async_commit();
       const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
       const double* sb = sa + TA::SIZE;
@@ -107,24 +120,36 @@ struct Gemm {
     __syncthreads();  // every warp is done with the ring: smem may be reused
   }
 
-  __device__ __forceinline__ static void zero(double (&acc)[MI][NI][2]) {
+  __device__ __forceinline__ static void zero(Acc& acc) {
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   }
 
-  // f(row_in_tile, col_in_tile (even), v0, v1): v0 at (row, col), v1 at (row, col+1)
+  // f(row_in_tile, col_in_tile (even), v0, v1): v0 at (row, col), v1 at (row, col+1);
+  // v0 / v1 are references into the accumulators.
   template <class F>
-  __device__ __forceinline__ static void foreach(double (&acc)[MI][NI][2], F f) {
+  __device__ __forceinline__ static void foreach(Acc& acc, F f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni)
         f(wm * WM + mi * 8 + g, wn * WN + ni * 8 + 2 * t, acc[mi][ni][0], acc[mi][ni][1]);
+  }
+
+  // acc = -C  (all loads issued back to back: one memory latency, overlapped with
+  // the cp.async prologue); with the DMMA accumulating P*Q on top, the epilogue
+  // stores -acc = C - P*Q without ever reading C again.
+  __device__ __forceinline__ static void load_negated(Acc& acc, const double* C, int ldc) {
+    foreach(acc, [&](int r, int c, double& v0, double& v1) {
+      const double2 o = *reinterpret_cast<const double2*>(C + (size_t)r * ldc + c);
+      v0 = -o.x;
+      v1 = -o.y;
+    });
   }
 };
 
@@ -135,6 +160,16 @@ __device__ __forceinline__ void tri_index(int t, int& ti, int& tj) {
   while (i * (i + 1) / 2 > t) --i;
   ti = i;
   tj = t - i * (i + 1) / 2;
+}
+
+// Same for 2:1 tiles (row tile = 2 column tiles wide): row ti holds the column
+// tiles tj = 0 .. 2*ti+1, i.e. everything up to the end of the diagonal block.
+__device__ __forceinline__ void tri_index_2to1(int t, int& ti, int& tj) {
+  int i = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((i + 1) * (i + 2) <= t) ++i;
+  while (i * (i + 1) > t) --i;
+  ti = i;
+  tj = t - i * (i + 1);
 }
 
 }  // namespace ocbo

@@ -1,4 +1,5 @@
 // DMMA tile kernels: C (-)= P Q^T, C (-)= P R, Sigma = K(Xa,Xb) - V1^T V2.
+// 128 x 64 tiles, 256 threads, two CTAs per SM (see gemm_core.cuh).
 #include "gemm_core.cuh"
 #include "kernels.h"
 
@@ -7,41 +8,43 @@ namespace ocbo {
 // ---------------------------------------------------------------------------
 // C_tile (mode 0: =, mode 1: -=)  P_tile * Q_tile^T
 //   P: rows follow C rows, k contiguous;  Q: rows follow C cols, k contiguous.
-// Used for the Cholesky trailing update (P = Q = L panel, mode 1) and the
-// panel solve X <- X * inv(L_jj)^T (P = X itself, Q = inv(L_jj), mode 0).
+// <128,64>: Cholesky rank-k updates (P = Q = L panel, mode 1).
+// <64,128>: panel solve X <- X * inv(L_jj)^T in place (P = X itself, Q = inv(L_jj),
+//           mode 0): the CTA owns complete rows of the 128-wide panel, so reading
+//           P over the whole k range and then overwriting it is race free.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(NtParams p) {
-  using G = Gemm<TILE, TILE, true, true>;
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(NtParams p) {
+  using G = Gemm<BM, BN, true, true, WARPS_M, WARPS_N>;
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.z;
   if (p.info && p.info[b] != 0) return;
   int ti, tj;
   if (p.tri) {
-    tri_index(blockIdx.x, ti, tj);
+    tri_index_2to1(blockIdx.x, ti, tj);
   } else {
     ti = blockIdx.x / p.ntc;
     tj = blockIdx.x % p.ntc;
-    if (p.lower_skip && p.row0 + ti * TILE + TILE - 1 < p.col0 + tj * TILE) return;
+    if (p.lower_skip && p.row0 + ti * BM + BM - 1 < p.col0 + tj * BN) return;
   }
-  const double* P = p.P + (size_t)b * p.sP + (size_t)ti * TILE * p.ldp;
-  const double* Q = p.Q + (size_t)b * p.sQ + (size_t)tj * TILE * p.ldq;
-  double* C = p.C + (size_t)b * p.sC + (size_t)ti * TILE * p.ldc + (size_t)tj * TILE;
-
-  double acc[G::MI][G::NI][2];
-  G::zero(acc);
-  G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
+  const double* P = p.P + (size_t)b * p.sP + (size_t)ti * BM * p.ldp;
+  const double* Q = p.Q + (size_t)b * p.sQ + (size_t)tj * BN * p.ldq;
+  double* C = p.C + (size_t)b * p.sC + (size_t)ti * BM * p.ldc + (size_t)tj * BN;
   const int ldc = p.ldc;
+
+  typename G::Acc acc;
+  G::prologue(P, p.ldp, Q, p.ldq, p.ktiles, smem);
   if (p.mode == 0) {
+    G::zero(acc);
+    G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
       *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(v0, v1);
     });
   } else {
+    G::load_negated(acc, C, ldc);
+    G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
-      double2* ptr = reinterpret_cast<double2*>(C + (size_t)r * ldc + c);
-      double2 o = *ptr;
-      o.x -= v0;
-      o.y -= v1;
-      *ptr = o;
+      *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(-v0, -v1);
     });
   }
 }
@@ -50,99 +53,109 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(NtParams p) {
 // C_tile (mode 0: =, 1: -=, 2: = rowvec + )  P_tile * R_tile
 //   P: rows follow C rows, k contiguous;  R: k rows, cols follow C cols.
 // Used for the left triangular solve (update + multiply by inv(L_II), in
-// place) and the sampling product F = mean + L Z (tri_k: k stops at the
-// diagonal block of the row tile).
+// place: each CTA's R tile is its own C tile) and the sampling product
+// F = mean + L Z.  tri_k: k stops at the diagonal block of the row tile;
+// pair_rows: the CTA computes row tile y and row tile ntr-1-y, so every CTA
+// of the triangular product carries the same amount of work.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nn_kernel(NnParams p) {
-  using G = Gemm<TILE, TILE, true, false>;
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
+  using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.z;
   if (p.info && p.info[b] != 0) return;
   const int tj = blockIdx.x;
-  const int ti = p.reverse_rows ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-  const double* P = p.P + (size_t)b * p.sP + (size_t)ti * TILE * p.ldp;
-  const double* R = p.R + (size_t)b * p.sR + (size_t)tj * TILE;
-  double* C = p.C + (size_t)b * p.sC + (size_t)ti * TILE * p.ldc + (size_t)tj * TILE;
-  int ktiles = p.ktiles;
-  if (p.tri_k) ktiles = min(ktiles, (ti + 1) * (TILE / BK));
-
-  double acc[G::MI][G::NI][2];
-  G::zero(acc);
-  G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
   const int ldc = p.ldc;
-  if (p.mode == 0) {
-    G::foreach(acc, [&](int r, int c, double v0, double v1) {
-      *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(v0, v1);
-    });
-  } else if (p.mode == 1) {
-    G::foreach(acc, [&](int r, int c, double v0, double v1) {
-      double2* ptr = reinterpret_cast<double2*>(C + (size_t)r * ldc + c);
-      double2 o = *ptr;
-      o.x -= v0;
-      o.y -= v1;
-      *ptr = o;
-    });
-  } else {
-    const double* rv = p.rowvec + (size_t)b * p.sRowvec + (size_t)ti * TILE;
-    G::foreach(acc, [&](int r, int c, double v0, double v1) {
-      const double mu = rv[r];
-      *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(mu + v0, mu + v1);
-    });
+  const int npass = p.pair_rows ? 2 : 1;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
+    if (pass == 1 && ti <= (int)blockIdx.y) break;
+    const double* P = p.P + (size_t)b * p.sP + (size_t)ti * BM * p.ldp;
+    const double* R = p.R + (size_t)b * p.sR + (size_t)tj * BN;
+    double* C = p.C + (size_t)b * p.sC + (size_t)ti * BM * ldc + (size_t)tj * BN;
+    int ktiles = p.ktiles;
+    if (p.tri_k) ktiles = min(ktiles, (ti + 1) * (BM / BK));
+
+    typename G::Acc acc;
+    G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
+    if (p.mode == 1) G::load_negated(acc, C, ldc);
+    else G::zero(acc);
+    G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
+    if (p.mode == 0) {
+      G::foreach(acc, [&](int r, int c, double v0, double v1) {
+        *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(v0, v1);
+      });
+    } else if (p.mode == 1) {
+      G::foreach(acc, [&](int r, int c, double v0, double v1) {
+        *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(-v0, -v1);
+      });
+    } else {
+      const double* rv = p.rowvec + (size_t)b * p.sRowvec + (size_t)ti * BM;
+      G::foreach(acc, [&](int r, int c, double v0, double v1) {
+        const double mu = rv[r];
+        *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(mu + v0, mu + v1);
+      });
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
 // C_tile = K(Xa_i, Xb_j) - sum_k V1[k][i] V2[k][j]     (posterior covariance)
 //   V1: n x ma, V2: n x mb row-major (k rows).  sym: Xa == Xb, V1 == V2,
-//   padding diagonal = 1; lower_only skips tiles above the diagonal.
+//   padding diagonal = 1; tri: lower-triangular tiles only (2:1 mapping).
 // The Gram term is evaluated in the epilogue from points staged (pre-scaled by
 // 1/bandwidth) in the drained cp.async ring, so K(Xs,Xs) never exists in HBM.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) postcov_kernel(CovParams p) {
-  using G = Gemm<TILE, TILE, false, false>;
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
+  using G = Gemm<BM, BN, false, false, WARPS_M, WARPS_N>;
+  static_assert(G::SMEM_DOUBLES >= MAXD * (BM + BN), "ring too small for the point staging");
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.z;
   int ti, tj;
   if (p.tri) {
-    tri_index(blockIdx.x, ti, tj);
+    tri_index_2to1(blockIdx.x, ti, tj);
   } else {
     ti = blockIdx.x / p.ntc;
     tj = blockIdx.x % p.ntc;
   }
-  const double* V1 = p.V1 + (size_t)b * p.sV1 + (size_t)ti * TILE;
-  const double* V2 = p.V2 + (size_t)b * p.sV2 + (size_t)tj * TILE;
-  double* C = p.C + (size_t)b * p.sC + (size_t)ti * TILE * p.ldc + (size_t)tj * TILE;
+  const double* V1 = p.V1 + (size_t)b * p.sV1 + (size_t)ti * BM;
+  const double* V2 = p.V2 + (size_t)b * p.sV2 + (size_t)tj * BN;
+  double* C = p.C + (size_t)b * p.sC + (size_t)ti * BM * p.ldc + (size_t)tj * BN;
 
-  double acc[G::MI][G::NI][2];
+  typename G::Acc acc;
   G::zero(acc);
+  G::prologue(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem);
   G::mainloop(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem, acc);
 
-  // stage scaled points: xa[d][128], xb[d][128]
+  // stage scaled points: xa[d][BM], xb[d][BN]
   const int D = p.dim;
   const double* th = p.theta + (size_t)b * p.sTheta;
   const double scale = th[TH_SCALE];
   double* xa = smem;
-  double* xb = smem + MAXD * TILE;
-  const double* Xa = p.Xa + (size_t)b * p.sXa + (size_t)ti * TILE * D;
-  const double* Xb = p.Xb + (size_t)b * p.sXb + (size_t)tj * TILE * D;
-  for (int e = threadIdx.x; e < TILE * D; e += GEMM_THREADS) {
+  double* xb = smem + MAXD * BM;
+  const double* Xa = p.Xa + (size_t)b * p.sXa + (size_t)ti * BM * D;
+  const double* Xb = p.Xb + (size_t)b * p.sXb + (size_t)tj * BN * D;
+  for (int e = threadIdx.x; e < BM * D; e += GEMM_THREADS) {
     const int r = e / D, d = e % D;
-    const double bw = th[TH_BW + d];
-    xa[d * TILE + r] = Xa[e] / bw;
-    xb[d * TILE + r] = Xb[e] / bw;
+    xa[d * BM + r] = Xa[e] / th[TH_BW + d];
+  }
+  for (int e = threadIdx.x; e < BN * D; e += GEMM_THREADS) {
+    const int r = e / D, d = e % D;
+    xb[d * BN + r] = Xb[e] / th[TH_BW + d];
   }
   __syncthreads();
   const int mav = p.mav ? p.mav[b] : p.ma;
   const int mbv = p.mbv ? p.mbv[b] : p.mb;
-  const int row0 = ti * TILE, col0 = tj * TILE;
+  const int row0 = ti * BM, col0 = tj * BN;
   const int kind = p.kind, sym = p.sym, ldc = p.ldc;
   G::foreach(acc, [&](int r, int c, double v0, double v1) {
     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
     for (int d = 0; d < MAXD; ++d) {
       if (d < D) {
-        const double xr = xa[d * TILE + r];
-        const double2 xc = *reinterpret_cast<const double2*>(xb + d * TILE + c);
+        const double xr = xa[d * BM + r];
+        const double2 xc = *reinterpret_cast<const double2*>(xb + d * BN + c);
         const double e0 = xr - xc.x, e1 = xr - xc.y;
         d0 = fma(e0, e0, d0);
         d1 = fma(e1, e1, d1);
@@ -160,47 +173,50 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) postcov_kernel(CovParams p) {
 
 // ------------------------------- launchers ---------------------------------
 template <class K>
-static cudaError_t ensure_smem(K kernel, int bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+static cudaError_t ensure_smem(K kernel, int bytes, bool& done) {
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) done = true;
+  return e;
 }
 
-cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st) {
-  using G = Gemm<TILE, TILE, true, true>;
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = ensure_smem(gemm_nt_kernel, G::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
+cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st, int panel) {
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
-  gemm_nt_kernel<<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  if (panel) {
+    using G = Gemm<TM / 2, TILE, true, true, 2, 4>;
+    static bool init = false;
+    cudaError_t e = ensure_smem(gemm_nt_kernel<TM / 2, TILE, 2, 4>, G::SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    gemm_nt_kernel<TM / 2, TILE, 2, 4><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  } else {
+    using G = Gemm<TM, TN, true, true, 4, 2>;
+    static bool init = false;
+    cudaError_t e = ensure_smem(gemm_nt_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    gemm_nt_kernel<TM, TN, 4, 2><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  }
   return counted(cudaGetLastError());
 }
 
-cudaError_t launch_gemm_nn(const NnParams& p, int ntr, int ntc, int batch, cudaStream_t st) {
-  using G = Gemm<TILE, TILE, true, false>;
+cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch, cudaStream_t st) {
+  using G = Gemm<TM, TN, true, false, 4, 2>;
   static bool init = false;
-  if (!init) {
-    cudaError_t e = ensure_smem(gemm_nn_kernel, G::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
-  if (ntr <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
-  gemm_nn_kernel<<<dim3(ntc, ntr, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  cudaError_t e = ensure_smem(gemm_nn_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
+  if (grid_rows <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
+  gemm_nn_kernel<TM, TN, 4, 2><<<dim3(ntc, grid_rows, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
   return counted(cudaGetLastError());
 }
 
 cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
-  using G = Gemm<TILE, TILE, false, false>;
-  static_assert(G::SMEM_DOUBLES >= 2 * MAXD * TILE, "ring too small for the point staging");
+  using G = Gemm<TM, TN, false, false, 4, 2>;
   static bool init = false;
-  if (!init) {
-    cudaError_t e = ensure_smem(postcov_kernel, G::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
+  cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
-  postcov_kernel<<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  postcov_kernel<TM, TN, 4, 2><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
   return counted(cudaGetLastError());
 }
 

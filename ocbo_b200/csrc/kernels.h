@@ -9,7 +9,7 @@ struct NtParams {  // C (=|-=) P Q^T ; all pointers pre-offset to the region ori
   const double* P; int ldp; int64_t sP;
   const double* Q; int ldq; int64_t sQ;
   double* C; int ldc; int64_t sC;
-  int ntc;         // column tiles of a rectangular region
+  int ntc;         // column tiles (of the kernel's BN) of a rectangular region
   int ktiles;      // k extent / 16
   int row0, col0;  // global element coordinates of the region origin (diagonal test)
   int tri;         // grid.x enumerates the lower-triangular tiles of a square region
@@ -24,8 +24,9 @@ struct NnParams {  // C (=|-=|= rowvec +) P R
   double* C; int ldc; int64_t sC;
   const double* rowvec; int64_t sRowvec;
   int ktiles;
+  int ntr;           // row tiles of the product (pair_rows)
   int tri_k;         // k stops at the diagonal block of the row tile (L lower)
-  int reverse_rows;  // heavy row tiles first
+  int pair_rows;     // CTA y computes row tiles y and ntr-1-y (balanced triangular product)
   int mode;          // 0 set, 1 sub, 2 rowvec + acc
   const int32_t* info;
 };
@@ -40,8 +41,9 @@ struct CovParams {  // C = K(Xa, Xb) - V1^T V2
   int ntc, ktiles, dim, kind, sym, tri;
 };
 
-cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st);
-cudaError_t launch_gemm_nn(const NnParams& p, int ntr, int ntc, int batch, cudaStream_t st);
+// panel = 0: 128 x 64 tiles (updates); panel = 1: 64 x 128 tiles (in-place panel solve)
+cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st, int panel = 0);
+cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch, cudaStream_t st);
 cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st);
 
 cudaError_t launch_gram(int kind, int dim, const double* X1, int n1, int64_t sX1, const int32_t* nv1,

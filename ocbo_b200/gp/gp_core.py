@@ -153,9 +153,32 @@ class B200GPCore(object):
         self.chol_jitter = post.jitter[0]
 
     def add_data_single(self, x, y):
+        """Append one observation.  Dragonfly rebuilds the posterior here; the
+        rebuild is deferred until something reads the posterior (``alpha`` is
+        None meanwhile, which is what the reference's wrapper tests, :87)."""
         self.X.append(np.asarray(x, dtype=np.float64).ravel())
         self.Y.append(float(y))
-        self.build_posterior()
+        self._post = None
+
+    def sample_and_pick(self, to_samp, seg_ptr, num_tasks):
+        """One joint posterior sample at ``to_samp`` reduced ON THE DEVICE to the
+        joint-MTS pick (src/strategies/joint_mts.py:42-57): ``seg_ptr`` holds the
+        row offsets of the T old-point segments followed by the T grid segments.
+        Returns (task, action index, gain)."""
+        Xd, mv_dev, mv, mean, V, Sigma = self._posterior_at(to_samp, True, True)
+        post = self._post
+
+        def reassemble(b0, b1):
+            post.cov(Xd, mv_dev, V, True, out=Sigma, b0=b0, b1=b1)
+
+        m, m_pad = mv[0], Sigma.shape[1]
+        _, info, jit = engine.factor_covariance(None, Sigma, mv_dev, mv, reassemble)
+        self.last_sample_jitter = jit[0]
+        Z = engine.pad_normals([rng.normals((m, 1))], mv, m_pad, 1)
+        Fm = engine.sample_from_factor(mean, Sigma, Z, info)
+        mx, ag = engine.segment_argmax(Fm, 1, np.asarray(seg_ptr, dtype=np.int32)[None, :])
+        task, act, gain = engine.joint_pick(mx, ag, num_tasks, num_tasks)
+        return int(task[0, 0].item()), int(act[0, 0].item()), float(gain[0, 0].item())
 
     def compute_log_marginal_likelihood(self):
         if self._post is None:

@@ -142,10 +142,12 @@ class B200GPFitter(GPFitterWrapper):
                           build_posterior=build)
 
     def get_next_gp(self):
-        """:127-133 -- next hyper-parameter draw, posterior built."""
+        """:127-133 -- next hyper-parameter draw.  The posterior is built on first
+        use (eval / draw_sample / build_posterior): the batched strategies rebuild
+        all tasks' posteriors in one device pass and never need the per-GP one."""
         theta = self.hp_list[self._next % len(self.hp_list)]
         self._next += 1
-        return B200GP(self._make_core(theta, True), self.options)
+        return B200GP(self._make_core(theta, False), self.options)
 
 
 def make_gp(X, Y, kernel_type, scale, bandwidths, noise_var, mu0, matern_nu=2.5, options=None,

@@ -1,0 +1,65 @@
+"""Generate tests/golden/mts_traces.json by running the REFERENCE's own,
+unmodified strategy classes (/root/reference/src, imported where it lies) on
+top of the numpy oracle, for the scenarios in tests/scenarios.py.
+
+Run in the build container only (the GPU box has no /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+import numpy as np  # noqa: E402
+
+from oracle import gp_numpy, refshim  # noqa: E402
+from tests import scenarios as sc  # noqa: E402
+
+
+def main():
+    refshim.install()
+    from strategies.mts import MTS
+    from strategies.joint_mts import JointMTS
+    from cstrats.profile_cts import CMTSPM, ContinuousMultiTaskTS
+    from util.misc_util import assemble_functions
+    from synth.continuous_2d import assemble_chopped_1d_functions
+    from synth.function_generator import get_easy_mass_functions, get_hard_mass_functions, \
+        get_med_mass_functions
+    from synth.sixd import hartmann6
+
+    out = {}
+    for name, cfg in sc.DISCRETE.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        if 'functions' in cfg:
+            f_infos = assemble_functions(cfg['functions'])
+        elif 'cts_f' in cfg:
+            f_infos = assemble_chopped_1d_functions(cfg['cts_f'], cfg['num_chops'])
+        else:
+            easy, med, hard = cfg['masses']
+            domain = [[0, 1] for _ in range(cfg['massf_dim'])]
+            f_infos = get_hard_mass_functions(hard, domain, None) + \
+                get_med_mass_functions(med, domain, None) + get_easy_mass_functions(easy, domain, None)
+        cls = MTS if cfg['kind'] == 'mts' else JointMTS
+        out[name] = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'dragonfly'))
+        print(name, out[name]['choice_timeline'])
+    for name, cfg in sc.CONTINUOUS.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        domain = [[0, 1] for _ in range(6)]
+        cls = ContinuousMultiTaskTS if cfg['kind'] == 'cmts' else CMTSPM
+        out[name] = sc.run_continuous(cfg, cls, hartmann6, domain,
+                                      sc.continuous_options(cfg, 'dragonfly'))
+        print(name, np.round(out[name]['regret'], 4).tolist())
+    path = os.path.join(ROOT, 'tests', 'golden', 'mts_traces.json')
+    with open(path, 'w') as fh:
+        json.dump(out, fh, indent=1)
+    print('wrote', path)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,99 @@
+"""End-to-end MTS selections: ocbo_b200's strategies on the B200 engine against
+golden traces produced by the REFERENCE's own strategy classes on the numpy
+oracle (tests/golden/make_golden.py), same global seed, same consumption of the
+numpy stream.  Picks must match exactly (north_star: "selected task/action
+indices bit-exact apart from documented ties"); query points to 1e-9."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'mts_traces.json')
+
+
+@pytest.fixture(scope='module')
+def golden():
+    with open(GOLDEN) as fh:
+        return json.load(fh)
+
+
+def _functions(cfg):
+    from ocbo_b200 import synth
+    if 'functions' in cfg:
+        return synth.assemble_functions(cfg['functions'])
+    if 'cts_f' in cfg:
+        return synth.assemble_chopped_1d_functions(cfg['cts_f'], cfg['num_chops'])
+    easy, med, hard = cfg['masses']
+    return synth.random_mass_functions(easy, med, hard, cfg['massf_dim'])
+
+
+@pytest.mark.parametrize('name', sorted(sc.DISCRETE))
+def test_discrete_mts_reproduces_reference_selections(golden, name):
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    from ocbo_b200.strategies import strategies
+    cfg = sc.DISCRETE[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    f_infos = _functions(cfg)
+    cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
+    got = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'b200'))
+    ref = golden[name]
+    assert got['choice_timeline'] == ref['choice_timeline']
+    assert np.max(np.abs(np.asarray(got['points']) - np.asarray(ref['points']))) <= 1e-9
+    assert np.max(np.abs(np.asarray(got['values']) - np.asarray(ref['values']))) <= 1e-9
+    assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', sorted(sc.CONTINUOUS))
+def test_continuous_mts_reproduces_reference_selections(golden, name):
+    from ocbo_b200 import synth
+    from ocbo_b200.cstrats import cstrats
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    cfg = sc.CONTINUOUS[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    cls = [s.impl for s in cstrats if s.name == cfg['kind']][0]
+    domain = [[0, 1] for _ in range(6)]
+    got = sc.run_continuous(cfg, cls, synth.hartmann6, domain, sc.continuous_options(cfg, 'b200'))
+    ref = golden[name]
+    assert np.max(np.abs(np.asarray(got['points']) - np.asarray(ref['points']))) <= 1e-9
+    assert np.max(np.abs(np.asarray(got['rewards']) - np.asarray(ref['rewards']))) <= 1e-9
+    assert np.max(np.abs(np.asarray(got['regret']) - np.asarray(ref['regret']))) <= 1e-9
+
+
+def test_reference_strategy_classes_drive_the_b200_engine():
+    """Drop-in at the GP seam: a strategy written against the reference's
+    GPWrapper API (per-task eval / draw_sample loop, as src/strategies/mts.py does)
+    gets the same answers from B200GP as from the oracle wrapper."""
+    from oracle import gp_numpy as o
+    from ocbo_b200 import rng
+    from ocbo_b200.gp.gp_interface import make_gp
+    from tests.util import problem
+    X, y, hp = problem(3, 25, 2, bw=0.2)
+    og = o.make_gp(X, y, 'se', 1.0, hp['bandwidths'], 1e-2, 0.0)
+    bg = make_gp(X, y, 'se', 1.0, hp['bandwidths'], 1e-2, 0.0)
+    rs = np.random.RandomState(0)
+    pts = np.vstack([X, rs.uniform(size=(100, 2))])
+    z = rs.normal(size=(len(pts), 1))
+    o.NORMAL_SOURCE = lambda size: z.reshape(size)
+    rng.NORMAL_SOURCE = lambda size: z.reshape(size)
+    try:
+        for gp in (og, bg):
+            gp.build_posterior()
+        so, sb = og.draw_sample(samp_pts=pts).ravel(), bg.draw_sample(samp_pts=pts).ravel()
+    finally:
+        o.NORMAL_SOURCE = None
+        rng.NORMAL_SOURCE = None
+    assert int(np.argmax(sb[25:])) == int(np.argmax(so[25:]))
+    assert abs((sb[25:].max() - sb[:25].max()) - (so[25:].max() - so[:25].max())) <= 1e-5
+    bg.add_data_single(pts[30], 0.3)
+    og.add_data_single(pts[30], 0.3)
+    assert bg.gp_core.alpha is None  # rebuilt lazily
+    bg.build_posterior()
+    assert np.max(np.abs(bg.gp_core.alpha - og.gp_core.alpha)) <= 1e-8 * np.max(np.abs(og.gp_core.alpha))
+    assert set(bg.get_kernel_hps()) == set(og.get_kernel_hps()) == {'scale', 'lengthscale'}
+    assert bg.get_estimated_noise() == og.get_estimated_noise() == 1e-2

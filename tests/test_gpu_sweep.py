@@ -1,0 +1,59 @@
+"""Sweep step (BASELINE configs[4] shape family) against the oracle, and the
+world-size invariance of the trial-indexed device RNG."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sweep_step_matches_oracle_small():
+    import torch
+    from ocbo_b200 import sweep
+    from oracle import philox, sweep_step
+    n, T, A, S = 256, 8, 128, 128
+    step = sweep.SweepStep(n, T, A, S, 6, batch=2)
+    trials = [5, 12]
+    inputs = [sweep.make_trial_inputs(t, n, T, A) for t in trials]
+    task, act, gain = step.step_host(trials, inputs)
+    F = step.F.cpu().numpy()
+    mean = step.mean.cpu().numpy()
+    for b, t in enumerate(trials):
+        X, y, Xs = inputs[b]
+        Z = philox.normals(sweep.SEED, t, T * A, S)
+        t_ref, a_ref, g_ref, F_ref, mu, var = sweep_step.step(X, y, Xs, T, S, Z=Z, return_samples=True)
+        assert np.max(np.abs(mean[b] - mu)) <= 1e-8 * np.max(np.abs(mu))
+        assert np.max(np.abs(F[b].T - F_ref)) <= 1e-8 * np.max(np.abs(F_ref))
+        assert np.array_equal(task[b], t_ref) and np.array_equal(act[b], a_ref)
+        assert np.max(np.abs(gain[b] - g_ref)) <= 1e-8 * np.max(np.abs(g_ref))
+
+
+def test_sweep_results_do_not_depend_on_batching_or_stream():
+    """Trial r gives the same picks whether it runs alone, in a batch, or on a
+    side stream -- the property that makes 1/2/4/8-GPU runs agree."""
+    import torch
+    from ocbo_b200 import sweep
+    n, T, A, S = 128, 4, 128, 64
+    inp = {t: sweep.make_trial_inputs(t, n, T, A) for t in (0, 1, 2)}
+    solo = {}
+    for t in inp:
+        st = sweep.SweepStep(n, T, A, S, 6, batch=1)
+        solo[t] = st.step_host([t], [inp[t]])
+    st3 = sweep.SweepStep(n, T, A, S, 6, batch=3, stream=torch.cuda.Stream())
+    task, act, gain = st3.step_host([2, 0, 1], [inp[2], inp[0], inp[1]])
+    for b, t in enumerate([2, 0, 1]):
+        assert np.array_equal(task[b], solo[t][0][0])
+        assert np.array_equal(act[b], solo[t][1][0])
+        assert np.array_equal(gain[b], solo[t][2][0])
+
+
+def test_run_sweep_single_process_gather():
+    from ocbo_b200 import dist as odist
+    from ocbo_b200 import sweep
+    n, T, A, S = 128, 4, 128, 64
+    res = odist.run_sweep(5, lambda s: sweep.SweepStep(n, T, A, S, 6, batch=2, stream=s),
+                          lambda t: sweep.make_trial_inputs(t, n, T, A), streams=2, batch=2)
+    task, act, gain = res
+    assert task.shape == (5, S) and (task >= 0).all() and (act >= 0).all() and np.isfinite(gain).all()
+    st = sweep.SweepStep(n, T, A, S, 6, batch=1)
+    t3 = st.step_host([3], [sweep.make_trial_inputs(3, n, T, A)])
+    assert np.array_equal(task[3], t3[0][0]) and np.array_equal(act[3], t3[1][0])
