@@ -68,8 +68,13 @@ class SharedPosterior(object):
     def __init__(self, post, B):
         self.B, self.D, self.kind, self.n_pad = B, post.D, post.kind, post.n_pad
         ex = lambda t: t.expand(B, *t.shape[1:])
-        self.X, self.y, self.theta, self.nv = ex(post.X), ex(post.y), ex(post.theta), ex(post.nv)
-        self.L, self.invd, self.alpha, self.info = ex(post.L), ex(post.invd), ex(post.alpha), ex(post.info)
+        # operands addressed through an explicit batch stride are shared (stride 0) ...
+        self.X, self.y, self.theta = ex(post.X), ex(post.y), ex(post.theta)
+        self.L, self.alpha = ex(post.L), ex(post.alpha)
+        # ... the per-problem arrays the kernels index as a[b] must be real
+        self.nv = post.nv.repeat(B)
+        self.info = torch.zeros((B,), dtype=engine.I32, device=post.L.device)
+        self.invd = post.invd.repeat(B, 1, 1, 1)  # batch stride of invdiag is implicit in the ABI
         self.nv_host = post.nv_host * B
 
     upload_points = DevicePosterior.upload_points

@@ -300,7 +300,7 @@ def joint_pick(mx, ag, n_old_seg, T):
 
 def pad_normals(Z_list, mv, m_pad, S):
     """Host normals [(m_b, S)] -> device [B, m_pad, S_pad] (zero padded)."""
-    S_pad = S if S <= 8 else pad_to(S)
+    S_pad = S if S <= 8 else pad_to(S, 64)
     Zh = np.zeros((len(Z_list), m_pad, S_pad))
     for b, z in enumerate(Z_list):
         Zh[b, :mv[b], :S] = np.asarray(z, dtype=np.float64).reshape(mv[b], S)

@@ -75,8 +75,8 @@ class SweepStep(object):
         engine.require_cuda()
         if n % TILE or (T * A) % TILE:
             raise ValueError('n and T*A must be multiples of %d' % TILE)
-        if S > 8 and S % TILE:
-            raise ValueError('S must be <= 8 or a multiple of %d' % TILE)
+        if S > 8 and S % 64:
+            raise ValueError('S must be <= 8 or a multiple of 64')
         self.n, self.T, self.A, self.S, self.D, self.B = n, T, A, S, dim, batch
         self.m = T * A
         self.kind = engine.kernel_kind(kernel_type)

@@ -21,6 +21,7 @@ from scipy.linalg import solve_triangular
 # Dragonfly's draw_gaussian_samples.  Tests that inject
 # identical normals into the oracle and the CUDA path replace this hook.
 NORMAL_SOURCE = None  # callable(size)->ndarray, or None for np.random.normal
+TRACE = None  # list collecting every draw (jitter rung, sample) while golden vectors are made
 
 
 def _normals(size):
@@ -156,9 +157,24 @@ def draw_gaussian_samples(num_samples, mu, K):
     """Appendix A ``draw_gaussian_samples``: L = stable_cholesky(K);
     U ~ N(0,1)^(m x S); return (L U)^T + mu, shape (S, m)."""
     mu = np.asarray(mu, dtype=np.float64).ravel()
-    L = stable_cholesky(K)
+    L, p = stable_cholesky(K, return_jitter=True)
     U = _normals((len(mu), num_samples))
-    return L.dot(U).T + mu
+    out = L.dot(U).T + mu
+    if TRACE is not None:  # golden-vector generation only
+        # How well-defined is this sample?  Re-factor one jitter rung higher and see how
+        # far the SAME normals land: on numerically semidefinite covariances a tiny lucky
+        # pivot amplifies rounding noise (column = residual / sqrt(pivot)), so the
+        # reference's own sample can move by O(1) between adjacent rungs.
+        md = float(np.max(np.diag(K))) if len(mu) else 0.0
+        p_next = (-12 if p is None else p) + 1
+        try:
+            L2 = np.linalg.cholesky(np.asarray(K) + (10.0 ** p_next) * md * np.eye(len(mu)))
+            sens = float(np.max(np.abs(L2.dot(U) - L.dot(U))))
+        except np.linalg.LinAlgError:
+            sens = float('inf')
+        TRACE.append(dict(jitter_p=p, max_diag=md, rung_sens=sens, mean=mu.copy(),
+                          sample=out[0].copy(), z_max=float(np.max(np.abs(U)))))
+    return out
 
 
 # --- the GP (Appendix A build_posterior / eval / draw_samples / add_data) -----

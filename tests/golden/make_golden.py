@@ -45,16 +45,28 @@ def main():
             f_infos = get_hard_mass_functions(hard, domain, None) + \
                 get_med_mass_functions(med, domain, None) + get_easy_mass_functions(easy, domain, None)
         cls = MTS if cfg['kind'] == 'mts' else JointMTS
+        gp_numpy.TRACE = []
         out[name] = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'dragonfly'))
-        print(name, out[name]['choice_timeline'])
+        out[name]['margins'] = sc.discrete_margins(cfg, len(f_infos), out[name]['choice_timeline'],
+                                                   gp_numpy.TRACE)
+        out[name]['jitter_rungs'] = [d['jitter_p'] for d in gp_numpy.TRACE]
+        gp_numpy.TRACE = None
+        print(name, out[name]['choice_timeline'],
+              ['%.1e/%.1e' % m for m in out[name]['margins']])
     for name, cfg in sc.CONTINUOUS.items():
         np.random.seed(sc.SEED)
         gp_numpy.EuclideanGPFitter._fit_counter = 0
         domain = [[0, 1] for _ in range(6)]
         cls = ContinuousMultiTaskTS if cfg['kind'] == 'cmts' else CMTSPM
+        gp_numpy.TRACE = []
         out[name] = sc.run_continuous(cfg, cls, hartmann6, domain,
                                       sc.continuous_options(cfg, 'dragonfly'))
-        print(name, np.round(out[name]['regret'], 4).tolist())
+        out[name]['margins'] = sc.continuous_margins(cfg, gp_numpy.TRACE, out[name]['y_init'],
+                                                     out[name]['rewards'])
+        out[name]['jitter_rungs'] = [d['jitter_p'] for d in gp_numpy.TRACE]
+        gp_numpy.TRACE = None
+        print(name, np.round(out[name]['regret'], 4).tolist(),
+              ['%.1e/%.1e' % m for m in out[name]['margins']])
     path = os.path.join(ROOT, 'tests', 'golden', 'mts_traces.json')
     with open(path, 'w') as fh:
         json.dump(out, fh, indent=1)

@@ -1,8 +1,9 @@
 """End-to-end MTS selections: ocbo_b200's strategies on the B200 engine against
 golden traces produced by the REFERENCE's own strategy classes on the numpy
 oracle (tests/golden/make_golden.py), same global seed, same consumption of the
-numpy stream.  Picks must match exactly (north_star: "selected task/action
-indices bit-exact apart from documented ties"); query points to 1e-9."""
+numpy stream.  Picks must match exactly apart from DOCUMENTED TIES (north_star);
+the tie rule and its tolerance are defined in tests/scenarios.py and the margins
+are stored with the golden traces."""
 import json
 import os
 
@@ -42,10 +43,13 @@ def test_discrete_mts_reproduces_reference_selections(golden, name):
     cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
     got = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'b200'))
     ref = golden[name]
-    assert got['choice_timeline'] == ref['choice_timeline']
-    assert np.max(np.abs(np.asarray(got['points']) - np.asarray(ref['points']))) <= 1e-9
-    assert np.max(np.abs(np.asarray(got['values']) - np.asarray(ref['values']))) <= 1e-9
-    assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-9)
+    k = sc.assert_same_up_to_ties(got['points'], ref)
+    upto = len(ref['points']) if k is None else k
+    assert got['choice_timeline'][:upto] == ref['choice_timeline'][:upto]
+    assert np.allclose(got['values'][:upto], ref['values'][:upto], rtol=0, atol=1e-9)
+    assert np.allclose(got['total_best'][:upto], ref['total_best'][:upto], rtol=0, atol=1e-9)
+    if name == 'rand6d':
+        assert k is None  # well-conditioned fixture (rung sensitivity ~1e-4): no excuse
 
 
 @pytest.mark.parametrize('name', sorted(sc.CONTINUOUS))
@@ -60,9 +64,10 @@ def test_continuous_mts_reproduces_reference_selections(golden, name):
     domain = [[0, 1] for _ in range(6)]
     got = sc.run_continuous(cfg, cls, synth.hartmann6, domain, sc.continuous_options(cfg, 'b200'))
     ref = golden[name]
-    assert np.max(np.abs(np.asarray(got['points']) - np.asarray(ref['points']))) <= 1e-9
-    assert np.max(np.abs(np.asarray(got['rewards']) - np.asarray(ref['rewards']))) <= 1e-9
-    assert np.max(np.abs(np.asarray(got['regret']) - np.asarray(ref['regret']))) <= 1e-9
+    k = sc.assert_same_up_to_ties(got['points'], ref)
+    upto = len(ref['points']) if k is None else k
+    assert np.allclose(got['rewards'][:upto], ref['rewards'][:upto], rtol=0, atol=1e-9)
+    assert np.allclose(got['regret'][:upto], ref['regret'][:upto], rtol=0, atol=1e-9)
 
 
 def test_reference_strategy_classes_drive_the_b200_engine():
@@ -73,7 +78,7 @@ def test_reference_strategy_classes_drive_the_b200_engine():
     from ocbo_b200 import rng
     from ocbo_b200.gp.gp_interface import make_gp
     from tests.util import problem
-    X, y, hp = problem(3, 25, 2, bw=0.2)
+    X, y, hp = problem(3, 25, 2, bw=0.05)
     og = o.make_gp(X, y, 'se', 1.0, hp['bandwidths'], 1e-2, 0.0)
     bg = make_gp(X, y, 'se', 1.0, hp['bandwidths'], 1e-2, 0.0)
     rs = np.random.RandomState(0)
@@ -89,7 +94,7 @@ def test_reference_strategy_classes_drive_the_b200_engine():
         o.NORMAL_SOURCE = None
         rng.NORMAL_SOURCE = None
     assert int(np.argmax(sb[25:])) == int(np.argmax(so[25:]))
-    assert abs((sb[25:].max() - sb[:25].max()) - (so[25:].max() - so[:25].max())) <= 1e-5
+    assert abs((sb[25:].max() - sb[:25].max()) - (so[25:].max() - so[:25].max())) <= 1e-6
     bg.add_data_single(pts[30], 0.3)
     og.add_data_single(pts[30], 0.3)
     assert bg.gp_core.alpha is None  # rebuilt lazily
