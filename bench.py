@@ -41,7 +41,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=6)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--streams', type=int, default=4, help='concurrent trial groups per GPU')
+    ap.add_argument('--streams', type=int, default=8, help='concurrent trial groups per GPU')
     ap.add_argument('--batch', type=int, default=1, help='trials per kernel launch (grid.z)')
     ap.add_argument('--cpu-trials', type=int, default=2, help='trials timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -361,7 +361,7 @@ def run_b200(args):
             'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
                            'MEASURED_PEAKS.json has no FP64 row',
             'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],
-                         'outer_update': ms3[3], 'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 512))},
+                         'outer_update': ms3[3], 'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 1024))},
             'step_tflops_per_gpu': step_tflops / world,
             'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,

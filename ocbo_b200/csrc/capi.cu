@@ -83,7 +83,7 @@ int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* n
 }
 
 // Two-level blocked right-looking Cholesky.  Outer panels of `outer` columns
-// (OCBO_POTRF_OUTER, default 512) are factored with 128-wide steps whose
+// (OCBO_POTRF_OUTER, default 1024) are factored with 128-wide steps whose
 // rank-128 updates stay inside the panel (L2-resident); the trailing matrix is
 // then updated ONCE per outer panel with a rank-`outer` DMMA update, so the
 // bulk of the m^3/3 flops runs with long k and touches each C tile once per
@@ -102,7 +102,7 @@ static int potrf_outer_tiles(int nt) {
   static int outer = -1;
   if (outer < 0) {
     const char* e = getenv("OCBO_POTRF_OUTER");
-    int v = e ? atoi(e) : 512;
+    int v = e ? atoi(e) : 1024;
     if (v < TILE) v = TILE;
     outer = v / TILE;
   }
