@@ -1,6 +1,8 @@
 // Diagonal-block Cholesky + triangular inverse, and the alpha / LML solve.
 // These are the latency-bound (one CTA per problem) pieces of the path; the
 // flops live in the DMMA kernels of gemm_kernels.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -160,6 +162,14 @@ potrf_diag_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, int64
 
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
                               int64_t sInv, int32_t* info, int batch, cudaStream_t st) {
+  // default: register-resident kernel (potrf_diag_reg.cu); OCBO_DIAG_KERNEL=smem keeps
+  // the shared-memory version selectable for A/B measurements
+  static int use_smem = -1;
+  if (use_smem < 0) {
+    const char* e = getenv("OCBO_DIAG_KERNEL");
+    use_smem = (e && e[0] == 's') ? 1 : 0;
+  }
+  if (!use_smem) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st);
   constexpr int SMEM = (NB * LDS_ + 2 * NB + MB * LDS_) * 8;
   static bool init = false;
   if (!init) {
