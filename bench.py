@@ -38,7 +38,7 @@ UNIT = 'samples/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=6)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--streams', type=int, default=8, help='concurrent trial groups per GPU')
@@ -115,10 +115,38 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
+def load_traffic(batch):
+    """DRAM bytes (read + write) of the DMMA update launches of one trial-step, from the
+    committed ncu capture (profiles/traffic.json); scaled by the batch.  None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        return {'dram_bytes': t['dram_bytes'] * batch, 'launches': t['launches'],
+                'scope': t['scope'], 'source': t['source']}
+    except Exception:
+        return None
+
+
+_BLAS_LIMIT = []
+
+
+def use_all_blas_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    if _BLAS_LIMIT:
+        return
+    try:
+        from threadpoolctl import threadpool_limits
+        _BLAS_LIMIT.append(threadpool_limits(limits=os.cpu_count() or 1, user_api='blas'))
+    except Exception:
+        _BLAS_LIMIT.append(None)
+
+
 def cpu_step_seconds(trial):
     """One full-size trial-step of the CPU restatement (numpy + LAPACK, all BLAS threads)."""
     from oracle import sweep_step
     from ocbo_b200.sweep import make_trial_inputs
+    use_all_blas_threads()
     X, y, Xs = make_trial_inputs(trial, N_OBS, N_TASK, N_ACT)
     np.random.seed(trial)
     t0 = time.perf_counter()
@@ -357,7 +385,7 @@ def run_b200(args):
             'bound': 'tensor', 'kernel': 'gemm_nt_kernel (Cholesky rank-k updates of chol(Sigma), DMMA.8x8x4 fp64)',
             'achieved': trailing_tflops, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': (trailing_tflops / peak) if (peak and trailing_tflops) else None,
-            'traffic': None,
+            'traffic': load_traffic(B),
             'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
                            'MEASURED_PEAKS.json has no FP64 row',
             'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],

@@ -1,0 +1,121 @@
+"""Continuous-context driver: ``python -m ocbo_b200.cts_ocbo --options <file>``.
+
+Host mirror of /root/reference/src/cts_ocbo.py:47-140 for CMTS / CMTS-PM; reads
+the reference's option files unchanged (src/options/conth42.txt ...).  Methods
+outside the MTS path (pei, revi, rand ...) are skipped unless
+``--strict_methods 1`` (then ``ValueError('Invalid method: ...')`` as at :139)."""
+import os
+import pickle as pkl
+import sys
+import time
+from argparse import Namespace
+
+import numpy as np
+
+from . import synth
+from .cstrats import cstrats
+from .cstrats.cts_opt import cts_opt_args
+from .cstrats.profile_cts import prof_args
+from .options import get_option_specs, load_options
+from .util import uniform_draw
+
+ocbo_args = [
+    get_option_specs('run_id', False, None, 'Unique ID for the run.'),
+    get_option_specs('options', False, None, 'Path to options file.'),
+    get_option_specs('trials', False, 3, 'Number of trials to run.'),
+    get_option_specs('max_capital', False, 50, 'Evaluations per trial after the initial ones.'),
+    get_option_specs('init_capital', False, 5, 'Initial evaluations.'),
+    get_option_specs('methods', False, None, 'Methods to run, comma separated.'),
+    get_option_specs('function', False, None, 'Name of the function to optimise.'),
+    get_option_specs('act_dim', False, 1, 'Size of the action domain.'),
+    get_option_specs('ctx_constraints', False, None, 'Number of allowed contexts (random).'),
+    get_option_specs('hp_tune_samps', False, None, 'Pre-tune HPs on this many samples, then fix.'),
+    get_option_specs('write_dir', False, None, 'Directory for per-trial pickles.'),
+    get_option_specs('show_fig', False, False, 'Ignored (no plotting).'),
+    get_option_specs('write_fig', False, False, 'Ignored (no plotting).'),
+    get_option_specs('description', False, None, 'Free-text description.'),
+    get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
+    get_option_specs('judge_act_size', False, None, 'Ignored (REVI only).'),
+    get_option_specs('judge_ctx_size', False, None, 'Ignored (REVI only).'),
+    get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
+]
+SEED = 100826730
+
+
+def find_function(name):
+    for f_info in synth.synth_functions:
+        if f_info.name.lower() == str(name).lower():
+            return f_info
+    raise ValueError('Invalid function: %s' % name)
+
+
+def assemble_methods(f_info, options):
+    if options.methods is None:
+        raise ValueError('Methods must be specified.')
+    domain = f_info.domain
+    ctx_dim = len(domain) - options.act_dim
+    slices = None
+    if options.ctx_constraints is not None:
+        slices = uniform_draw(domain[:ctx_dim], int(options.ctx_constraints))
+    methods, eval_set, skipped = [], None, []
+    for m_name in options.methods.split(','):
+        impl = [s.impl for s in cstrats if s.name.lower() == m_name.lower()]
+        if not impl:
+            if options.strict_methods:
+                raise ValueError('Invalid method: %s' % m_name)
+            skipped.append(m_name)
+            continue
+        methods.append(impl[0](f_info.function, domain, ctx_dim, options, eval_set=eval_set,
+                               ctx_constraints=slices))
+        eval_set = methods[-1].get_eval_set()
+    if skipped:
+        sys.stderr.write('ocbo_b200: methods outside the MTS hot path skipped: %s\n' % ','.join(skipped))
+    if not methods:
+        raise ValueError('No runnable method in: %s' % options.methods)
+    return methods
+
+
+def run_single(methods, f_info, options):
+    init_pts = list(uniform_draw(f_info.domain, options.init_capital))
+    samps = None if options.hp_tune_samps is None else int(options.hp_tune_samps)
+    results = {}
+    for method in methods:
+        method.set_clean()
+        t0 = time.time()
+        hist = method.optimize(options.max_capital, init_pts=init_pts, hp_tune_samps=samps)
+        hist.time_elapsed = time.time() - t0
+        results[method.get_strat_name()] = hist
+    return results
+
+
+def run(argv=None):
+    options = load_options(ocbo_args + cts_opt_args + prof_args, cmd_line=True, argv=argv)
+    if options.set_seed:
+        np.random.seed(SEED)
+    if options.run_id is None:
+        raise ValueError('run_id not specified.')
+    rand_state = np.random.get_state()
+    f_info = find_function(options.function)
+    methods = assemble_methods(f_info, options)
+    created = None
+    if options.write_dir is not None:
+        created = os.path.join(options.write_dir, options.run_id)
+        if os.path.isdir(created):
+            raise ValueError('Run ID already exists: %s' % options.run_id)
+        os.makedirs(created)
+        for name, obj in (('run_info.pkl', options), ('rand_state.pkl', rand_state),
+                          ('eval_set.pkl', methods[0].get_eval_set())):
+            with open(os.path.join(created, name), 'wb') as fh:
+                pkl.dump(obj, fh, protocol=2)
+    all_results = []
+    for t_id in range(options.trials):
+        results = run_single(methods, f_info, options)
+        if created is not None:
+            with open(os.path.join(created, 'trial_%d.pkl' % t_id), 'wb') as fh:
+                pkl.dump(results, fh, protocol=2)
+        all_results.append(results)
+    return all_results
+
+
+if __name__ == '__main__':
+    run()

@@ -1,0 +1,143 @@
+"""Discrete / joint driver: ``python -m ocbo_b200.ocbo --options <file>``.
+
+Host mirror of /root/reference/src/ocbo.py:67-144 for the MTS family: it reads
+the reference's option files UNCHANGED (src/options/set2d.txt, rand6d.txt,
+jointbran.txt ...), seeds numpy with the reference's seed (:74-75), builds the
+task functions, runs ``trials`` x methods and (optionally) pickles per-trial
+results under ``write_dir/run_id`` with the reference's file names (:95-107).
+
+Methods of the option file that are not on the accelerated MTS path (agn-*,
+mei, random, revi ...) are reported and skipped unless ``--strict_methods 1``,
+in which case they raise ``ValueError('Invalid method: ...')`` like the
+reference (:187).  Plotting is out of scope.
+"""
+import os
+import pickle as pkl
+import sys
+from copy import deepcopy
+
+import numpy as np
+
+from .options import get_option_specs, load_options
+from .strategies import strategies
+from .strategies.multi_opt import multi_opt_args
+from . import synth
+
+docbo_args = [
+    get_option_specs('run_id', False, None, 'Unique ID for the run.'),
+    get_option_specs('options', False, None, 'Path to options file.'),
+    get_option_specs('trials', False, 10, 'Number of trials to run.'),
+    get_option_specs('max_capital', False, 50, 'Evaluations per trial after the initial ones.'),
+    get_option_specs('init_capital', False, 5, 'Initial evaluations per task.'),
+    get_option_specs('methods', False, None, 'Methods to run, comma separated.'),
+    get_option_specs('functions', False, None, 'Named task functions, comma separated.'),
+    get_option_specs('cts_f', False, None, '2-D function to chop into 1-D tasks.'),
+    get_option_specs('num_chops', False, 5, 'Number of chops of cts_f.'),
+    get_option_specs('tune_every', False, 1, 'How often to tune hyper-parameters.'),
+    get_option_specs('pretune_for_joint', False, False, 'Pre-tune one joint prior GP.'),
+    get_option_specs('tunings', False, None, 'Per-method tuning methods, comma separated.'),
+    get_option_specs('write_dir', False, None, 'Directory for per-trial pickles.'),
+    get_option_specs('show_fig', False, False, 'Ignored (no plotting).'),
+    get_option_specs('write_fig', False, False, 'Ignored (no plotting).'),
+    get_option_specs('description', False, None, 'Free-text description.'),
+    get_option_specs('max_opt_evals', False, 100, 'Candidate actions per task and step.'),
+    get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
+    get_option_specs('run_ei_after', False, None, 'Ignored (REVI only).'),
+    get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
+]
+rand_fs_args = [
+    get_option_specs('easy_masses', False, 0, 'Easy random mass functions.'),
+    get_option_specs('med_masses', False, 0, 'Medium random mass functions.'),
+    get_option_specs('hard_masses', False, 0, 'Hard random mass functions.'),
+    get_option_specs('global_mass_scale', False, None, 'Common scale of the masses.'),
+    get_option_specs('massf_dim', False, 2, 'Dimension of the mass functions.'),
+]
+SEED = 100826730
+
+
+def assemble(options):
+    f_infos = synth.assemble_functions(options.functions)
+    scaling = options.global_mass_scale
+    scaling = scaling if scaling is None else int(scaling)
+    f_infos += synth.random_mass_functions(options.easy_masses, options.med_masses,
+                                           options.hard_masses, options.massf_dim, scaling)
+    if options.cts_f is not None:
+        f_infos += synth.assemble_chopped_1d_functions(options.cts_f, options.num_chops)
+    if not f_infos:
+        raise ValueError('No functions specified')
+    return f_infos
+
+
+def assemble_methods(f_infos, options):
+    if options.methods is None:
+        raise ValueError('Methods must be specified.')
+    names = options.methods.split(',')
+    tunings = options.tunings.split(',') if options.tunings is not None else None
+    if tunings is not None and len(tunings) != len(names):
+        raise ValueError('Number of tuning methods must match number of methods.')
+    methods, rn_info, skipped = [], None, []
+    for m_idx, m_name in enumerate(names):
+        impl = [s.impl for s in strategies if s.name.lower() == m_name.lower()]
+        if not impl:
+            if options.strict_methods:
+                raise ValueError('Invalid method: %s' % m_name)
+            skipped.append(m_name)
+            continue
+        if tunings is not None:
+            options.tuning_methods = tunings[m_idx]
+        methods.append(impl[0](f_infos, options, pre_tuned_gps=None, rn_info=rn_info))
+        rn_info = (methods[-1].rn_grids, methods[-1].rn_bests)
+    if skipped:
+        sys.stderr.write('ocbo_b200: methods outside the MTS hot path skipped: %s\n' % ','.join(skipped))
+    if not methods:
+        raise ValueError('No runnable method in: %s' % options.methods)
+    return methods
+
+
+def run_single(methods, f_infos, options):
+    init_pts = []
+    for wrap in f_infos:
+        low, high = zip(*wrap.domain)
+        init_pts.append([np.random.uniform(low, high) for _ in range(options.init_capital)])
+    results = {}
+    for method in methods:
+        method.set_clean()
+        hist = method.optimize(options.max_capital, init_pts=init_pts)
+        key = method.get_method_name_with_tuning() if options.tunings is not None \
+            else method.get_opt_method_name()
+        results[key] = hist
+    return results
+
+
+def run(argv=None):
+    options = load_options(docbo_args + multi_opt_args + rand_fs_args, cmd_line=True, argv=argv)
+    if options.set_seed:
+        np.random.seed(SEED)
+    if options.run_id is None:
+        raise ValueError('run_id not specified.')
+    rand_state = np.random.get_state()
+    f_infos = assemble(options)
+    methods = assemble_methods(f_infos, options)
+    created = None
+    if options.write_dir is not None:
+        created = os.path.join(options.write_dir, options.run_id)
+        if os.path.isdir(created):
+            raise ValueError('Run ID already exists: %s' % options.run_id)
+        os.makedirs(created)
+        clones = [deepcopy({k: v for k, v in vars(f).items() if k != 'function'}) for f in f_infos]
+        for name, obj in (('run_info.pkl', options), ('rand_state.pkl', rand_state),
+                          ('functions.pkl', clones)):
+            with open(os.path.join(created, name), 'wb') as fh:
+                pkl.dump(obj, fh, protocol=2)
+    all_results = []
+    for t_id in range(options.trials):
+        results = run_single(methods, f_infos, options)
+        if created is not None:
+            with open(os.path.join(created, 'trial_%d.pkl' % t_id), 'wb') as fh:
+                pkl.dump(results, fh, protocol=2)
+        all_results.append(results)
+    return all_results
+
+
+if __name__ == '__main__':
+    run()

@@ -44,7 +44,8 @@ def load_options(list_of_options, descr='', cmd_line=False, partial_options=None
     opts = Namespace(**{name: s['default'] for name, s in specs.items()})
     if cmd_line or argv is not None:
         parser = argparse.ArgumentParser(description=descr)
-        parser.add_argument('--options', default=None, help='file of --key value lines')
+        if 'options' not in specs:
+            parser.add_argument('--options', default=None, help='file of --key value lines')
         for name, s in specs.items():
             parser.add_argument('--' + name, default=None, help=s['help'])
         if argv is None:

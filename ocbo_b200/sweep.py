@@ -190,10 +190,48 @@ class SweepStep(object):
         """Synchronise the stream and return (task[B,S], action[B,S], gain[B,S])."""
         self.stream.synchronize()
         info = self.hinfo.numpy()
+        self.jitter = [(None, None)] * self.B
         if info.any():
-            raise ValueError('Cholesky failed in sweep step (info=%s); use the ladder path '
-                             '(B200GP.draw_sample) for this trial' % info.tolist())
+            # the fast path factors without the ladder; trials whose K or Sigma is not
+            # numerically PD are redone alone through Dragonfly's stable_cholesky ladder
+            for b in np.nonzero(info.any(axis=0))[0]:
+                self._redo_with_ladder(int(b))
+            self._download()
+            self.stream.synchronize()
         return self.htask.numpy().copy(), self.haction.numpy().copy(), self.hgain.numpy().copy()
+
+    def _redo_with_ladder(self, b):
+        """Slow path for one trial: same kernels, stable_cholesky semantics
+         for both factorisations; the normals Z[b] are reused."""
+        s = slice(b, b + 1)
+        n, m, D, S, T = self.n, self.m, self.D, self.S, self.T
+        X, Xs, th = self.X[s], self.Xs[s], self.theta[s]
+        with torch.cuda.stream(self.stream):
+            def asm_K(b0, b1):
+                engine.gram(self.kind, X, None, X, None, th, self.LK[s],
+                            _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE)
+            asm_K(0, 1)
+            jK = engine.chol_with_ladder(asm_K, self.LK[s], self.invdK[s], self.info[0, s], None, [n])
+            st = ctypes.c_void_p(self.stream.cuda_stream)
+            call('ocbo_solve_alpha_lml', _p(self.LK[s]), n, n, 0, _p(self.invdK[s]), _p(self.y[s]), 0,
+                 None, _p(th), 0, _p(self.alpha[s]), 0, _p(self.lml[s]), _p(self.info[0, s]), 1, st)
+            call('ocbo_post_mean', self.kind, D, _p(Xs), m, 0, None, _p(X), n, 0, None, _p(th), 0,
+                 _p(self.alpha[s]), 0, _p(self.mean[s]), 0, 1, st)
+            engine.gram(self.kind, X, None, Xs, None, th, self.V[s], 0)
+            engine.trsm_lower(self.LK[s], self.invdK[s], self.V[s], self.info[0, s])
+
+            def asm_S(b0, b1):
+                call('ocbo_post_cov', self.kind, D, _p(Xs), m, 0, None, _p(self.V[s]), n, m, 0,
+                     _p(th), 0, _p(self.Sigma[s]), m, 0, 1, 1, st)
+            asm_S(0, 1)
+            jS = engine.chol_with_ladder(asm_S, self.Sigma[s], self.invdS[s], self.info[1, s], None, [m])
+            call('ocbo_sample', _p(self.mean[s]), 0, _p(self.Sigma[s]), m, m, 0, _p(self.Z[s]), S, S, 0,
+                 _p(self.F[s]), S, 0, _p(self.info[1, s]), 1, st)
+            call('ocbo_segment_argmax', _p(self.F[s]), S, S, 0, _p(self.seg[s]), T,
+                 _p(self.seg_max[s]), _p(self.seg_arg[s]), 1, st)
+            call('ocbo_joint_pick', _p(self.seg_max[s]), _p(self.seg_arg[s]), T, 0, T, S,
+                 _p(self.task[s]), _p(self.action[s]), _p(self.gain[s]), 1, st)
+        self.jitter[b] = (jK[0], jS[0])
 
     def step_host(self, trial_ids, inputs):
         self.submit_host(trial_ids, inputs)

@@ -57,3 +57,25 @@ def test_run_sweep_single_process_gather():
     st = sweep.SweepStep(n, T, A, S, 6, batch=1)
     t3 = st.step_host([3], [sweep.make_trial_inputs(3, n, T, A)])
     assert np.array_equal(task[3], t3[0][0]) and np.array_equal(act[3], t3[1][0])
+
+
+def test_sweep_falls_back_to_the_jitter_ladder():
+    """Isotropic 0.25 bandwidths make Sigma numerically singular (SURVEY 8d's own
+    choice): the ladder-free fast path reports info != 0 and
+    the trial is redone through stable_cholesky; picks stay valid and the mean
+    (which does not depend on Sigma) still matches the oracle to 1e-8."""
+    from ocbo_b200 import sweep
+    from oracle import sweep_step
+    n, T, A, S = 256, 8, 128, 64
+    st = sweep.SweepStep(n, T, A, S, 6, batch=2, bandwidths=0.25)
+    trials = [3, 4]
+    inputs = [sweep.make_trial_inputs(t, n, T, A) for t in trials]
+    task, act, gain = st.step_host(trials, inputs)
+    assert any(j[1] is not None for j in st.jitter), st.jitter
+    assert (task >= 0).all() and (task < T).all() and (act >= 0).all() and (act < A).all()
+    assert np.isfinite(gain).all()
+    mean = st.mean.cpu().numpy()
+    for b, t in enumerate(trials):
+        X, y, Xs = inputs[b]
+        _, _, _, _, mu, _ = sweep_step.step(X, y, Xs, T, 2, bandwidths=0.25, return_samples=True)
+        assert np.max(np.abs(mean[b] - mu)) <= 1e-8 * np.max(np.abs(mu))

@@ -1,0 +1,81 @@
+"""Option handling and drivers (host logic, no GPU unless marked)."""
+import os
+
+import numpy as np
+import pytest
+
+REF_OPTS = '/root/reference/src/options'
+
+
+def test_option_specs_types_and_file(tmp_path):
+    from ocbo_b200.options import get_option_specs, load_options
+    specs = [get_option_specs('trials', False, 10, ''), get_option_specs('risk_neutral', False, False, ''),
+             get_option_specs('description', False, None, ''), get_option_specs('scale', False, 0.5, ''),
+             get_option_specs('methods', False, None, '')]
+    f = tmp_path / 'o.txt'
+    f.write_text('--trials 3\n--risk_neutral 1\n--description "two words"\n--methods a,b\n')
+    o = load_options(specs, cmd_line=True, argv=['--options', str(f), '--scale', '2'])
+    assert o.trials == 3 and o.risk_neutral is True and o.description == 'two words'
+    assert o.scale == 2.0 and o.methods == 'a,b'
+    d = load_options(specs, cmd_line=False)
+    assert d.trials == 10 and d.description is None
+
+
+@pytest.mark.refsrc
+@pytest.mark.parametrize('name', ['set2d.txt', 'jointbran.txt', 'rand6d.txt'])
+def test_reference_discrete_option_files_parse_unchanged(name):
+    from ocbo_b200 import ocbo
+    from ocbo_b200.options import load_options
+    from ocbo_b200.strategies.multi_opt import multi_opt_args
+    o = load_options(ocbo.docbo_args + multi_opt_args + ocbo.rand_fs_args, cmd_line=True,
+                     argv=['--options', os.path.join(REF_OPTS, name)])
+    assert o.run_id == name[:-4] and o.trials == 10 and o.tune_every == 1
+    assert 'mts' in o.methods
+    np.random.seed(0)
+    f_infos = ocbo.assemble(o)
+    assert len(f_infos) == {'set2d.txt': 5, 'jointbran.txt': 10, 'rand6d.txt': 30}[name]
+
+
+@pytest.mark.refsrc
+def test_reference_continuous_option_file_parses_unchanged():
+    from ocbo_b200 import cts_ocbo
+    from ocbo_b200.cstrats.cts_opt import cts_opt_args
+    from ocbo_b200.cstrats.profile_cts import prof_args
+    from ocbo_b200.options import load_options
+    o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args, cmd_line=True,
+                     argv=['--options', os.path.join(REF_OPTS, 'conth42.txt')])
+    assert o.run_id == 'conth42' and o.max_capital == 750 and o.act_dim == 2
+    assert cts_ocbo.find_function(o.function).name == 'hartmann6'
+
+
+def test_strict_methods_raise_like_the_reference():
+    from argparse import Namespace
+    from ocbo_b200 import ocbo
+    opts = Namespace(methods='revi', tunings=None, strict_methods=True)
+    with pytest.raises(ValueError, match='Invalid method'):
+        ocbo.assemble_methods([], opts)
+
+
+@pytest.mark.gpu
+def test_discrete_driver_runs_an_option_file(tmp_path):
+    from ocbo_b200 import ocbo
+    f = tmp_path / 'mini.txt'
+    f.write_text('--run_id mini\n--trials 2\n--max_capital 3\n--tune_every 1\n--tuning_methods ml\n'
+                 '--methods agn-thomp,mts,random\n--functions branin,parabaloid\n'
+                 '--write_dir %s\n' % tmp_path)
+    res = ocbo.run(argv=['--options', str(f)])
+    assert len(res) == 2 and set(res[0]) == {'mts'}
+    assert len(res[0]['mts'].choice_timeline) == 3
+    assert os.path.exists(tmp_path / 'mini' / 'trial_1.pkl')
+
+
+@pytest.mark.gpu
+def test_continuous_driver_runs_an_option_file(tmp_path):
+    from ocbo_b200 import cts_ocbo
+    f = tmp_path / 'mini.txt'
+    f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--methods cmts,cmts-pm,pei\n'
+                 '--function hartmann6\n--act_dim 2\n--num_profiles 5\n--eval_ctx_fidel 4\n'
+                 '--eval_act_fidel 4\n')
+    res = cts_ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'cmts', 'cmts-pm'}
+    assert len(res[0]['cmts'].query_history) == 2 and len(res[0]['cmts'].score_history) == 2
