@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--streams', type=int, default=8, help='concurrent trial groups per GPU')
-    ap.add_argument('--batch', type=int, default=1, help='trials per kernel launch (grid.z)')
+    ap.add_argument('--batch', type=int, default=2, help='trials per kernel launch (grid.z)')
     ap.add_argument('--cpu-trials', type=int, default=2, help='trials timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-peaks', action='store_true')
@@ -421,6 +421,15 @@ def run_b200(args):
             'roofline': roof,
             'cpu_baseline': cpu,
         }
+        if not args.no_cpu_baseline and world == 1:
+            # second half of BASELINE.json's metric: MTS BO decision steps/s at the option-file
+            # shapes (fixed HPs), batched device pass vs the numpy oracle loop on the host cores
+            try:
+                from tests.tools import bench_small
+                use_all_blas_threads()
+                line['mts_bo_steps'] = bench_small.measure()
+            except Exception as exc:  # secondary figure: never lose the headline line
+                line['mts_bo_steps'] = {'error': repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -70,6 +70,10 @@ def _h2d(arr, dtype=F64):
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if t.dtype != dtype:
         t = t.to(dtype)
+    if t.numel() * t.element_size() < (1 << 20):
+        # small operands (the option-file shapes): a pageable copy costs ~10 us, pinning
+        # a fresh buffer costs a cudaHostAlloc (~100 us) per call
+        return t.to(device())
     return t.pin_memory().to(device(), non_blocking=True)
 
 

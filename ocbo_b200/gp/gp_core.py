@@ -234,10 +234,8 @@ class B200GPCore(object):
             Sigma, mean = engine._h2d(Sh), engine._h2d(Mh)
             mv = [m]
             mv_dev = engine._h2d(np.asarray(mv, dtype=np.int32), engine.I32)
-            pinned = torch.from_numpy(Sh).pin_memory()
-
             def reassemble(b0, b1):
-                Sigma.copy_(pinned, non_blocking=True)
+                Sigma.copy_(torch.from_numpy(Sh))  # ladder retry only
         m, m_pad = mv[0], Sigma.shape[1]
         _, info, jit = engine.factor_covariance(None, Sigma, mv_dev, mv, reassemble)
         self.last_sample_jitter = jit[0]

@@ -2,7 +2,7 @@
 every step, evaluate the numpy oracle on the SAME inputs and normals; print both
 picks and the oracle's top-two gain gap."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import gp_numpy as o
 from tests import scenarios as sc
