@@ -389,7 +389,11 @@ def run_b200(args):
             'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
                            'MEASURED_PEAKS.json has no FP64 row',
             'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],
-                         'outer_update': ms3[3], 'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 1024))},
+                         'outer_update': ms3[3], 'batch': B,
+                         'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 2048)),
+                         'inner': os.environ.get('OCBO_POTRF_INNER', 'left'),
+                         'note': 'serialised launches of ONE group (batch trials) on an otherwise idle '
+                                 'GPU; in the timed region 16 trials overlap'},
             'step_tflops_per_gpu': step_tflops / world,
             'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,

@@ -146,6 +146,18 @@ int ocbo_post_cross_cov(int kind, int dim,
                         double* C, int ldc, int64_t s_c,
                         int batch, ocbo_stream_t stream);
 
+/* Diagonal of Sigma and expected improvement, fused, without forming Sigma:
+ *   var[b][i] = scale_b - sum_k V[b][k][i]^2,
+ *   ei[b][i]  = std (z Phi(z) + phi(z)),  z = (mean[b][i] - best[b]) / std   (-inf on padding).
+ * var or ei may be NULL.  Replaces eval(pts, True) + covmat.diagonal() + the EI formula of
+ * the EI-family acquisitions (src/util/misc_util.py:368-385, src/strategies/joint_mei.py:39-48,
+ * src/cstrats/profile_cts.py:54-67) and eval(x, 'std') (misc_util.py:321,326). */
+int ocbo_post_var_ei(const double* V, int n, int ldv, int64_t s_v, const int32_t* nv,
+                     const double* mean, int64_t s_mean,
+                     const double* theta, int64_t s_theta, const double* best,
+                     int m, const int32_t* mv, double* var, int64_t s_var,
+                     double* ei, int64_t s_ei, int batch, ocbo_stream_t stream);
+
 /* Copy the lower triangle onto the upper one (full symmetric covar for eval). */
 int ocbo_symmetrize_lower(double* A, int n, int lda, int64_t s_a, int batch,
                           ocbo_stream_t stream);

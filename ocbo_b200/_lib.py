@@ -26,6 +26,8 @@ _PROTOS = {
     'ocbo_post_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _I, _L, _VP, _L, _VP, _I, _L, _I, _I, _VP]),
     'ocbo_post_cross_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _I, _L,
                                  _I, _VP, _L, _VP, _I, _L, _I, _VP]),
+    'ocbo_post_var_ei': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _L, _VP, _I, _VP, _VP, _L, _VP, _L,
+                              _I, _VP]),
     'ocbo_symmetrize_lower': (_I, [_VP, _I, _I, _L, _I, _VP]),
     'ocbo_philox_normal': (_I, [_VP, _I, _I, _I, _L, _U64, _VP, _I, _VP]),
     'ocbo_sample': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _I, _L, _VP, _I, _VP]),

@@ -100,3 +100,60 @@ def profile_step(gp, act_sets, Z_list):
     s_at = Fm[:, :, 0].gather(1, idx[:, None])[:, 0].cpu().numpy()
     core.last_sample_jitter = jit
     return mx[:, 0], ag[:, 0], mmx, mag, s_at
+
+
+# ---------------------------------------------------------------------------
+# EI family: posterior mean + diagonal variance + EI + arg-max,
+# never forming the m x m covariance (ocbo_post_var_ei).
+# ---------------------------------------------------------------------------
+def _ei_reduce(post, pts_list, best):
+    """best: device tensor [B] or a callable(mean_max[B] tensor) -> tensor [B]."""
+    Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
+    mean = post.mean(Xd, mv_dev)
+    V = post.solve_cross(Xd, mv_dev)
+    segs = np.asarray([[0, m] for m in mv], dtype=np.int32)
+    if callable(best):
+        mmx, _ = engine.segment_argmax(mean.unsqueeze(2), 1, segs)
+        best = best(mmx[:, 0, 0])
+    ei = torch.empty((post.B, m_pad), dtype=F64, device=mean.device)
+    engine.call('ocbo_post_var_ei', engine._p(V), post.n_pad, V.stride(1), V.stride(0),
+                engine._p(post.nv), engine._p(mean), mean.stride(0), engine._p(post.theta),
+                post.theta.stride(0), engine._p(best), m_pad, engine._p(mv_dev), None, 0,
+                engine._p(ei), ei.stride(0), post.B, engine._stream())
+    emx, eag = engine.segment_argmax(ei.unsqueeze(2), 1, segs)
+    return emx[:, 0, 0].cpu().numpy(), eag[:, 0, 0].cpu().numpy()
+
+
+def mei_step(gps, pts_list, best_list):
+    """Independent-GP MEI (src/strategies/mei.py:29-46 via misc_util.py:368-385) for all
+    tasks at once.  Returns per task (max EI, arg-max index)."""
+    T = len(gps)
+    groups = defaultdict(list)
+    for f, gp in enumerate(gps):
+        groups[(gp.gp_core.dim, gp.gp_core.kernel.kind)].append(f)
+    out = [None] * T
+    for (D, kind), members in groups.items():
+        cores = [gps[f].gp_core for f in members]
+        post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
+                               np.asarray([c.theta() for c in cores]), kind, D).build()
+        best = engine._h2d(np.asarray([best_list[f] for f in members], dtype=np.float64))
+        pts = [np.asarray(pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
+        emx, eag = _ei_reduce(post, pts, best)
+        for k, f in enumerate(members):
+            out[f] = (float(emx[k]), int(eag[k]))
+    return out
+
+
+def shared_ei_step(gp, pts_list, best_list=None, cap=None):
+    """EI over several candidate sets of ONE GP (joint-MEI: src/strategies/joint_mei.py:
+    26-52; PEI: src/cstrats/profile_cts.py:54-67).  ``best_list`` gives the incumbent per
+    set; with ``cap`` (PEI) the incumbent is min(max posterior mean of the set, cap)."""
+    core = gp.gp_core
+    if core._post is None:
+        core.build_posterior()
+    post = SharedPosterior(core._post, len(pts_list))
+    if cap is not None:
+        best = lambda mean_max: torch.clamp(mean_max, max=float(cap)).contiguous()
+    else:
+        best = engine._h2d(np.asarray(best_list, dtype=np.float64))
+    return _ei_reduce(post, pts_list, best)

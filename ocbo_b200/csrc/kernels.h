@@ -59,6 +59,11 @@ cudaError_t launch_symmetrize(double* A, int n, int lda, int64_t sA, int batch, 
 // factor the 128x128 diagonal block at (j0, j0) of every problem, write inv(L_jj)
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
                               int64_t sInv, int32_t* info, int batch, cudaStream_t st);
+cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, const int32_t* nv,
+                               const double* mean, int64_t sMean, const double* theta,
+                               int64_t sTheta, const double* best, int m, const int32_t* mv,
+                               double* var, int64_t sVar, double* ei, int64_t sEi, int batch,
+                               cudaStream_t st);
 cudaError_t launch_potrf_diag_reg(double* A, int lda, int64_t sA, int j0, double* invdiag,
                                   int64_t sInv, int32_t* info, int batch, cudaStream_t st);
 cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,

@@ -49,6 +49,25 @@ class ProfileOpt(ContinuousOpt):
         raise NotImplementedError('Abstract Method')
 
 
+class ProfileEI(ProfileOpt):
+    """PEI (:47-67): per context, EI against min(max posterior mean, best reward seen);
+    no sampling -- fused mean + diagonal variance + EI on the device."""
+
+    @staticmethod
+    def get_strat_name():
+        return 'pei'
+
+    def _determine_next_query(self):
+        ctxs = self._get_ctx_candidates(self.num_profiles)
+        act_sets = [sample_grid([list(ctx)], self.act_domain, self.profile_evals) for ctx in ctxs]
+        ei_max, ei_arg = batched.shared_ei_step(self.gp, act_sets, cap=np.max(self.y_data))
+        best_pt, best_imp = None, float('-inf')
+        for i in range(len(ctxs)):
+            if ei_max[i] > best_imp:
+                best_pt, best_imp = act_sets[i][int(ei_arg[i])], ei_max[i]
+        return best_pt
+
+
 class CMTSPM(ProfileOpt):
     """gain = max(sample) - min(max(means), max(y_data))   (:76-86)."""
 
@@ -71,5 +90,6 @@ class ContinuousMultiTaskTS(ProfileOpt):
         return sample_max - sample_at_mean_argmax
 
 
-prof_strats = [Namespace(impl=CMTSPM, name=CMTSPM.get_strat_name()),
+prof_strats = [Namespace(impl=ProfileEI, name=ProfileEI.get_strat_name()),
+               Namespace(impl=CMTSPM, name=CMTSPM.get_strat_name()),
                Namespace(impl=ContinuousMultiTaskTS, name=ContinuousMultiTaskTS.get_strat_name())]

@@ -202,6 +202,18 @@ class B200GPCore(object):
     def eval(self, X_test, uncert_form='none'):
         if uncert_form not in ('none', 'std', 'covar'):
             raise ValueError('uncert_form must be none, std or covar.')
+        if uncert_form == 'std':
+            # diagonal only: fused scale - |V[:, i]|^2, the m x m covariance is never formed
+            Xd, mv_dev, mv, mean, _, _ = self._posterior_at(X_test, False, False)
+            post = self._post
+            V = post.solve_cross(Xd, mv_dev)
+            var = torch.empty_like(mean)
+            engine.call('ocbo_post_var_ei', engine._p(V), post.n_pad, V.stride(1), V.stride(0),
+                        engine._p(post.nv), None, 0, engine._p(post.theta), post.theta.stride(0), None,
+                        mean.shape[1], engine._p(mv_dev), engine._p(var), var.stride(0), None, 0, 1,
+                        engine._stream())
+            m = mv[0]
+            return mean[0, :m].cpu().numpy(), np.sqrt(var[0, :m].cpu().numpy())
         _, _, mv, mean, _, Sigma = self._posterior_at(X_test, uncert_form != 'none', False)
         m = mv[0]
         mu = mean[0, :m].cpu().numpy()

@@ -1,13 +1,17 @@
 """Strategy registry in the reference's format (src/strategies/__init__.py:13-27):
 ``Namespace(impl=cls, name=str)`` entries matched case-insensitively by the
-drivers (src/ocbo.py:176-177).  Only the MTS family is on the accelerated hot
-path."""
+drivers (src/ocbo.py:176-177).  The MTS family is the accelerated hot path
+(SURVEY 8a); MEI / joint-MEI are the first "next" row (8f, f2) and share its kernels."""
 from argparse import Namespace
 
+from .joint_mei import JointMEI
 from .joint_mts import JointMTS
+from .mei import MEI
 from .mts import MTS
 
 strategies = [
     Namespace(impl=MTS, name=MTS.get_opt_method_name()),
     Namespace(impl=JointMTS, name=JointMTS.get_opt_method_name()),
+    Namespace(impl=MEI, name=MEI.get_opt_method_name()),
+    Namespace(impl=JointMEI, name=JointMEI.get_opt_method_name()),
 ]

@@ -22,6 +22,7 @@ from scipy.linalg import solve_triangular
 # identical normals into the oracle and the CUDA path replace this hook.
 NORMAL_SOURCE = None  # callable(size)->ndarray, or None for np.random.normal
 TRACE = None  # list collecting every draw (jitter rung, sample) while golden vectors are made
+TRACE_EVAL = None  # list collecting (mean, diag covar) of every eval(..., 'covar') likewise
 
 
 def _normals(size):
@@ -236,6 +237,8 @@ class EuclideanGP(object):
         else:
             covar = K_ss
         if uncert_form == 'covar':
+            if TRACE_EVAL is not None:  # golden-vector generation only (EI-family margins)
+                TRACE_EVAL.append(dict(mean=mu.copy(), var=np.diag(covar).copy()))
             return mu, covar
         if uncert_form == 'std':
             return mu, np.sqrt(np.diag(covar))

@@ -24,7 +24,9 @@ def main():
     refshim.install()
     from strategies.mts import MTS
     from strategies.joint_mts import JointMTS
-    from cstrats.profile_cts import CMTSPM, ContinuousMultiTaskTS
+    from strategies.mei import MEI
+    from strategies.joint_mei import JointMEI
+    from cstrats.profile_cts import CMTSPM, ContinuousMultiTaskTS, ProfileEI
     from util.misc_util import assemble_functions
     from synth.continuous_2d import assemble_chopped_1d_functions
     from synth.function_generator import get_easy_mass_functions, get_hard_mass_functions, \
@@ -44,7 +46,7 @@ def main():
             domain = [[0, 1] for _ in range(cfg['massf_dim'])]
             f_infos = get_hard_mass_functions(hard, domain, None) + \
                 get_med_mass_functions(med, domain, None) + get_easy_mass_functions(easy, domain, None)
-        cls = MTS if cfg['kind'] == 'mts' else JointMTS
+        cls = {'mts': MTS, 'joint-mts': JointMTS, 'mei': MEI, 'joint-mei': JointMEI}[cfg['kind']]
         gp_numpy.TRACE = []
         out[name] = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'dragonfly'))
         out[name]['margins'] = sc.discrete_margins(cfg, len(f_infos), out[name]['choice_timeline'],
@@ -57,11 +59,13 @@ def main():
         np.random.seed(sc.SEED)
         gp_numpy.EuclideanGPFitter._fit_counter = 0
         domain = [[0, 1] for _ in range(6)]
-        cls = ContinuousMultiTaskTS if cfg['kind'] == 'cmts' else CMTSPM
-        gp_numpy.TRACE = []
+        cls = {'cmts': ContinuousMultiTaskTS, 'cmts-pm': CMTSPM, 'pei': ProfileEI}[cfg['kind']]
+        gp_numpy.TRACE, gp_numpy.TRACE_EVAL = [], []
         out[name] = sc.run_continuous(cfg, cls, hartmann6, domain,
                                       sc.continuous_options(cfg, 'dragonfly'))
-        out[name]['margins'] = sc.continuous_margins(cfg, gp_numpy.TRACE, out[name]['y_init'],
+        trace = gp_numpy.TRACE_EVAL if cfg['kind'] == 'pei' else gp_numpy.TRACE
+        gp_numpy.TRACE_EVAL = None
+        out[name]['margins'] = sc.continuous_margins(cfg, trace, out[name]['y_init'],
                                                      out[name]['rewards'])
         out[name]['jitter_rungs'] = [d['jitter_p'] for d in gp_numpy.TRACE]
         gp_numpy.TRACE = None

@@ -19,6 +19,11 @@ DISCRETE = {
     # jointbran.txt: joint-MTS over chopped Branin, risk-neutral bookkeeping on
     'jointbran': dict(kind='joint-mts', cts_f='branin', num_chops=4, capital=8, init_capital=5,
                       tuning_methods='ml', hp_samples=3, risk_neutral=True),
+    # EI family: the other GP-driven methods of the same option files
+    'set2d-mei': dict(kind='mei', functions='branin,parabaloid,parabaloid', capital=8, init_capital=5,
+                      tuning_methods='ml', hp_samples=3, risk_neutral=False),
+    'jointbran-mei': dict(kind='joint-mei', cts_f='branin', num_chops=4, capital=8, init_capital=5,
+                          tuning_methods='ml', hp_samples=3, risk_neutral=True),
 }
 CONTINUOUS = {
     # conth42.txt: Hartmann-6 with 4 context + 2 action dims
@@ -26,6 +31,8 @@ CONTINUOUS = {
                          profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
     'conth42-cmts-pm': dict(kind='cmts-pm', act_dim=2, capital=6, init_capital=5, num_profiles=10,
                             profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+    'conth42-pei': dict(kind='pei', act_dim=2, capital=6, init_capital=5, num_profiles=10,
+                        profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
 }
 
 
@@ -116,6 +123,8 @@ def discrete_margins(cfg, num_tasks, timeline, trace, A=100):
     """Per step: (margin of the reference's pick over the runner-up, tie tolerance)."""
     counts = [cfg['init_capital']] * num_tasks
     out = []
+    if cfg['kind'] in ('mei', 'joint-mei'):
+        return [(float('inf'), 0.0)] * len(timeline)  # no sampling: exact match required
     per_step = 1 if cfg['kind'] == 'joint-mts' else num_tasks
     for t, chosen in enumerate(timeline):
         draws = trace[t * per_step:(t + 1) * per_step]
@@ -140,6 +149,8 @@ def discrete_margins(cfg, num_tasks, timeline, trace, A=100):
 def continuous_margins(cfg, trace, y_init, rewards):
     P = cfg['num_profiles']
     out = []
+    if cfg['kind'] == 'pei':
+        return pei_margins(cfg, trace, y_init, rewards)
     y = list(y_init)
     for t in range(cfg['capital']):
         draws = trace[t * P:(t + 1) * P]
@@ -152,6 +163,34 @@ def continuous_margins(cfg, trace, y_init, rewards):
                 gains.append(np.max(s) - min(np.max(mu), np.max(y)))
             within.append(_top2_gap(s))
         out.append((min(_top2_gap(gains), within[int(np.argmax(gains))]), _tol(draws)))
+        y.append(rewards[t])
+    return out
+
+
+EI_TIE_REL = 1e-6  # EI arg-max ties: relative gap of the two largest EI values
+
+
+def pei_margins(cfg, evals, y_init, rewards):
+    """PEI (profile_cts.py:54-67) draws no samples; its pick is an arg-max over EI
+    values that underflow towards 0 when no candidate is likely to improve.  Margin =
+    relative gap between the two largest EI values (across contexts and inside the
+    winning context); below EI_TIE_REL the two candidates are tied in fp64.  The
+    reference evaluates the score GP once more per step (cts_opt.py:312) -- those
+    evals are 'none'-form and not traced."""
+    from scipy.stats import norm
+    P = cfg['num_profiles']
+    out, y = [], list(y_init)
+    for t in range(cfg['capital']):
+        best_vals, within = [], []
+        for d in evals[t * P:(t + 1) * P]:
+            mu, sd = d['mean'], np.sqrt(d['var'])
+            z = (mu - min(np.max(mu), np.max(y))) / sd
+            ei = sd * (z * norm.cdf(z) + norm.pdf(z))
+            best_vals.append(np.max(ei))
+            within.append(_top2_gap(ei))
+        top = max(np.max(best_vals), 1e-300)
+        margin = min(_top2_gap(best_vals), within[int(np.argmax(best_vals))]) / top
+        out.append((float(margin), EI_TIE_REL))
         y.append(rewards[t])
     return out
 

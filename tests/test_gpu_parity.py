@@ -316,3 +316,34 @@ def test_full_size_cholesky_backward_error(mods):
     _, cov_ref = og.eval(Xs[idx], include_covar=True)
     got = Sfull[idx][:, idx].cpu().numpy()
     assert np.max(np.abs(got - cov_ref)) <= TOL * np.max(np.abs(cov_ref))
+
+
+def test_std_and_expected_improvement_without_forming_sigma(mods):
+    """eval(x, 'std') and the EI-family reduction use the fused diagonal-variance kernel;
+    compare with the oracle's full-covariance route (misc_util.py:368-385)."""
+    from scipy.stats import norm
+    from ocbo_b200 import batched
+    X, y, og, bg = both_gps(mods, 41, 90, 3, noise=1e-2, bw=0.2)
+    rs = np.random.RandomState(3)
+    pts = rs.uniform(size=(150, 3))
+    mu_o, sd_o = og.gp_core.eval(pts, 'std')
+    mu_b, sd_b = bg.gp_core.eval(pts, 'std')
+    assert rel_err(mu_b, mu_o) <= TOL and rel_err(sd_b, sd_o) <= TOL
+    sets = [rs.uniform(size=(100, 3)) for _ in range(4)]
+    bests = [0.1, 0.5, -0.2, 0.9]
+    ei_max, ei_arg = batched.shared_ei_step(bg, sets, best_list=bests)
+    for p, best, em, ea in zip(sets, bests, ei_max, ei_arg):
+        mu, cov = og.eval(p, include_covar=True)
+        sd = np.sqrt(np.diag(cov))
+        z = (mu - best) / sd
+        ei = sd * (z * norm.cdf(z) + norm.pdf(z))
+        assert int(ea) == int(np.argmax(ei))
+        assert abs(em - ei.max()) <= 1e-8 * max(ei.max(), 1e-12) + 1e-14
+    cap = 0.3
+    ei_max2, ei_arg2 = batched.shared_ei_step(bg, sets, cap=cap)
+    for p, em, ea in zip(sets, ei_max2, ei_arg2):
+        mu, cov = og.eval(p, include_covar=True)
+        sd = np.sqrt(np.diag(cov))
+        z = (mu - min(mu.max(), cap)) / sd
+        ei = sd * (z * norm.cdf(z) + norm.pdf(z))
+        assert int(ea) == int(np.argmax(ei))

@@ -60,6 +60,30 @@ def _fake_profile_step(gp, act_sets, Z_list):
     return [np.asarray(c) for c in zip(*res)]
 
 
+def _ei(gp, pts, best):
+    from scipy.stats import norm
+    mu, cov = gp.gp_core.eval(pts, 'covar')
+    sd = np.sqrt(np.diag(cov))
+    z = (mu - best) / sd
+    ei = sd * (z * norm.cdf(z) + norm.pdf(z))
+    return float(np.max(ei)), int(np.argmax(ei)), float(np.max(mu))
+
+
+def _fake_mei_step(gps, pts_list, best_list):
+    return [_ei(g, p, b)[:2] for g, p, b in zip(gps, pts_list, best_list)]
+
+
+def _fake_shared_ei_step(gp, pts_list, best_list=None, cap=None):
+    out = []
+    for i, p in enumerate(pts_list):
+        if cap is not None:
+            best = min(float(np.max(gp.gp_core.eval(p)[0])), float(cap))
+        else:
+            best = best_list[i]
+        out.append(_ei(gp, p, best)[:2])
+    return np.asarray([o[0] for o in out]), np.asarray([o[1] for o in out])
+
+
 @pytest.fixture
 def oracle_engine(monkeypatch):
     from ocbo_b200 import batched
@@ -70,6 +94,8 @@ def oracle_engine(monkeypatch):
         monkeypatch.setattr(mod, 'get_gp_fitter', fitter)
     monkeypatch.setattr(batched, 'mts_step', _fake_mts_step)
     monkeypatch.setattr(batched, 'profile_step', _fake_profile_step)
+    monkeypatch.setattr(batched, 'mei_step', _fake_mei_step)
+    monkeypatch.setattr(batched, 'shared_ei_step', _fake_shared_ei_step)
     o.EuclideanGPFitter._fit_counter = 0
     with open(GOLDEN) as fh:
         return json.load(fh)
@@ -117,8 +143,8 @@ def test_continuous_host_logic_matches_reference(oracle_engine, name):
 def test_registry_and_names():
     from ocbo_b200.cstrats import cstrats
     from ocbo_b200.strategies import strategies
-    assert {s.name for s in strategies} == {'mts', 'joint-mts'}
-    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm'}
+    assert {s.name for s in strategies} == {'mts', 'joint-mts', 'mei', 'joint-mei'}
+    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm', 'pei'}
     for s in strategies:
         assert s.impl.get_opt_method_name() == s.name
     for s in cstrats:

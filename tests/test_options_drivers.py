@@ -73,7 +73,7 @@ def test_discrete_driver_runs_an_option_file(tmp_path):
 def test_continuous_driver_runs_an_option_file(tmp_path):
     from ocbo_b200 import cts_ocbo
     f = tmp_path / 'mini.txt'
-    f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--methods cmts,cmts-pm,pei\n'
+    f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--methods cmts,cmts-pm,revi\n'
                  '--function hartmann6\n--act_dim 2\n--num_profiles 5\n--eval_ctx_fidel 4\n'
                  '--eval_act_fidel 4\n')
     res = cts_ocbo.run(argv=['--options', str(f)])
