@@ -146,6 +146,26 @@ int ocbo_post_cross_cov(int kind, int dim,
                         double* C, int ldc, int64_t s_c,
                         int batch, ocbo_stream_t stream);
 
+/* Forward half of the above: w = L^{-1}(y - mu0) and the LML (= -1/2 w^T w - ...).
+ * With V = L^{-1} K(X, Xs) already at hand, the posterior mean is mu0 + V^T w
+ * (ocbo_post_mean_var_from_v): no back-substitution, no second pass over the kernel. */
+int ocbo_solve_forward_lml(const double* L, int n, int ldl, int64_t s_l,
+                           const double* invdiag,
+                           const double* y, int64_t s_y, const int32_t* nv,
+                           const double* theta, int64_t s_theta,
+                           double* w, int64_t s_w, double* lml,
+                           const int32_t* info, int batch, ocbo_stream_t stream);
+
+/* mean[b][i] = mu0 + sum_k V[b][k][i] w[b][k],  var[b][i] = scale - sum_k V[b][k][i]^2
+ * in one HBM-bound pass over V (either output may be NULL).  Same values as
+ * GP.eval(X, 'std')'s mean / std^2 (src/gp/gp_interface.py:69-74). */
+int ocbo_post_mean_var_from_v(const double* V, int n, int ldv, int64_t s_v, const int32_t* nv,
+                              const double* w, int64_t s_w,
+                              const double* theta, int64_t s_theta,
+                              int m, const int32_t* mv,
+                              double* mean, int64_t s_mean, double* var, int64_t s_var,
+                              int batch, ocbo_stream_t stream);
+
 /* Diagonal of Sigma and expected improvement, fused, without forming Sigma:
  *   var[b][i] = scale_b - sum_k V[b][k][i]^2,
  *   ei[b][i]  = std (z Phi(z) + phi(z)),  z = (mean[b][i] - best[b]) / std   (-inf on padding).

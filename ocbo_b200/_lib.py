@@ -26,6 +26,10 @@ _PROTOS = {
     'ocbo_post_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _I, _L, _VP, _L, _VP, _I, _L, _I, _I, _VP]),
     'ocbo_post_cross_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _I, _L,
                                  _I, _VP, _L, _VP, _I, _L, _I, _VP]),
+    'ocbo_solve_forward_lml': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _VP, _L, _VP, _L, _VP, _VP, _I,
+                                    _VP]),
+    'ocbo_post_mean_var_from_v': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _L, _I, _VP, _VP, _L, _VP,
+                                       _L, _I, _VP]),
     'ocbo_post_var_ei': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _L, _VP, _I, _VP, _VP, _L, _VP, _L,
                               _I, _VP]),
     'ocbo_symmetrize_lower': (_I, [_VP, _I, _I, _L, _I, _VP]),

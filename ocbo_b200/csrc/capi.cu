@@ -353,6 +353,40 @@ int ocbo_post_cross_cov(int kind, int dim, const double* Xa, int ma, int64_t s_x
   return 0;
 }
 
+int ocbo_solve_forward_lml(const double* L, int n, int ldl, int64_t s_l, const double* invdiag,
+                           const double* y, int64_t s_y, const int32_t* nv, const double* theta,
+                           int64_t s_theta, double* w, int64_t s_w, double* lml,
+                           const int32_t* info, int batch, ocbo_stream_t stream) {
+  if (!L) return fail_arg(1, "L null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (n > 24576) return fail_arg(2, "n too large for the single-CTA solve");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!y) return fail_arg(6, "y null");
+  if (!theta) return fail_arg(9, "theta null");
+  if (!w && !lml) return fail_arg(11, "w and lml both null");
+  if (batch <= 0) return fail_arg(15, "batch");
+  CK(launch_solve_alpha_lml(L, n, ldl, s_l, invdiag, ocbo_invdiag_elems(n), y, s_y, nv, theta,
+                            s_theta, nullptr, 0, lml, info, batch, (cudaStream_t)stream, w, s_w),
+     "ocbo_solve_forward_lml");
+  return 0;
+}
+
+int ocbo_post_mean_var_from_v(const double* V, int n, int ldv, int64_t s_v, const int32_t* nv,
+                              const double* w, int64_t s_w, const double* theta, int64_t s_theta,
+                              int m, const int32_t* mv, double* mean, int64_t s_mean, double* var,
+                              int64_t s_var, int batch, ocbo_stream_t stream) {
+  if (n < 0) return fail_arg(2, "n");
+  if (n > 0 && (!V || !w)) return fail_arg(1, "V / w null");
+  if (!theta) return fail_arg(8, "theta null");
+  if (m <= 0) return fail_arg(10, "m");
+  if (!mean && !var) return fail_arg(12, "mean and var both null");
+  if (batch <= 0) return fail_arg(16, "batch");
+  CK(launch_post_var_ei(V, n, ldv, s_v, nv, nullptr, 0, theta, s_theta, nullptr, m, mv, var, s_var,
+                        nullptr, 0, batch, (cudaStream_t)stream, w, s_w, mean, s_mean),
+     "ocbo_post_mean_var_from_v");
+  return 0;
+}
+
 int ocbo_post_var_ei(const double* V, int n, int ldv, int64_t s_v, const int32_t* nv,
                      const double* mean, int64_t s_mean, const double* theta, int64_t s_theta,
                      const double* best, int m, const int32_t* mv, double* var, int64_t s_var,

@@ -63,14 +63,16 @@ cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, cons
                                const double* mean, int64_t sMean, const double* theta,
                                int64_t sTheta, const double* best, int m, const int32_t* mv,
                                double* var, int64_t sVar, double* ei, int64_t sEi, int batch,
-                               cudaStream_t st);
+                               cudaStream_t st, const double* w = nullptr, int64_t sW = 0,
+                               double* mean_out = nullptr, int64_t sMeanOut = 0);
 cudaError_t launch_potrf_diag_reg(double* A, int lda, int64_t sA, int j0, double* invdiag,
                                   int64_t sInv, int32_t* info, int batch, cudaStream_t st);
 cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,
                                    const double* invdiag, int64_t sInv, const double* y, int64_t sY,
                                    const int32_t* nv, const double* theta, int64_t sTheta,
                                    double* alpha, int64_t sAlpha, double* lml,
-                                   const int32_t* info, int batch, cudaStream_t st);
+                                   const int32_t* info, int batch, cudaStream_t st,
+                                   double* w = nullptr, int64_t sW = 0);
 cudaError_t launch_post_mean(int kind, int dim, const double* Xs, int m, int64_t sXs,
                              const int32_t* mv, const double* X, int n, int64_t sX,
                              const int32_t* nv, const double* theta, int64_t sTheta,

@@ -195,6 +195,7 @@ struct SolveArgs {
   const double* theta; int64_t sTheta;
   double* alpha; int64_t sAlpha; double* lml;
   const int32_t* info;
+  double* w; int64_t sW;  // optional: w = L^{-1}(y - mu0) (mean = mu0 + V^T w needs no back-solve)
 };
 
 __global__ void __launch_bounds__(256) solve_alpha_lml_kernel(SolveArgs a) {
@@ -251,6 +252,10 @@ __global__ void __launch_bounds__(256) solve_alpha_lml_kernel(SolveArgs a) {
     for (int w = 0; w < 8; ++w) s += red[w];
     a.lml[b] = s - 0.5 * (double)nv * 1.8378770664093453;  // log(2 pi)
   }
+  if (a.w) {
+    double* wout = a.w + (size_t)b * a.sW;
+    for (int i = tid; i < n; i += 256) wout[i] = r[i];
+  }
   if (!a.alpha) return;
   // backward: alpha = L^{-T} w
   for (int I = nblk - 1; I >= 0; --I) {
@@ -281,8 +286,10 @@ cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,
                                    const double* invdiag, int64_t sInv, const double* y, int64_t sY,
                                    const int32_t* nv, const double* theta, int64_t sTheta,
                                    double* alpha, int64_t sAlpha, double* lml,
-                                   const int32_t* info, int batch, cudaStream_t st) {
-  SolveArgs a{L, n, ldl, sL, invdiag, sInv, y, sY, nv, theta, sTheta, alpha, sAlpha, lml, info};
+                                   const int32_t* info, int batch, cudaStream_t st, double* w,
+                                   int64_t sW) {
+  SolveArgs a{L, n, ldl, sL, invdiag, sInv, y, sY, nv, theta, sTheta, alpha, sAlpha, lml, info,
+              w, sW};
   const int smem = (n + NB) * 8;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(solve_alpha_lml_kernel,

@@ -127,16 +127,18 @@ class SweepStep(object):
              _p(th), th.stride(0), _p(self.LK), n, self.LK.stride(0), B,
              _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE, st)
         call('ocbo_potrf', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK), _p(infoK), B, st)
-        call('ocbo_solve_alpha_lml', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK),
+        # w = L_K^{-1}(y - mu0) (+ LML); the mean is mu0 + V^T w, one HBM pass over V
+        # instead of a second sweep over the kernel and a back-substitution
+        call('ocbo_solve_forward_lml', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK),
              _p(self.y), self.y.stride(0), None, _p(th), th.stride(0), _p(self.alpha),
              self.alpha.stride(0), _p(self.lml), _p(infoK), B, st)
-        call('ocbo_post_mean', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(X), n, X.stride(0),
-             None, _p(th), th.stride(0), _p(self.alpha), self.alpha.stride(0), _p(self.mean),
-             self.mean.stride(0), B, st)
         call('ocbo_gram', self.kind, D, _p(X), n, X.stride(0), None, _p(Xs), m, Xs.stride(0), None,
              _p(th), th.stride(0), _p(self.V), m, self.V.stride(0), B, 0, st)
         call('ocbo_trsm_lower', _p(self.LK), n, n, self.LK.stride(0), _p(self.invdK), _p(self.V), m,
              m, self.V.stride(0), _p(infoK), B, st)
+        call('ocbo_post_mean_var_from_v', _p(self.V), n, m, self.V.stride(0), None, _p(self.alpha),
+             self.alpha.stride(0), _p(th), th.stride(0), m, None, _p(self.mean), self.mean.stride(0),
+             None, 0, B, st)
         call('ocbo_post_cov', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
              self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B, st)
         call('ocbo_potrf', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(infoS), B, st)
