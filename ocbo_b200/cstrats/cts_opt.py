@@ -1,10 +1,19 @@
-"""Continuous-context BO loop with one GP over (context, action) -- host mirror
-of the reference's ``ContinuousOpt`` (/root/reference/src/cstrats/cts_opt.py) so
-its driver (src/cts_ocbo.py:95-140) and option files run on the B200 engine.
+"""Continuous-context BO loop (one GP over context (+) action) on the B200 engine.
 
-Same constructor ``(function, domain, ctx_dim, options, eval_set=None,
-ctx_constraints=None)``, ``get_eval_set / set_clean / optimize(max_capital,
-init_pts, pre_tune=False, hp_tune_samps=None) / get_strat_name`` and histories.
+Plays the role of the reference's ``ContinuousOpt``
+(/root/reference/src/cstrats/cts_opt.py): constructor ``(function, domain,
+ctx_dim, options, eval_set=None, ctx_constraints=None)``, ``optimize(max_capital,
+init_pts, pre_tune=False, hp_tune_samps=None)``, ``get_eval_set / set_eval_set /
+set_clean / set_gp / suggest_next_eval / receive_feedback / get_strat_name`` and
+the histories its driver stores (src/cts_ocbo.py:95-140).  The organisation is
+our own: the scoring grid and the posterior-mean policy score live in
+``PolicyScore``; the loop is "suggest -> evaluate -> absorb".
+
+Behaviour kept: hyper-parameters are refit every ``tune_every`` evaluations;
+every ``score_every`` evaluations a separate ML-tuned GP scores the greedy policy
+on the evaluation grid (reference :297-323) -- on the device this is one fused
+Gram x alpha pass over the 10^4 grid points; the global numpy stream is consumed
+in the reference's order.
 """
 from argparse import Namespace
 from copy import deepcopy
@@ -30,61 +39,110 @@ cts_opt_args = [
 ]
 
 
+class PolicyScore(object):
+    """Evaluation grid (contexts x actions) and the greedy posterior-mean policy score."""
+
+    def __init__(self, pts, grid):
+        self.pts, self.grid = pts, grid
+
+    @classmethod
+    def draw(cls, ctx_domain, act_domain, ctx_fidel, act_fidel):
+        """Random grid: every context paired with the SAME random actions (:332-350)."""
+        ctxs = uniform_draw(ctx_domain, ctx_fidel)
+        acts = uniform_draw(act_domain, act_fidel)
+        pts = np.hstack([np.repeat(ctxs, act_fidel, axis=0), np.tile(acts, (ctx_fidel, 1))])
+        return cls(pts, pts.reshape(ctx_fidel, act_fidel, pts.shape[1]))
+
+    @property
+    def shape(self):
+        return self.grid.shape[:2]
+
+    def oracle_best(self, function):
+        vals = np.asarray([function(p) for p in self.pts]).reshape(self.shape)
+        return np.mean(np.max(vals, axis=1))
+
+    def greedy(self, gp, function, pts=None, grid=None):
+        pts = self.pts if pts is None else pts
+        grid = self.grid if grid is None else grid
+        mu = gp.eval(pts)[0].reshape(grid.shape[:2])
+        chosen = grid[np.arange(grid.shape[0]), np.argmax(mu, axis=1), :]
+        total = 0
+        for p in chosen:
+            total += function(p)
+        return total / grid.shape[0], chosen
+
+
 class ContinuousOpt(object):
 
     def __init__(self, function, domain, ctx_dim, options, eval_set=None, ctx_constraints=None,
                  is_synthetic=True):
-        self.function = function
-        self.domain = domain
+        self.function, self.domain = function, domain
+        self.ctx_dim, self.dim = ctx_dim, len(domain)
+        self.act_dim = self.dim - ctx_dim
         self.ctx_domain, self.act_domain = domain[:ctx_dim], domain[ctx_dim:]
-        self.dim, self.ctx_dim, self.act_dim = len(domain), ctx_dim, len(domain) - ctx_dim
         self.is_synthetic = is_synthetic
-        if eval_set is None:
-            self.eval_ctx_fidel = options.eval_ctx_fidel
-            self.eval_act_fidel = options.eval_act_fidel
-            self.eval_pts, self.eval_grid = self._get_eval_set()
-            self._find_best_score()
-        elif is_synthetic:
-            self.set_eval_set(eval_set[0], eval_set[1])
         self.ctx_constraints = ctx_constraints
         self.options = options
-        self.eval_ctx_fidel = options.eval_ctx_fidel
-        self.eval_act_fidel = options.eval_act_fidel
-        self.score_every = options.score_every
-        self.tune_every = options.tune_every
-        self.gp_engine = options.gp_engine
-        self.cand_size = options.cand_size
-        self.gp_options = load_options(euclidean_gp_args, cmd_line=False)
-        self.gp_options.kernel_type = options.kernel_type
-        self.gp_options.hp_tune_criterion = options.tuning_methods
-        self.gp_options.hp_samples = options.hp_samples
-        self.gp_options.dim = self.dim
-        self.gp_options.act_dim = self.act_dim
-        self.gp_options.use_additive_gp = options.use_additive_gp
-        self.gp_options.add_max_group_size = options.add_max_group_size
+        if eval_set is None:
+            self._install_score(PolicyScore.draw(self.ctx_domain, self.act_domain,
+                                                 options.eval_ctx_fidel, options.eval_act_fidel))
+        elif is_synthetic:
+            self.set_eval_set(eval_set[0], eval_set[1])
+        self.eval_ctx_fidel, self.eval_act_fidel = options.eval_ctx_fidel, options.eval_act_fidel
+        self.score_every, self.tune_every = options.score_every, options.tune_every
+        self.gp_engine, self.cand_size = options.gp_engine, options.cand_size
+        gp_opts = load_options(euclidean_gp_args, cmd_line=False)
+        for key, val in (('kernel_type', options.kernel_type),
+                         ('hp_tune_criterion', options.tuning_methods),
+                         ('hp_samples', options.hp_samples), ('dim', self.dim),
+                         ('act_dim', self.act_dim), ('use_additive_gp', options.use_additive_gp),
+                         ('add_max_group_size', options.add_max_group_size)):
+            setattr(gp_opts, key, val)
         if hasattr(options, 'hp_search_candidates'):
-            self.gp_options.hp_search_candidates = options.hp_search_candidates
-        self.eval_options = deepcopy(self.gp_options)
-        self.eval_options.hp_tune_criterion = 'ml'
+            gp_opts.hp_search_candidates = options.hp_search_candidates
+        self.gp_options = gp_opts
+        self.eval_options = deepcopy(gp_opts)
+        self.eval_options.hp_tune_criterion = 'ml'  # the scoring GP is always ML-tuned (:99-100)
         self._child_set_up(function, domain, ctx_dim, options)
         self.set_clean()
 
-    def set_clean(self):
-        self.gp = None
-        self.gp_fitter = None
-        self.x_data, self.x_init, self.y_data, self.y_init = [], [], [], []
-        self.query_history, self.score_history, self.hp_history = [], [], []
-        self.t = 0
-        self.pre_loaded_fit = False
+    # ------------------------------------------------------------------ evaluation grid
+    def _install_score(self, score):
+        self._score = score
+        self.eval_pts, self.eval_grid = score.pts, score.grid
+        self.best_score = score.oracle_best(self.function)
 
+    def get_eval_set(self):
+        return self.eval_pts, self.eval_grid
+
+    def set_eval_set(self, eval_pts, eval_grid):
+        self._install_score(PolicyScore(eval_pts, eval_grid))
+        self.eval_ctx_fidel, self.eval_act_fidel = eval_grid.shape[:2]
+
+    # ------------------------------------------------------------------ run state
+    def set_clean(self):
+        self.gp = self.gp_fitter = None
+        self.x_data, self.y_data, self.x_init, self.y_init = [], [], [], []
+        self.query_history, self.score_history, self.hp_history = [], [], []
+        self.pre_loaded_fit = False
+        self.t = 0
+
+    def get_histories(self):
+        return Namespace(query_history=self.query_history, score_history=self.score_history,
+                         hp_history=self.hp_history, x_init=self.x_init, y_init=self.y_init)
+
+    def set_gp(self, gp):
+        self.gp, self.pre_loaded_fit = gp, True
+
+    # ------------------------------------------------------------------ main loop
     def optimize(self, max_capital, init_pts, pre_tune=False, hp_tune_samps=None):
-        init_rewards = [self.function(pt) for pt in init_pts]
+        rewards = [self.function(pt) for pt in init_pts]
         if hp_tune_samps is not None:
-            self.pre_tune_gp(hp_tune_samps, init_pts, init_rewards)
+            self.pre_tune_gp(hp_tune_samps, init_pts, rewards)
         elif pre_tune:
-            self.pre_load_points(init_pts, init_rewards)
+            self.pre_load_points(init_pts, rewards)
         else:
-            self.load_init_pts(init_pts, init_rewards)
+            self.load_init_pts(init_pts, rewards)
         for _ in range(max_capital):
             pt = self.suggest_next_eval()
             self.receive_feedback(pt, self.function(pt))
@@ -104,47 +162,29 @@ class ContinuousOpt(object):
         if not self.pre_loaded_fit and self.t % self.tune_every == 0:
             self._make_new_gp_fitter()
 
-    def load_init_pts(self, eval_pts, rewards):
+    # three ways of starting a run (:170-214)
+    def _remember_init(self, eval_pts, rewards):
         self.x_data += eval_pts
         self.y_data += rewards
         self.x_init, self.y_init = eval_pts, rewards
+
+    def load_init_pts(self, eval_pts, rewards):
+        self._remember_init(eval_pts, rewards)
         self._make_new_gp_fitter()
 
     def pre_load_points(self, eval_pts, rewards):
-        self.x_data += eval_pts
-        self.y_data += rewards
-        self.x_init, self.y_init = eval_pts, rewards
-        self.pre_loaded_fit = True
-        self.gp = get_tuned_gp(self.gp_engine, eval_pts, rewards,
-                               kernel_type=self.gp_options.kernel_type)[0]
+        self._remember_init(eval_pts, rewards)
+        self.set_gp(get_tuned_gp(self.gp_engine, eval_pts, rewards,
+                                 kernel_type=self.gp_options.kernel_type)[0])
 
     def pre_tune_gp(self, hp_tune_samps, eval_pts, rewards):
-        self.x_data += eval_pts
-        self.y_data += rewards
-        self.x_init, self.y_init = eval_pts, rewards
-        self.pre_loaded_fit = True
-        self.gp = get_best_prior(self.function, self.domain,
-                                 kernel_type=self.gp_options.kernel_type,
-                                 num_samples=hp_tune_samps, gp_engine=self.gp_engine)
+        self._remember_init(eval_pts, rewards)
+        self.set_gp(get_best_prior(self.function, self.domain, kernel_type=self.gp_options.kernel_type,
+                                   num_samples=hp_tune_samps, gp_engine=self.gp_engine))
         for pt, rew in zip(eval_pts, rewards):
             self.gp.add_data_single(pt, rew)
 
-    def get_histories(self):
-        return Namespace(query_history=self.query_history, score_history=self.score_history,
-                         hp_history=self.hp_history, x_init=self.x_init, y_init=self.y_init)
-
-    def get_eval_set(self):
-        return self.eval_pts, self.eval_grid
-
-    def set_eval_set(self, eval_pts, eval_grid):
-        self.eval_pts, self.eval_grid = eval_pts, eval_grid
-        self.eval_ctx_fidel, self.eval_act_fidel = eval_grid.shape[:2]
-        self._find_best_score()
-
-    def set_gp(self, gp):
-        self.gp = gp
-        self.pre_loaded_fit = True
-
+    # ------------------------------------------------------------------ to be specialised
     @staticmethod
     def get_strat_name():
         raise NotImplementedError('Abstract Method')
@@ -155,25 +195,16 @@ class ContinuousOpt(object):
     def _child_set_up(self, function, domain, ctx_dim, options):
         pass
 
+    # ------------------------------------------------------------------ helpers
+    def _get_ctx_candidates(self, num_candidates):
+        if self.ctx_constraints is not None:
+            picks = np.random.randint(0, len(self.ctx_constraints), num_candidates)
+            return np.asarray([self.ctx_constraints[i] for i in picks])
+        return uniform_draw(self.ctx_domain, num_candidates)
+
     def _make_candidate_set(self):
         ctxs = self._get_ctx_candidates(self.cand_size).reshape(self.cand_size, self.ctx_dim)
         return np.hstack([ctxs, uniform_draw(self.act_domain, self.cand_size)])
-
-    def _get_ctx_candidates(self, num_candidates):
-        if self.ctx_constraints is None:
-            lows, highs = zip(*self.ctx_domain)
-            return np.random.uniform(lows, highs, (num_candidates, len(lows)))
-        idxs = np.random.randint(0, len(self.ctx_constraints), num_candidates)
-        return np.asarray([self.ctx_constraints[i] for i in idxs])
-
-    def _update_history(self, pt, reward):
-        self.query_history.append(Namespace(t=self.t, pt=pt, reward=reward))
-        if self.is_synthetic and self.score_every is not None and self.t % self.score_every == 0:
-            score = self._get_current_score()
-            self.score_history.append(Namespace(t=self.t, score=score,
-                                                regret=self.best_score - score))
-        if self.gp is not None:
-            self.hp_history.append(Namespace(t=self.t, hps=self.gp.get_kernel_hps()))
 
     def _draw_next_gp(self):
         if self.pre_loaded_fit:
@@ -185,35 +216,28 @@ class ContinuousOpt(object):
         self.gp_fitter = get_gp_fitter(self.gp_engine, self.x_data, self.y_data, self.gp_options)
         self.gp_fitter.fit_gp()
 
+    def _scoring_gp(self):
+        if self.pre_loaded_fit:
+            return self.gp
+        fitter = get_gp_fitter(self.gp_engine, self.x_data, self.y_data, self.eval_options)
+        fitter.fit_gp()
+        return fitter.get_next_gp()
+
     def _get_current_score(self, return_max_pts=False, eval_gp=None, e_pts=None, e_grid=None):
-        """Posterior-mean policy score (cts_opt.py:297-323): fused Gram x alpha on
-        the device, never materialising K(eval_pts, X)."""
-        if eval_gp is None:
-            if self.pre_loaded_fit:
-                eval_gp = self.gp
-            else:
-                fitter = get_gp_fitter(self.gp_engine, self.x_data, self.y_data, self.eval_options)
-                fitter.fit_gp()
-                eval_gp = fitter.get_next_gp()
+        gp = self._scoring_gp() if eval_gp is None else eval_gp
         if e_pts is None or e_grid is None:
-            e_pts, e_grid = self.eval_pts, self.eval_grid
-        mu = eval_gp.eval(e_pts)[0].reshape(e_grid.shape[:2])
-        max_pts = e_grid[np.arange(e_grid.shape[0]), np.argmax(mu, axis=1), :]
-        score = 0
-        for max_pt in max_pts:
-            score += self.function(max_pt)
-        avg = score / e_grid.shape[0]
-        return (avg, max_pts) if return_max_pts else avg
+            e_pts = e_grid = None
+        avg, chosen = self._score.greedy(gp, self.function, e_pts, e_grid)
+        return (avg, chosen) if return_max_pts else avg
 
     def _find_best_score(self):
-        evals = np.asarray([self.function(pt) for pt in self.eval_pts])
-        self.best_score = np.mean(np.max(evals.reshape(self.eval_grid.shape[:2]), axis=1))
+        self.best_score = self._score.oracle_best(self.function)
 
-    def _get_eval_set(self, ctx_fidel=None, act_fidel=None):
-        ctx_fidel = self.eval_ctx_fidel if ctx_fidel is None else ctx_fidel
-        act_fidel = self.eval_act_fidel if act_fidel is None else act_fidel
-        ctxs = np.repeat(uniform_draw(self.ctx_domain, ctx_fidel), act_fidel, axis=0)
-        acts = uniform_draw(self.act_domain, act_fidel)
-        acts = np.tile(acts.ravel(), ctx_fidel).reshape(ctx_fidel * act_fidel, self.act_dim)
-        eval_pts = np.hstack([ctxs, acts])
-        return eval_pts, eval_pts.reshape(ctx_fidel, act_fidel, self.ctx_dim + self.act_dim)
+    def _update_history(self, pt, reward):
+        self.query_history.append(Namespace(t=self.t, pt=pt, reward=reward))
+        scoring = self.is_synthetic and self.score_every is not None and self.t % self.score_every == 0
+        if scoring:
+            score = self._get_current_score()
+            self.score_history.append(Namespace(t=self.t, score=score, regret=self.best_score - score))
+        if self.gp is not None:
+            self.hp_history.append(Namespace(t=self.t, hps=self.gp.get_kernel_hps()))

@@ -1,40 +1,50 @@
-"""Joint-GP Multi-task Thompson Sampling -- host mirror of
-/root/reference/src/strategies/joint_mts.py:11-57.
+"""Joint-GP Multi-task Thompson Sampling on the B200 engine.
 
-One joint posterior sample over [all past points (task by task) ; T x A grid
-(task-major)]; the per-task reduction (old best, gains, arg-max task then
-action: :43-57) runs on the device (ocbo_segment_argmax + ocbo_joint_pick), so
-only (task, action index, gain) comes back to the host."""
+Plays the role of the reference's ``JointMTS``
+(/root/reference/src/strategies/joint_mts.py:11-57): ONE joint posterior sample
+over [every past query, task by task ; the T x A candidate grid, task-major],
+then per task ``gain = sample(new) - max sample(old)``, arg-max over tasks, then
+over that task's actions (np.argmax: first maximum wins).
+
+Only the candidate layout is assembled on the host; posterior, covariance,
+Cholesky (with Dragonfly's jitter ladder), sample and the whole reduction run on
+the device (``B200GPCore.sample_and_pick`` -> ocbo_segment_argmax +
+ocbo_joint_pick), so (task, action index, gain) is all that comes back.
+"""
 import numpy as np
 
 from .joint_opt import JointOpt
 from ..util import sample_grid
 
 
-class JointMTS(JointOpt):
+def joint_layout(f_locs, per_task_points, grid):
+    """Rows to sample and their segmentation: T segments of old points (in task
+    order) followed by T grid segments of equal length."""
+    T = len(f_locs)
+    counts = [len(p) for p in per_task_points]
+    old_rows = [np.append(f_locs[t], pt) for t in range(T) for pt in per_task_points[t]]
+    n_old = sum(counts)
+    width = grid.shape[1]
+    rows = np.vstack([np.asarray(old_rows, dtype=np.float64).reshape(n_old, width), grid])
+    per_task = len(grid) // T
+    bounds = np.concatenate([[0], np.cumsum(counts), n_old + per_task * np.arange(1, T + 1)])
+    return rows, bounds.astype(np.int32)
 
-    def decide_next_query(self):
-        self.gps[0].build_posterior()
-        return self._find_best_query()
+
+class JointMTS(JointOpt):
 
     @staticmethod
     def get_opt_method_name():
         return 'joint-mts'
 
+    def decide_next_query(self):
+        self.gps[0].build_posterior()
+        return self._find_best_query()
+
     def _find_best_query(self):
-        A = self.options.max_opt_evals
-        T = len(self.fcns)
-        grid_pts = sample_grid(self.f_locs, self.domains[0], A)
-        past_pts, num_qs = [], []
-        for f_idx, f_name in enumerate(self.f_names):
-            for hist in self.query_history[f_name]:
-                past_pts.append(np.append(self.f_locs[f_idx], hist.pt))
-            num_qs.append(len(self.query_history[f_name]))
-        total_qs = sum(num_qs)
-        to_samp = np.vstack([np.asarray(past_pts).reshape(total_qs, -1), grid_pts])
-        divs = np.concatenate([[0], np.cumsum(num_qs)])
-        seg = np.concatenate([divs, total_qs + A * np.arange(1, T + 1)]).astype(np.int32)
-        best_ctx, best_idx, _ = self.gps[0].gp_core.sample_and_pick(to_samp, seg, T)
-        loc_dim = len(self.f_locs[0])
-        best_pt = grid_pts.reshape((T, A, -1))[best_ctx, best_idx, :].ravel()
-        return best_ctx, best_pt[loc_dim:]
+        T, A = len(self.fcns), self.options.max_opt_evals
+        grid = sample_grid(self.f_locs, self.domains[0], A)       # consumes the global stream first
+        asked = [[q.pt for q in self.query_history[name]] for name in self.f_names]
+        rows, bounds = joint_layout(self.f_locs, asked, grid)
+        task, action, _ = self.gps[0].gp_core.sample_and_pick(rows, bounds, T)
+        return task, grid[task * A + action, len(self.f_locs[0]):]

@@ -1,16 +1,22 @@
-"""Discrete multi-task BO loop with one GP per task -- host-side mirror of the
-reference's ``MultiOpt`` (/root/reference/src/strategies/multi_opt.py) so that
-its callers (src/ocbo.py:139-143,180-183) and its option files drive the B200
-engine unchanged.  Same constructor, attributes, public methods and state
-machine; the GP work goes through ``get_gp_fitter`` with ``gp_engine='b200'``.
+"""Discrete multi-task BO loop (one GP per task) on the B200 engine.
 
-State-machine facts honoured:
-  * per step: draw GPs -> decide -> f(pt) -> add point -> history (-> refit)
-    (reference :122-129);
-  * the risk-neutral update sees the GP after ``add_data_single`` and before
-    the refit (:294-296 precede :316-319);
-  * the ``post_sampling`` cache: once a task holds ``hp_samples`` drawn GPs it
-    keeps re-using the right-most one until that task is refit (:226-236,:286).
+Plays the role of the reference's ``MultiOpt``
+(/root/reference/src/strategies/multi_opt.py): same constructor
+``(f_infos, options, pre_tuned_gps=None, rn_info=None)``, same public methods
+(``optimize, set_clean, get_histories, prep_for_optimization,
+draw_and_suggest_query, receive_feedback, get_method_name_with_tuning``) and the
+same history attributes, so the drivers (src/ocbo.py:139-143,180-183) and the
+option files work unchanged.  The organisation is our own: bookkeeping lives in
+``TaskLedger``; what differs between independent-GP and joint-GP strategies is
+expressed through four small hooks (``_gp_input``, ``_refit``, ``_next_gps``,
+``_rn_query``) instead of re-implemented loops.
+
+Behaviour kept from the reference (SURVEY 8a "state-machine facts"):
+  * per step: draw GPs -> decide -> f(pt) -> add point -> log (-> refit)   (:122-129)
+  * the risk-neutral pick sees the GP after the new point, before the refit (:294-296,:316-319)
+  * the ``post_sampling`` cache: once a task holds ``hp_samples`` drawn GPs the
+    right-most one is re-used until that task is refit                     (:226-236,:286)
+  * the global numpy stream is consumed in the same order
 """
 from argparse import Namespace
 from collections import deque
@@ -18,6 +24,7 @@ from copy import deepcopy
 
 import numpy as np
 
+from .ledger import TaskLedger
 from ..gp.gp_util import get_gp_fitter
 from ..options import euclidean_gp_args, get_option_specs, load_options
 
@@ -32,6 +39,11 @@ multi_opt_args = [
 ]
 
 
+def _box(domain):
+    lows, highs = zip(*domain)
+    return lows, highs
+
+
 class MultiOpt(object):
 
     def __init__(self, f_infos, options, pre_tuned_gps=None, rn_info=None):
@@ -39,32 +51,32 @@ class MultiOpt(object):
         self.domains = [fi.domain for fi in f_infos]
         self.dims = [len(d) for d in self.domains]
         self.f_names = [fi.name for fi in f_infos]
+        self.options = options
         self.pre_tuned_gps = pre_tuned_gps
         self.tune_every = options.tune_every
-        self.options = options
         self.risk_neutral = options.risk_neutral
+        self.hp_samples = options.hp_samples
+        self.gp_engine = getattr(options, 'gp_engine', 'b200')
+        # risk-neutral evaluation grids are shared between methods through rn_info
         if rn_info is not None:
             self.rn_grids, self.rn_bests = rn_info
         elif self.risk_neutral:
-            self.rn_grids, self.rn_bests = self._create_rn_grids()
+            grids = [self._rn_grid(f) for f in range(len(self.fcns))]
+            self.rn_grids = grids
+            self.rn_bests = [self._grid_optimum(f, g) for f, g in enumerate(grids)]
         else:
-            self.rn_grids, self.rn_bests = None, None
-        self.gp_options = load_options(euclidean_gp_args, cmd_line=False)
-        self.gp_options.kernel_type = options.kernel_type
-        self.gp_options.hp_tune_criterion = '-'.join(str(options.tuning_methods).split(','))
-        self.gp_options.hp_samples = options.hp_samples
+            self.rn_grids = self.rn_bests = None
+        gp_opts = load_options(euclidean_gp_args, cmd_line=False)
+        gp_opts.kernel_type = options.kernel_type
+        gp_opts.hp_tune_criterion = str(options.tuning_methods).replace(',', '-')
+        gp_opts.hp_samples = options.hp_samples
         if hasattr(options, 'hp_search_candidates'):
-            self.gp_options.hp_search_candidates = options.hp_search_candidates
-        self.hp_samples = options.hp_samples
-        self.gp_engine = getattr(options, 'gp_engine', 'b200')
-        self.gps = self.gp_fitters = self.sampled_gps = None
-        self.query_history = self.curr_best = self.total_best = None
-        self.choice_timeline = self.allocation_count = None
-        self.rn_choice = self.rn_total = None
+            gp_opts.hp_search_candidates = options.hp_search_candidates
+        self.gp_options = gp_opts
         self.t = 0
         self.set_clean()
 
-    # ---- to be provided by the strategy ---------------------------------------
+    # ------------------------------------------------------------------ strategy API
     def decide_next_query(self):
         raise NotImplementedError('Child implementation missing.')
 
@@ -73,33 +85,61 @@ class MultiOpt(object):
         raise NotImplementedError('Child implementation missing.')
 
     def get_method_name_with_tuning(self):
-        return '-'.join([self.gp_options.hp_tune_criterion, self.get_opt_method_name()])
+        return '%s-%s' % (self.gp_options.hp_tune_criterion, self.get_opt_method_name())
 
-    # ---- public loop ------------------------------------------------------------
+    # ------------------------------------------------------------------ run state
+    def set_clean(self):
+        num = len(self.f_names)
+        self.gps = self._fresh_pretuned() if self.pre_tuned_gps is not None else [None] * num
+        self.gp_fitters = [None] * num
+        self.sampled_gps = [deque() for _ in range(num)]
+        self._ledger = TaskLedger(self.f_names, self.risk_neutral)
+        # the reference's attribute names, bound to the ledger's containers
+        led = self._ledger
+        self.query_history, self.curr_best, self.rn_choice = led.query_history, led.curr_best, led.rn_choice
+        self.total_best, self.rn_total = led.total_best, led.rn_total
+        self.choice_timeline, self.allocation_count = led.choice_timeline, led.allocation_count
+        self.t = 0
+
+    def _fresh_pretuned(self):
+        return [deepcopy(gp) for gp in self.pre_tuned_gps]
+
+    def get_histories(self):
+        return self._ledger.as_histories()
+
+    # ------------------------------------------------------------------ main loop
     def optimize(self, capital, init_capital=5, init_pts=None):
-        if init_pts is not None:
-            self._handle_init_pts(init_pts)
-        else:
+        tuned = self.pre_tuned_gps is not None
+        if init_pts is None:
             for f_idx in range(len(self.fcns)):
-                self._make_random_queries(f_idx, init_capital)
-        if self.pre_tuned_gps is None:
+                for _ in range(init_capital):
+                    self._evaluate_and_log(f_idx, np.random.uniform(*_box(self.domains[f_idx])), True)
+        else:
+            for f_idx, pts in enumerate(init_pts):
+                for pt in pts:
+                    self._evaluate_and_log(f_idx, pt, True)
+        if not tuned:
             self._update_models()
         for _ in range(capital):
             self.t += 1
-            if self.pre_tuned_gps is None:
+            if not tuned:
                 self._draw_next_gps()
             f_idx, pt = self.decide_next_query()
-            val = self.fcns[f_idx](pt)
-            self._add_point_to_gp(f_idx, pt, val)
-            self._update_history(f_idx, pt, val)
+            self._evaluate_and_log(f_idx, pt, False)
         return self.get_histories()
 
+    def _evaluate_and_log(self, f_idx, pt, is_init):
+        val = self.fcns[f_idx](pt)
+        if self.gps[f_idx] is not None:
+            self._add_point_to_gp(f_idx, pt, val)
+        self._update_history(f_idx, pt, val, init_pt=is_init)
+
+    # ask / tell interface (reference :133-167)
     def prep_for_optimization(self, init_evals):
         for q_info in init_evals:
-            idx = self.f_names.index(q_info.f_name)
-            q_info.init_pt = True
-            q_info.t = 0
-            self._update_history(idx, q_info.pt, q_info.val, init_pt=True, q_info=q_info)
+            q_info.init_pt, q_info.t = True, 0
+            self._update_history(self.f_names.index(q_info.f_name), q_info.pt, q_info.val,
+                                 init_pt=True, q_info=q_info)
         self._update_models()
 
     def draw_and_suggest_query(self):
@@ -109,120 +149,83 @@ class MultiOpt(object):
 
     def receive_feedback(self, q_info):
         self.t += 1
-        idx = self.f_names.index(q_info.f_name)
         q_info.t = self.t
-        self._update_history(idx, q_info.pt, q_info.val, q_info=q_info)
+        self._update_history(self.f_names.index(q_info.f_name), q_info.pt, q_info.val, q_info=q_info)
 
-    def get_histories(self):
-        return Namespace(query_history=self.query_history, curr_best=self.curr_best,
-                         total_best=self.total_best, choice_timeline=self.choice_timeline,
-                         rn_choice=self.rn_choice, rn_total=self.rn_total)
+    # ------------------------------------------------------------------ hooks
+    def _gp_input(self, f_idx, pt):
+        """The point as task ``f_idx``'s GP sees it."""
+        return pt
 
-    def set_clean(self):
-        if self.pre_tuned_gps is not None:
-            self.gps = [deepcopy(gp) for gp in self.pre_tuned_gps]
-        else:
-            self.gps = [None] * len(self.f_names)
-        self.gp_fitters = [None] * len(self.f_names)
-        self.sampled_gps = [deque() for _ in self.f_names]
-        self.query_history = {fn: [] for fn in self.f_names}
-        self.curr_best = {fn: [] for fn in self.f_names}
-        self.rn_choice = {fn: [] for fn in self.f_names}
-        self.total_best, self.rn_total, self.choice_timeline = [], [], []
-        self.allocation_count = [0] * len(self.f_names)
-        self.t = 0
-
-    # ---- hooks subclasses override ----------------------------------------------
     def _add_point_to_gp(self, f_idx, pt, val):
-        self.gps[f_idx].add_data_single(pt, val)
+        self.gps[f_idx].add_data_single(self._gp_input(f_idx, pt), val)
 
-    def _handle_init_pts(self, init_pts):
-        for idx, pts in enumerate(init_pts):
-            for pt in pts:
-                val = self.fcns[idx](pt)
-                if self.gps[idx] is not None:
-                    self._add_point_to_gp(idx, pt, val)
-                self._update_history(idx, pt, val, init_pt=True)
+    def _refit(self, f_idx):
+        """New hyper-parameter fit for task ``f_idx`` from its own observations."""
+        xs, ys = self._ledger.observations(f_idx)
+        fitter = get_gp_fitter(self.gp_engine, xs, ys, self.gp_options)
+        fitter.fit_gp()
+        self.gp_fitters[f_idx] = fitter
+        self.sampled_gps[f_idx] = deque()
 
-    def _make_random_queries(self, f_idx, queries):
-        for _ in range(queries):
-            low, high = zip(*self.domains[f_idx])
-            pt = np.random.uniform(low, high)
-            val = self.fcns[f_idx](pt)
-            if self.gps[f_idx] is not None:
-                self._add_point_to_gp(f_idx, pt, val)
-            self._update_history(f_idx, pt, val, init_pt=True)
+    def _next_gps(self):
+        """One GP per task for the coming decision."""
+        cycling = 'post_sampling' in self.gp_options.hp_tune_criterion and self.hp_samples > 1
+        out = []
+        for f_idx, fitter in enumerate(self.gp_fitters):
+            if not cycling:
+                out.append(fitter.get_next_gp())
+                continue
+            cache = self.sampled_gps[f_idx]
+            gp = cache.pop() if len(cache) == self.hp_samples else fitter.get_next_gp()
+            cache.append(gp)
+            out.append(gp)
+        return out
+
+    def _rn_grid(self, f_idx):
+        return np.random.uniform(*_box(self.domains[f_idx]),
+                                 (self.options.rn_eval_size, len(self.domains[f_idx])))
+
+    def _rn_query(self, f_idx, grid_row):
+        """Action to evaluate for a row of the risk-neutral grid."""
+        return grid_row
+
+    def _grid_optimum(self, f_idx, grid):
+        best = float('-inf')
+        for row in grid:
+            best = max(best, self.fcns[f_idx](self._rn_query(f_idx, row)))
+        return best
+
+    # names the reference's subclasses / callers use
+    def _update_models(self):
+        for f_idx in range(len(self.fcns)):
+            self._update_model(f_idx)
+
+    def _update_model(self, idx):
+        self._refit(idx)
 
     def _draw_next_gps(self):
         assert None not in self.gp_fitters
-        cycling = 'post_sampling' in self.gp_options.hp_tune_criterion and self.hp_samples > 1
-        if not cycling:
-            self.gps = [gpf.get_next_gp() for gpf in self.gp_fitters]
-            return
-        self.gps = []
-        for f_idx in range(len(self.fcns)):
-            cache = self.sampled_gps[f_idx]
-            if len(cache) == self.hp_samples:
-                nxt = cache.pop()
-            else:
-                nxt = self.gp_fitters[f_idx].get_next_gp()
-            cache.append(nxt)
-            self.gps.append(nxt)
-
-    def _update_models(self):
-        for idx in range(len(self.fcns)):
-            self._update_model(idx)
-
-    def _update_model(self, idx):
-        hist = self.query_history[self.f_names[idx]]
-        x_data = [h.pt for h in hist]
-        y_data = [h.val for h in hist]
-        gpf = get_gp_fitter(self.gp_engine, x_data, y_data, self.gp_options)
-        gpf.fit_gp()
-        self.gp_fitters[idx] = gpf
-        self.sampled_gps[idx] = deque()
+        self.gps = self._next_gps()
 
     def _rn_update(self, f_idx):
-        f_name = self.f_names[f_idx]
-        self.gps[f_idx].build_posterior()
+        """Risk-neutral pick: arg-max of the posterior mean on the task's grid (fused
+        Gram x alpha on the device), evaluated on the true function."""
+        gp = self.gps[f_idx]
+        gp.build_posterior()
         grid = self.rn_grids[f_idx]
-        mean_vals = self.gps[f_idx].eval(grid)[0].ravel()
-        rn_pt = grid[np.argmax(mean_vals)]
-        self.rn_choice[f_name].append((self.fcns[f_idx](rn_pt), rn_pt))
-
-    def _create_rn_grids(self):
-        grids, bests = [], []
-        for f_idx in range(len(self.f_names)):
-            lows, highs = zip(*self.domains[f_idx])
-            grid = np.random.uniform(lows, highs, (self.options.rn_eval_size, len(lows)))
-            best = float('-inf')
-            for pt in grid:
-                best = max(best, self.fcns[f_idx](pt))
-            grids.append(grid)
-            bests.append(best)
-        return grids, bests
+        row = grid[np.argmax(gp.eval(grid)[0].ravel())]
+        pt = self._rn_query(f_idx, row)
+        return self.fcns[f_idx](pt), pt
 
     def _update_history(self, f_idx, pt, val, init_pt=False, q_info=None):
-        self.allocation_count[f_idx] += 1
         if q_info is None:
             q_info = Namespace(pt=pt, val=val, init_pt=init_pt, time=self.t)
-        f_name = self.f_names[f_idx]
-        self.query_history[f_name].append(q_info)
+        rn_entry = None
         if self.risk_neutral:
-            if init_pt:
-                self.rn_choice[f_name].append((val, pt))
-            else:
-                self._rn_update(f_idx)
-        bests = self.curr_best[f_name]
-        if not bests or bests[-1][0] < val:
-            bests.append((val, pt))
-        else:
-            bests.append(bests[-1])
-        if self.t > 0:
-            self.total_best.append(sum(b[-1][0] for b in self.curr_best.values()))
-            self.choice_timeline.append(f_idx)
-            if self.risk_neutral:
-                self.rn_total.append(sum(r[-1][0] for r in self.rn_choice.values()))
-        if self.tune_every > 0 and self.t > 0:
-            if len(self.query_history[f_name]) % self.tune_every == 0:
-                self._update_model(f_idx)
+            rn_entry = (val, pt) if init_pt else self._rn_update(f_idx)
+        self._ledger.record(f_idx, q_info, self.t, rn_entry)
+        due = self.tune_every > 0 and self.t > 0 and \
+            self._ledger.num_queries(f_idx) % self.tune_every == 0
+        if due:
+            self._update_model(f_idx)
