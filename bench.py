@@ -376,13 +376,26 @@ def run_b200(args):
         alg = (m ** 3 / 3.0 - nt * 128.0 ** 3 / 3.0
                - sum(r * 128.0 * 128.0 ** 2 for r in range(1, nt))) * B
         ms_upd = ms3[2] + ms3[3]
-        trailing_tflops = alg / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else None
+        all_updates_tflops = alg / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else None
+        # the kernel's dominant role: the rank-`outer` trailing updates (one launch per outer
+        # panel); algorithmic flops = lower triangle incl. diagonal of the trailing block, 2*k each
+        outer = int(os.environ.get('OCBO_POTRF_OUTER', 2048))
+        ot = max(outer // 128, 1)
+        alg_outer = 0.0
+        for j1 in range(ot, nt, ot):
+            rows = (nt - j1) * 128.0
+            alg_outer += rows * (rows + 1.0) / 2.0 * 2.0 * (ot * 128.0)
+        alg_outer *= B
+        trailing_tflops = alg_outer / (ms3[3] * 1e-3) / 1e12 if ms3[3] > 0 else all_updates_tflops
         peaks = {} if args.no_peaks else measure_fp64_peaks(torch, lib_call, dev)
         peak = peaks.get('cublas_dgemm_tflops')
         step_tflops = sweep.step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
             / (ms_resident * 1e-3) / 1e12
         roof = {
-            'bound': 'tensor', 'kernel': 'gemm_nt_kernel (Cholesky rank-k updates of chol(Sigma), DMMA.8x8x4 fp64)',
+            'bound': 'tensor',
+            'kernel': 'gemm_nt_kernel<128,64> in its rank-%d trailing updates of chol(Sigma) '
+                      '(DMMA.8x8x4 fp64; %.0f%% of the factorisation update flops)' % (
+                          ot * 128, 100.0 * alg_outer / max(alg, 1.0)),
             'achieved': trailing_tflops, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': (trailing_tflops / peak) if (peak and trailing_tflops) else None,
             'traffic': load_traffic(B),
@@ -394,6 +407,7 @@ def run_b200(args):
                          'inner': os.environ.get('OCBO_POTRF_INNER', 'left'),
                          'note': 'serialised launches of ONE group (batch trials) on an otherwise idle '
                                  'GPU; in the timed region 16 trials overlap'},
+            'all_update_launches_tflops': all_updates_tflops,
             'step_tflops_per_gpu': step_tflops / world,
             'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,
