@@ -87,6 +87,27 @@ int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* n
 int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
                double* invdiag, int32_t* info, int batch, ocbo_stream_t stream);
 
+/* ocbo_potrf for identity-padded problems: nv[b] (device, may be NULL) is the valid
+ * size of problem b; elimination steps that would only touch the identity padding
+ * are skipped (bit-identical result, shorter serial chain for small n). */
+int ocbo_potrf_nv(double* A, int n, int lda, int64_t s_a, const int32_t* nv,
+                  double* invdiag, int32_t* info, int batch, ocbo_stream_t stream);
+
+/* Device-side walk of stable_cholesky's jitter ladder (Dragonfly
+ * draw_gaussian_samples / build_posterior) for a whole batch without a host round
+ * trip per rung.  While a ladder is walked info[b] means: 0 attempt pending or
+ * succeeded, k>0 last attempt failed at column k, -1 parked (succeeded earlier).
+ * One rung p = ocbo_ladder_restore(factor = 10^p) ; ocbo_ladder_advance(p, finish=0) ;
+ * ocbo_potrf[_nv].  After the last rung ocbo_ladder_advance(finish=1) maps -1 -> 0.
+ *   restore: for problems with info[b] > 0, A[b] <- A0[b] + factor * max_i<nv A0[b][i][i]
+ *            on the valid diagonal (tiles on/below the diagonal of 128-blocks);
+ *   advance: info > 0 -> rung[b] = p, info[b] = 0;  info == 0 -> info[b] = -1. */
+int ocbo_ladder_restore(double* A, const double* A0, int n, int lda, int64_t s_a,
+                        int lda0, int64_t s_a0, const int32_t* nv, const int32_t* info,
+                        double factor, int batch, ocbo_stream_t stream);
+int ocbo_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int batch,
+                        ocbo_stream_t stream);
+
 /* ocbo_potrf with CUDA events around every launch, summed per kernel class into
  * ms_host[4] = { diagonal-block, panel-solve, in-panel rank-128 update,
  * outer rank-k trailing update } milliseconds.

@@ -19,20 +19,31 @@ from .engine import DevicePosterior, F64
 
 def _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post=False):
     """Common tail: posterior at pts -> L_Sigma (ladder) -> mu + L z -> segment
-    max/argmax.  Returns (seg_max [B, nseg], seg_arg [B, nseg], mean dev, F dev, mv)."""
+    max/argmax, enqueued without a host round trip; the first read-back is the step's one
+    synchronisation.  Returns (seg_max [B, nseg], seg_arg [B, nseg], mean dev, F dev, mv, jit)."""
     Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
+    Z = engine.pad_normals(Z_list, mv, m_pad, 1)
+    seg = np.asarray(seg_lists, dtype=np.int32)
     mean = post.mean(Xd, mv_dev)
     V = post.solve_cross(Xd, mv_dev)
     Sigma = post.cov(Xd, mv_dev, V, True)
+    pend = engine.PendingCholesky(Sigma, mv_dev)
 
-    def reassemble(b0, b1):
-        post.cov(Xd, mv_dev, V, True, out=Sigma, b0=b0, b1=b1)
+    def tail():
+        Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
+        return (Fm,) + engine.segment_argmax(Fm, 1, seg)
 
-    _, info, jit = engine.factor_covariance(post, Sigma, mv_dev, mv, reassemble)
-    Z = engine.pad_normals(Z_list, mv, m_pad, 1)
-    Fm = engine.sample_from_factor(mean, Sigma, Z, info)
-    seg = np.asarray(seg_lists, dtype=np.int32)
-    mx, ag = engine.segment_argmax(Fm, 1, seg)
+    Fm, mx, ag = tail()
+    status = pend.status()
+    if getattr(post, 'unchecked', False) and post.info.cpu().numpy().any():
+        # a prior Gram matrix needed the ladder (rare): rebuild with the host-walked ladder, redo
+        post.build()
+        return _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post)
+    if (status[0] > 0).any():
+        jit = pend.resolve(status)
+        Fm, mx, ag = tail()
+    else:
+        jit = pend.resolve(status)
     return mx[:, :, 0].cpu().numpy(), ag[:, :, 0].cpu().numpy(), mean, Fm, mv, jit
 
 
@@ -50,7 +61,7 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
         post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
-                               np.asarray([c.theta() for c in cores]), kind, D).build()
+                               np.asarray([c.theta() for c in cores]), kind, D).build(check=False)
         pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
         segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
         mx, ag, _, _, _, jit = _sample_reduce(post, pts, [Z_list[f] for f in members], segs)

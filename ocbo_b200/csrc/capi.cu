@@ -112,7 +112,7 @@ static int potrf_outer_tiles(int nt) {
 }
 
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
-                     int batch, cudaStream_t st, PotrfTimer* tm) {
+                     int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr) {
   const int nt = n / TILE;
   const int64_t sInv = ocbo_invdiag_elems(n);
   const int NBO = potrf_outer_tiles(nt);
@@ -137,7 +137,8 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         CK(launch_gemm_nt(u, (nt - j) * u.ntc, batch, st), "potrf panel update");
         if (tm) tm->mark(st, 2);
       }
-      CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st), "potrf_diag");
+      CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st, nv),
+         "potrf_diag");
       if (tm) tm->mark(st, 0);
       const int r = nt - 1 - j;
       if (r == 0) break;
@@ -189,6 +190,44 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t*
   if (!info) return fail_arg(6, "info null");
   if (batch <= 0) return fail_arg(7, "batch");
   return potrf_run(A, n, lda, s_a, invdiag, info, batch, (cudaStream_t)stream, nullptr);
+}
+
+int ocbo_potrf_nv(double* A, int n, int lda, int64_t s_a, const int32_t* nv, double* invdiag,
+                  int32_t* info, int batch, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (lda < n || (lda & 1)) return fail_arg(3, "lda must be even and >= n");
+  if (!invdiag) return fail_arg(6, "invdiag null");
+  if (!info) return fail_arg(7, "info null");
+  if (batch <= 0) return fail_arg(8, "batch");
+  return potrf_run(A, n, lda, s_a, invdiag, info, batch, (cudaStream_t)stream, nullptr, nv);
+}
+
+int ocbo_ladder_restore(double* A, const double* A0, int n, int lda, int64_t s_a, int lda0,
+                        int64_t s_a0, const int32_t* nv, const int32_t* info, double factor,
+                        int batch, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (!A0) return fail_arg(2, "A0 null");
+  if (!tile_ok(n)) return fail_arg(3, "n must be a positive multiple of 128");
+  if (lda < n) return fail_arg(4, "lda");
+  if (lda0 < n) return fail_arg(6, "lda0");
+  if (!info) return fail_arg(9, "info null");
+  if (!(factor >= 0.0)) return fail_arg(10, "factor must be >= 0");
+  if (batch <= 0) return fail_arg(11, "batch");
+  CK(launch_ladder_restore(A, A0, n, lda, s_a, lda0, s_a0, nv, info, factor, batch,
+                           (cudaStream_t)stream),
+     "ocbo_ladder_restore");
+  return 0;
+}
+
+int ocbo_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int batch,
+                        ocbo_stream_t stream) {
+  if (!info) return fail_arg(1, "info null");
+  if (!finish && !rung) return fail_arg(2, "rung null");
+  if (batch <= 0) return fail_arg(5, "batch");
+  CK(launch_ladder_advance(info, rung, p, finish, batch, (cudaStream_t)stream),
+     "ocbo_ladder_advance");
+  return 0;
 }
 
 // Same factorisation, instrumented: CUDA events after every launch on `stream`,

@@ -57,8 +57,10 @@ cudaError_t launch_diag_max(const double* A, int n, int lda, int64_t sA, const i
 cudaError_t launch_symmetrize(double* A, int n, int lda, int64_t sA, int batch, cudaStream_t st);
 
 // factor the 128x128 diagonal block at (j0, j0) of every problem, write inv(L_jj)
+// (nv: optional per-problem valid size -- elimination steps on identity padding are skipped)
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
-                              int64_t sInv, int32_t* info, int batch, cudaStream_t st);
+                              int64_t sInv, int32_t* info, int batch, cudaStream_t st,
+                              const int32_t* nv = nullptr);
 cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, const int32_t* nv,
                                const double* mean, int64_t sMean, const double* theta,
                                int64_t sTheta, const double* best, int m, const int32_t* mv,
@@ -66,7 +68,14 @@ cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, cons
                                cudaStream_t st, const double* w = nullptr, int64_t sW = 0,
                                double* mean_out = nullptr, int64_t sMeanOut = 0);
 cudaError_t launch_potrf_diag_reg(double* A, int lda, int64_t sA, int j0, double* invdiag,
-                                  int64_t sInv, int32_t* info, int batch, cudaStream_t st);
+                                  int64_t sInv, int32_t* info, int batch, cudaStream_t st,
+                                  const int32_t* nv = nullptr);
+// jitter ladder on the device (ladder.cu)
+cudaError_t launch_ladder_restore(double* A, const double* A0, int n, int lda, int64_t sA, int lda0,
+                                  int64_t sA0, const int32_t* nv, const int32_t* info,
+                                  double factor, int batch, cudaStream_t st);
+cudaError_t launch_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int batch,
+                                  cudaStream_t st);
 cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,
                                    const double* invdiag, int64_t sInv, const double* y, int64_t sY,
                                    const int32_t* nv, const double* theta, int64_t sTheta,

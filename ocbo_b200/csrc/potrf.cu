@@ -161,7 +161,8 @@ potrf_diag_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, int64
 }
 
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
-                              int64_t sInv, int32_t* info, int batch, cudaStream_t st) {
+                              int64_t sInv, int32_t* info, int batch, cudaStream_t st,
+                              const int32_t* nv) {
   // default: register-resident kernel (potrf_diag_reg.cu); OCBO_DIAG_KERNEL=smem keeps
   // the shared-memory version selectable for A/B measurements
   static int use_smem = -1;
@@ -169,7 +170,7 @@ cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* in
     const char* e = getenv("OCBO_DIAG_KERNEL");
     use_smem = (e && e[0] == 's') ? 1 : 0;
   }
-  if (!use_smem) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st);
+  if (!use_smem) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
   constexpr int SMEM = (NB * LDS_ + 2 * NB + MB * LDS_) * 8;
   static bool init = false;
   if (!init) {

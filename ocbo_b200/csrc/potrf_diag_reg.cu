@@ -104,7 +104,7 @@ __device__ __forceinline__ int diag_steps(double (&a)[NBLK][NBLK], double (&w)[N
 
 __global__ void __launch_bounds__(G * G, 1)
 potrf_diag_reg_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, int64_t sInv,
-                      int32_t* info) {
+                      int32_t* info, const int32_t* nv) {
   __shared__ DiagSmem sm;
   const int b = blockIdx.x;
   if (info[b] != 0) return;
@@ -129,14 +129,24 @@ potrf_diag_reg_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, i
   }
   if (ty == 0) sm.rowX[0][tx] = w[0][0];
 
-  int fail = diag_steps<0>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<1>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<2>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<3>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<4>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<5>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<6>(a, w, sm, tx, ty);
-  if (!fail) fail = diag_steps<7>(a, w, sm, tx, ty);
+  // Rows/columns >= nv[b] of the matrix are padding (identity, see the header): their
+  // elimination steps are no-ops (pivot 1, l = 0), so only the 16-column stages that
+  // hold valid columns are run.  Bit-identical to running all eight.
+  int stages = NBLK;
+  if (nv) {
+    int nvl = nv[b] - j0;
+    nvl = nvl < 0 ? 0 : (nvl > NBR ? NBR : nvl);
+    stages = (nvl + G - 1) / G;
+  }
+  int fail = 0;
+  if (stages > 0) fail = diag_steps<0>(a, w, sm, tx, ty);
+  if (!fail && stages > 1) fail = diag_steps<1>(a, w, sm, tx, ty);
+  if (!fail && stages > 2) fail = diag_steps<2>(a, w, sm, tx, ty);
+  if (!fail && stages > 3) fail = diag_steps<3>(a, w, sm, tx, ty);
+  if (!fail && stages > 4) fail = diag_steps<4>(a, w, sm, tx, ty);
+  if (!fail && stages > 5) fail = diag_steps<5>(a, w, sm, tx, ty);
+  if (!fail && stages > 6) fail = diag_steps<6>(a, w, sm, tx, ty);
+  if (!fail && stages > 7) fail = diag_steps<7>(a, w, sm, tx, ty);
   if (fail) {
     if (tid == 0) info[b] = j0 + fail;
     return;
@@ -162,8 +172,9 @@ potrf_diag_reg_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, i
 }  // namespace
 
 cudaError_t launch_potrf_diag_reg(double* A, int lda, int64_t sA, int j0, double* invdiag,
-                                  int64_t sInv, int32_t* info, int batch, cudaStream_t st) {
-  potrf_diag_reg_kernel<<<batch, G * G, 0, st>>>(A, lda, sA, j0, invdiag, sInv, info);
+                                  int64_t sInv, int32_t* info, int batch, cudaStream_t st,
+                                  const int32_t* nv) {
+  potrf_diag_reg_kernel<<<batch, G * G, 0, st>>>(A, lda, sA, j0, invdiag, sInv, info, nv);
   return counted(cudaGetLastError());
 }
 

@@ -61,7 +61,17 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # older torch: the slow public path
+    _raw_stream = None
+
+
 def _stream():
+    """cudaStream_t of torch's current stream (the raw getter costs ~0.3 us; the public
+    ``current_stream()`` object ~13 us, which is a visible share of a small MTS step)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -96,9 +106,12 @@ def gram(kind, X1, nv1, X2, nv2, theta, out, flags):
     _count(1)
 
 
-def potrf(A, invd, info):
+def potrf(A, invd, info, nv=None):
+    """Batched in-place Cholesky; ``nv`` (device int32 [B]) marks identity padding whose
+    elimination steps the diagonal-block kernel may skip."""
     B, n, _ = A.shape
-    call('ocbo_potrf', _p(A), n, A.stride(1), A.stride(0), _p(invd), _p(info), B, _stream())
+    call('ocbo_potrf_nv', _p(A), n, A.stride(1), A.stride(0), _p(nv), _p(invd), _p(info), B,
+         _stream())
     _count(3 * (n // TILE) - 2)
 
 
@@ -117,7 +130,7 @@ def chol_with_ladder(assemble, A, invd, info, nv_dev, nv_host):
     used per problem (None = none needed)."""
     B = A.shape[0]
     info.zero_()
-    potrf(A, invd, info)
+    potrf(A, invd, info, nv_dev)
     status = info.cpu().numpy()
     jit = [None] * B
     if not status.any():
@@ -137,7 +150,7 @@ def chol_with_ladder(assemble, A, invd, info, nv_dev, nv_host):
             call('ocbo_add_diag', _p(Ab), n, Ab.stride(1), Ab.stride(0), _p(nvb), _p(val), 1, _stream())
             _count(2)
             inf_b.zero_()
-            potrf(Ab, ib, inf_b)
+            potrf(Ab, ib, inf_b, nvb)
             if int(inf_b.item()) == 0:
                 jit[b] = p
                 done = True
@@ -187,10 +200,19 @@ class DevicePosterior(object):
              self.theta[b0:b1], self.L[b0:b1],
              _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE)
 
-    def build(self):
+    def build(self, check=True):
+        """K + noise I -> L (stable_cholesky) -> alpha, LML.  ``check=False`` enqueues the plain
+        factorisation only and leaves ``unchecked`` set: the caller reads ``info`` together with
+        its results and calls ``build()`` again (host-walked ladder) if any problem failed --
+        with noise on the diagonal that is the rare case."""
         self._assemble_K(0, self.B)
-        self.jitter = chol_with_ladder(self._assemble_K, self.L, self.invd, self.info, self.nv,
-                                       self.nv_host)
+        self.unchecked = not check
+        if check:
+            self.jitter = chol_with_ladder(self._assemble_K, self.L, self.invd, self.info, self.nv,
+                                           self.nv_host)
+        else:
+            self.info.zero_()
+            potrf(self.L, self.invd, self.info, self.nv)
         call('ocbo_solve_alpha_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
              _p(self.invd), _p(self.y), self.y.stride(0), _p(self.nv), _p(self.theta),
              self.theta.stride(0), _p(self.alpha), self.alpha.stride(0), _p(self.lml), _p(self.info),
@@ -249,13 +271,72 @@ class DevicePosterior(object):
         return out
 
 
-def factor_covariance(post_or_none, Sigma, mv_dev, mv_host, reassemble):
-    """stable_cholesky of a batch of (padded) covariance matrices, in place."""
-    B, m_pad, _ = Sigma.shape
-    invd = torch.empty((B, m_pad // TILE, TILE, TILE), dtype=F64, device=Sigma.device)
-    info = torch.zeros((B,), dtype=I32, device=Sigma.device)
-    jit = chol_with_ladder(reassemble, Sigma, invd, info, mv_dev, mv_host)
-    return invd, info, jit
+NO_RUNG = -100          # rung[b] while no jitter has been needed
+LADDER = range(-11, 5)  # stable_cholesky's exponents
+
+
+def ladder_rungs(A, A0, invd, info, rung, nv, exponents):
+    """Enqueue ladder rungs for a whole batch (include/ocbo_b200.h, ocbo_ladder_*): problems
+    whose last attempt failed are restored from ``A0`` with jitter 10^p max(diag) and
+    refactored; the others are parked.  No synchronisation."""
+    B, n, _ = A.shape
+    st = _stream()
+    for p in exponents:
+        call('ocbo_ladder_restore', _p(A), _p(A0), n, A.stride(1), A.stride(0), A0.stride(1),
+             A0.stride(0), _p(nv), _p(info), float(10.0 ** p), B, st)
+        call('ocbo_ladder_advance', _p(info), _p(rung), int(p), 0, B, st)
+        _count(2)
+        potrf(A, invd, info, nv)
+    call('ocbo_ladder_advance', _p(info), _p(rung), 0, 1, B, st)
+    _count(1)
+
+
+class PendingCholesky(object):
+    """A batched stable_cholesky in flight: the plain attempt and the first ``spec`` rungs
+    are enqueued without a host round trip (small problems hit the ladder routinely:
+    MTS samples at the queried points, so Sigma is numerically singular); ``status`` is the
+    one synchronisation, ``resolve`` walks the remaining rungs for whatever still fails."""
+
+    def __init__(self, A, nv_dev, spec=None):
+        B, m_pad, _ = A.shape
+        nt = m_pad // TILE
+        self.A, self.nv = A, nv_dev
+        self.invd = torch.empty((B, nt, TILE, TILE), dtype=F64, device=A.device)
+        self.info = torch.zeros((B,), dtype=I32, device=A.device)
+        self.rung = torch.full((B,), NO_RUNG, dtype=I32, device=A.device)
+        self.A0 = A.clone()
+        _count(3)
+        if spec is None:
+            # a parked rung still costs its (empty) launches: speculate only when a rung is cheap
+            spec = 2 if nt <= 4 else 0
+        potrf(A, self.invd, self.info, nv_dev)
+        self.next = LADDER[0] + spec
+        if spec:
+            ladder_rungs(A, self.A0, self.invd, self.info, self.rung, nv_dev, LADDER[:spec])
+
+    def status(self):
+        return self.info.cpu().numpy(), self.rung.cpu().numpy()
+
+    def resolve(self, status=None):
+        """Finish the ladder (one synchronisation per further rung).  Returns the jitter
+        exponent per problem (None = none needed); ValueError like stable_cholesky."""
+        info_h, rung_h = status if status is not None else self.status()
+        while (info_h > 0).any():
+            if self.next > LADDER[-1]:
+                raise ValueError('stable_cholesky: matrix could not be made PD.')
+            ladder_rungs(self.A, self.A0, self.invd, self.info, self.rung, self.nv, [self.next])
+            self.next += 1
+            info_h, rung_h = self.status()
+        return [None if r == NO_RUNG else int(r) for r in rung_h]
+
+
+def factor_covariance(post_or_none, Sigma, mv_dev, mv_host=None, reassemble=None):
+    """stable_cholesky of a batch of (padded) covariance matrices, in place (synchronous
+    form of PendingCholesky; ``reassemble`` is not needed any more: retries restore from a
+    device copy)."""
+    pend = PendingCholesky(Sigma, mv_dev)
+    jit = pend.resolve()
+    return pend.invd, pend.info, jit
 
 
 def sample_from_factor(mean, Lsig, Z, info=None):

@@ -166,18 +166,21 @@ class B200GPCore(object):
         row offsets of the T old-point segments followed by the T grid segments.
         Returns (task, action index, gain)."""
         Xd, mv_dev, mv, mean, V, Sigma = self._posterior_at(to_samp, True, True)
-        post = self._post
-
-        def reassemble(b0, b1):
-            post.cov(Xd, mv_dev, V, True, out=Sigma, b0=b0, b1=b1)
-
         m, m_pad = mv[0], Sigma.shape[1]
-        _, info, jit = engine.factor_covariance(None, Sigma, mv_dev, mv, reassemble)
-        self.last_sample_jitter = jit[0]
         Z = engine.pad_normals([rng.normals((m, 1))], mv, m_pad, 1)
-        Fm = engine.sample_from_factor(mean, Sigma, Z, info)
-        mx, ag = engine.segment_argmax(Fm, 1, np.asarray(seg_ptr, dtype=np.int32)[None, :])
-        task, act, gain = engine.joint_pick(mx, ag, num_tasks, num_tasks)
+        seg = np.asarray(seg_ptr, dtype=np.int32)[None, :]
+        pend = engine.PendingCholesky(Sigma, mv_dev)
+
+        def tail():
+            Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
+            mx, ag = engine.segment_argmax(Fm, 1, seg)
+            return engine.joint_pick(mx, ag, num_tasks, num_tasks)
+
+        task, act, gain = tail()
+        status = pend.status()
+        self.last_sample_jitter = pend.resolve(status)[0]
+        if status[0][0] > 0:
+            task, act, gain = tail()
         return int(task[0, 0].item()), int(act[0, 0].item()), float(gain[0, 0].item())
 
     def compute_log_marginal_likelihood(self):

@@ -193,6 +193,84 @@ def test_jitter_ladder_on_singular_covariance(mods):
         mods['rng'].NORMAL_SOURCE = None
 
 
+def test_device_ladder_walks_each_problem_to_its_own_rung(mods):
+    """ocbo_ladder_* on a ragged batch: a PD problem (no jitter, parked through every rung), an
+    exactly singular one (needs a small rung), one that needs a LARGE rung (beyond the
+    speculative ones: host-continued) and an identity-padded small one.  Rung and factor must
+    equal numpy's stable_cholesky of the same matrices; an indefinite matrix raises
+    ValueError like the reference."""
+    torch, engine, o = mods['torch'], mods['engine'], mods['o']
+    rs = np.random.RandomState(7)
+    m_pad = 256
+
+    def psd(m, rank):
+        G = rs.normal(size=(m, rank))
+        return G.dot(G.T) / rank
+
+    mats = [psd(200, 400) + 1e-3 * np.eye(200),   # PD
+            psd(256, 100),                        # singular: ladder
+            psd(150, 50) - 1e-6 * np.eye(150),    # slightly indefinite: needs a large rung
+            psd(40, 10)]                          # small + singular, padded with identity
+    mv = [len(M) for M in mats]
+    ref = [o.stable_cholesky(M, return_jitter=True) for M in mats]
+    assert ref[0][1] is None and ref[1][1] is not None and ref[2][1] > -10
+    Sh = np.tile(np.eye(m_pad), (len(mats), 1, 1))
+    for b, M in enumerate(mats):
+        Sh[b, :mv[b], :mv[b]] = M
+    Sd = engine._h2d(Sh)
+    mv_dev = engine._h2d(np.asarray(mv, dtype=np.int32), engine.I32)
+    pend = engine.PendingCholesky(Sd, mv_dev)
+    jit = pend.resolve()
+    assert (pend.info.cpu().numpy() == 0).all()
+    Lh = Sd.cpu().numpy()
+    for b, (Lref, pref) in enumerate(ref):
+        if pref is None:
+            assert jit[b] is None
+        else:
+            # knife-edge ladder decisions may differ by one rung (documented)
+            assert jit[b] is not None and abs(jit[b] - pref) <= 1
+        if jit[b] == pref:
+            Lb = np.tril(Lh[b, :mv[b], :mv[b]])
+            scale = 1.0 if pref is None else 10.0 ** pref
+            A = mats[b] + (0 if pref is None else scale * np.max(np.diag(mats[b])) * np.eye(mv[b]))
+            assert rel_err(Lb.dot(Lb.T), A) <= 1e-12
+        # identity padding survives the ladder untouched
+        assert np.array_equal(np.tril(Lh[b, mv[b]:, mv[b]:]), np.eye(m_pad - mv[b]))
+    bad = np.tile(np.eye(128), (1, 1, 1))
+    bad[0, :4, :4] = -np.eye(4) * 1e6 + 1.0
+    bad[0, 0, 0] = 1.0   # max(diag) = 1 but a -1e6 pivot: no rung up to 1e4 fixes it
+    Bd = engine._h2d(bad)
+    with pytest.raises(ValueError):
+        engine.PendingCholesky(Bd, engine._h2d(np.asarray([4], dtype=np.int32), engine.I32)).resolve()
+
+
+def test_potrf_skips_identity_padding_bit_exactly(mods):
+    """ocbo_potrf_nv == ocbo_potrf on identity-padded problems, bit for bit (L and the
+    inverted diagonal blocks), for valid sizes on and off the 16-column stage boundaries."""
+    torch, engine = mods['torch'], mods['engine']
+    rs = np.random.RandomState(3)
+    mv = [1, 16, 50, 128, 129, 200, 255, 256]
+    m_pad = 256
+    Ah = np.tile(np.eye(m_pad), (len(mv), 1, 1))
+    for b, m in enumerate(mv):
+        G = rs.normal(size=(m, m + 5))
+        Ah[b, :m, :m] = G.dot(G.T) / m + 0.1 * np.eye(m)
+    outs = []
+    for use_nv in (False, True):
+        Ad = engine._h2d(Ah)
+        invd = torch.zeros((len(mv), m_pad // 128, 128, 128), dtype=torch.float64, device=Ad.device)
+        info = torch.zeros((len(mv),), dtype=torch.int32, device=Ad.device)
+        nv = engine._h2d(np.asarray(mv, dtype=np.int32), engine.I32) if use_nv else None
+        engine.potrf(Ad, invd, info, nv)
+        assert (info.cpu().numpy() == 0).all()
+        outs.append((np.tril(Ad.cpu().numpy()), invd.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    for b, m in enumerate(mv):
+        L = outs[1][0][b, :m, :m]
+        assert rel_err(L.dot(L.T), Ah[b, :m, :m]) <= 1e-13
+
+
 def test_dmma_sampling_path_many_draws(mods):
     """S = 256 draws go through the DMMA L*Z kernel; compare with numpy."""
     torch, engine = mods['torch'], mods['engine']
