@@ -135,6 +135,15 @@ int ocbo_solve_alpha_lml(const double* L, int n, int ldl, int64_t s_l,
                          double* alpha, int64_t s_alpha, double* lml,
                          const int32_t* info, int batch, ocbo_stream_t stream);
 
+/* Same solve with all three outputs optional: alpha, w = L^{-1}(y - mu0) and the LML
+ * (w feeds ocbo_post_mean_var_from_v: posterior mean without a second pass over the kernel). */
+int ocbo_solve_alpha_w_lml(const double* L, int n, int ldl, int64_t s_l,
+                           const double* invdiag,
+                           const double* y, int64_t s_y, const int32_t* nv,
+                           const double* theta, int64_t s_theta,
+                           double* alpha, int64_t s_alpha, double* w, int64_t s_w,
+                           double* lml, const int32_t* info, int batch, ocbo_stream_t stream);
+
 /* mean[b][i] = mu0 + sum_j k(xs_i, x_j) alpha_j, i < mv[b] (0 on padding).
  * Replaces the mean half of GP.eval (src/gp/gp_interface.py:69-74). */
 int ocbo_post_mean(int kind, int dim,

@@ -25,6 +25,8 @@ _PROTOS = {
     'ocbo_potrf_profile': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP, _VP]),
     'ocbo_trsm_lower': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _I, _L, _VP, _I, _VP]),
     'ocbo_solve_alpha_lml': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _VP, _L, _VP, _L, _VP, _VP, _I, _VP]),
+    'ocbo_solve_alpha_w_lml': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _VP, _L, _VP, _L, _VP, _L, _VP,
+                                    _VP, _I, _VP]),
     'ocbo_post_mean': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _L, _VP, _L, _VP, _L, _I, _VP]),
     'ocbo_post_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _I, _L, _VP, _L, _VP, _I, _L, _I, _I, _VP]),
     'ocbo_post_cross_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _I, _L,

@@ -24,8 +24,8 @@ def _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post=False):
     Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
     Z = engine.pad_normals(Z_list, mv, m_pad, 1)
     seg = np.asarray(seg_lists, dtype=np.int32)
-    mean = post.mean(Xd, mv_dev)
     V = post.solve_cross(Xd, mv_dev)
+    mean = post.mean_from_v(V, mv_dev)
     Sigma = post.cov(Xd, mv_dev, V, True)
     pend = engine.PendingCholesky(Sigma, mv_dev)
 
@@ -61,7 +61,7 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
         post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
-                               np.asarray([c.theta() for c in cores]), kind, D).build(check=False)
+                               np.asarray([c.theta() for c in cores]), kind, D).build(check=False, need_alpha=False)
         pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
         segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
         mx, ag, _, _, _, jit = _sample_reduce(post, pts, [Z_list[f] for f in members], segs)
@@ -81,7 +81,7 @@ class SharedPosterior(object):
         ex = lambda t: t.expand(B, *t.shape[1:])
         # operands addressed through an explicit batch stride are shared (stride 0) ...
         self.X, self.y, self.theta = ex(post.X), ex(post.y), ex(post.theta)
-        self.L, self.alpha = ex(post.L), ex(post.alpha)
+        self.L, self.alpha, self.w = ex(post.L), ex(post.alpha), ex(post.w)
         # ... the per-problem arrays the kernels index as a[b] must be real
         self.nv = post.nv.repeat(B)
         self.info = torch.zeros((B,), dtype=engine.I32, device=post.L.device)
@@ -90,6 +90,7 @@ class SharedPosterior(object):
 
     upload_points = DevicePosterior.upload_points
     mean = DevicePosterior.mean
+    mean_from_v = DevicePosterior.mean_from_v
     solve_cross = DevicePosterior.solve_cross
     cov = DevicePosterior.cov
 
@@ -120,8 +121,8 @@ def profile_step(gp, act_sets, Z_list):
 def _ei_reduce(post, pts_list, best):
     """best: device tensor [B] or a callable(mean_max[B] tensor) -> tensor [B]."""
     Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
-    mean = post.mean(Xd, mv_dev)
     V = post.solve_cross(Xd, mv_dev)
+    mean = post.mean_from_v(V, mv_dev)
     segs = np.asarray([[0, m] for m in mv], dtype=np.int32)
     if callable(best):
         mmx, _ = engine.segment_argmax(mean.unsqueeze(2), 1, segs)

@@ -116,11 +116,17 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
   const int nt = n / TILE;
   const int64_t sInv = ocbo_invdiag_elems(n);
   const int NBO = potrf_outer_tiles(nt);
-  static int left = -1;  // OCBO_POTRF_INNER=right selects right-looking in-panel updates
-  if (left < 0) {
+  static int left_env = -1;  // OCBO_POTRF_INNER=right|left forces the in-panel variant
+  if (left_env < 0) {
     const char* e = getenv("OCBO_POTRF_INNER");
-    left = (e && e[0] == 'r') ? 0 : 1;
+    left_env = !e ? 2 : (e[0] == 'r' ? 0 : 1);
   }
+  // Left-looking panels run each block column's update as ONE long-k launch of
+  // 2 (nt - j) batch CTAs: right for the sweep (the other streams fill the SMs), wrong for a
+  // small problem on an idle GPU, where those few CTAs serialise (jointbran, m = 1280, one
+  // problem: 19 launches x 27 us).  Small problems therefore take rank-128 right-looking
+  // updates, whose launches expose (nt - j)^2 batch tiles of short k.
+  const int left = left_env != 2 ? left_env : ((nt <= 16 && batch * nt * 2 < 296) ? 0 : 1);
   for (int J0 = 0; J0 < nt; J0 += NBO) {
     const int J1 = (J0 + NBO < nt) ? J0 + NBO : nt;
     for (int j = J0; j < J1; ++j) {
@@ -311,6 +317,24 @@ int ocbo_solve_alpha_lml(const double* L, int n, int ldl, int64_t s_l, const dou
   CK(launch_solve_alpha_lml(L, n, ldl, s_l, invdiag, ocbo_invdiag_elems(n), y, s_y, nv, theta,
                             s_theta, alpha, s_alpha, lml, info, batch, (cudaStream_t)stream),
      "ocbo_solve_alpha_lml");
+  return 0;
+}
+
+int ocbo_solve_alpha_w_lml(const double* L, int n, int ldl, int64_t s_l, const double* invdiag,
+                           const double* y, int64_t s_y, const int32_t* nv, const double* theta,
+                           int64_t s_theta, double* alpha, int64_t s_alpha, double* w, int64_t s_w,
+                           double* lml, const int32_t* info, int batch, ocbo_stream_t stream) {
+  if (!L) return fail_arg(1, "L null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (n > 24576) return fail_arg(2, "n too large for the single-CTA solve");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!y) return fail_arg(6, "y null");
+  if (!theta) return fail_arg(9, "theta null");
+  if (!alpha && !w && !lml) return fail_arg(11, "no output requested");
+  if (batch <= 0) return fail_arg(17, "batch");
+  CK(launch_solve_alpha_lml(L, n, ldl, s_l, invdiag, ocbo_invdiag_elems(n), y, s_y, nv, theta,
+                            s_theta, alpha, s_alpha, lml, info, batch, (cudaStream_t)stream, w, s_w),
+     "ocbo_solve_alpha_w_lml");
   return 0;
 }
 

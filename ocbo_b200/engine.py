@@ -189,6 +189,7 @@ class DevicePosterior(object):
         self.L = torch.empty((B, n_pad, n_pad), dtype=F64, device=dev)
         self.invd = torch.empty((B, n_pad // TILE, TILE, TILE), dtype=F64, device=dev)
         self.alpha = torch.empty((B, n_pad), dtype=F64, device=dev)
+        self.w = torch.empty((B, n_pad), dtype=F64, device=dev)
         self.lml = torch.empty((B,), dtype=F64, device=dev)
         self.info = torch.zeros((B,), dtype=I32, device=dev)
         self.jitter = [None] * B
@@ -200,7 +201,7 @@ class DevicePosterior(object):
              self.theta[b0:b1], self.L[b0:b1],
              _lib.GRAM_SYM | _lib.GRAM_LOWER | _lib.GRAM_ADD_NOISE)
 
-    def build(self, check=True):
+    def build(self, check=True, need_alpha=True):
         """K + noise I -> L (stable_cholesky) -> alpha, LML.  ``check=False`` enqueues the plain
         factorisation only and leaves ``unchecked`` set: the caller reads ``info`` together with
         its results and calls ``build()`` again (host-walked ladder) if any problem failed --
@@ -213,10 +214,12 @@ class DevicePosterior(object):
         else:
             self.info.zero_()
             potrf(self.L, self.invd, self.info, self.nv)
-        call('ocbo_solve_alpha_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
+        # alpha for the mean-only evaluations (K(Xs, X) alpha), w = L^{-1}(y - mu0) for the ones that
+        # have V = L^{-1} K(X, Xs) at hand anyway (mean = mu0 + V^T w: one pass over V, no kernel)
+        call('ocbo_solve_alpha_w_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
              _p(self.invd), _p(self.y), self.y.stride(0), _p(self.nv), _p(self.theta),
-             self.theta.stride(0), _p(self.alpha), self.alpha.stride(0), _p(self.lml), _p(self.info),
-             self.B, _stream())
+             self.theta.stride(0), _p(self.alpha) if need_alpha else None, self.alpha.stride(0),
+             _p(self.w), self.w.stride(0), _p(self.lml), _p(self.info), self.B, _stream())
         _count(1)
         self.built = True
         return self
@@ -237,6 +240,17 @@ class DevicePosterior(object):
         call('ocbo_post_mean', self.kind, self.D, _p(Xs), m_pad, Xs.stride(0), _p(mv_dev), _p(self.X),
              self.n_pad, self.X.stride(0), _p(self.nv), _p(self.theta), self.theta.stride(0),
              _p(self.alpha), self.alpha.stride(0), _p(out), out.stride(0), B, _stream())
+        _count(1)
+        return out
+
+    def mean_from_v(self, V, mv_dev):
+        """mean = mu0 + V^T w with V = L^{-1} K(X, Xs) from ``solve_cross`` (same value as
+        ``mean``; HBM-bound single pass over V instead of m n kernel evaluations)."""
+        B, _, m_pad = V.shape
+        out = torch.empty((B, m_pad), dtype=F64, device=V.device)
+        call('ocbo_post_mean_var_from_v', _p(V), self.n_pad, V.stride(1), V.stride(0), _p(self.nv),
+             _p(self.w), self.w.stride(0), _p(self.theta), self.theta.stride(0), m_pad, _p(mv_dev),
+             _p(out), out.stride(0), None, 0, B, _stream())
         _count(1)
         return out
 
