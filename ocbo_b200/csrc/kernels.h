@@ -70,6 +70,9 @@ cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, cons
 cudaError_t launch_potrf_diag_reg(double* A, int lda, int64_t sA, int j0, double* invdiag,
                                   int64_t sInv, int32_t* info, int batch, cudaStream_t st,
                                   const int32_t* nv = nullptr);
+cudaError_t launch_potrf_diag_blk(double* A, int lda, int64_t sA, int j0, double* invdiag,
+                                  int64_t sInv, int32_t* info, int batch, cudaStream_t st,
+                                  const int32_t* nv = nullptr);
 // jitter ladder on the device (ladder.cu)
 cudaError_t launch_ladder_restore(double* A, const double* A0, int n, int lda, int64_t sA, int lda0,
                                   int64_t sA0, const int32_t* nv, const int32_t* info,

@@ -163,14 +163,16 @@ potrf_diag_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, int64
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
                               int64_t sInv, int32_t* info, int batch, cudaStream_t st,
                               const int32_t* nv) {
-  // default: register-resident kernel (potrf_diag_reg.cu); OCBO_DIAG_KERNEL=smem keeps
-  // the shared-memory version selectable for A/B measurements
-  static int use_smem = -1;
-  if (use_smem < 0) {
+  // default: blocked register-resident kernel (potrf_diag_blk.cu); OCBO_DIAG_KERNEL=reg keeps
+  // the column-per-barrier register kernel and =smem the shared-memory version selectable
+  // for A/B measurements (blk and reg are bit-identical)
+  static int which = -1;
+  if (which < 0) {
     const char* e = getenv("OCBO_DIAG_KERNEL");
-    use_smem = (e && e[0] == 's') ? 1 : 0;
+    which = !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'r' ? 1 : 2));
   }
-  if (!use_smem) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
+  if (which == 2) return launch_potrf_diag_blk(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
+  if (which == 1) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
   constexpr int SMEM = (NB * LDS_ + 2 * NB + MB * LDS_) * 8;
   static bool init = false;
   if (!init) {
