@@ -17,13 +17,18 @@ from . import engine
 from .engine import DevicePosterior, F64
 
 
-def _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post=False):
-    """Common tail: posterior at pts -> L_Sigma (ladder) -> mu + L z -> segment
-    max/argmax, enqueued without a host round trip; the first read-back is the step's one
-    synchronisation.  Returns (seg_max [B, nseg], seg_arg [B, nseg], mean dev, F dev, mv, jit)."""
-    Xd, mv_dev, mv, m_pad = post.upload_points(pts_list)
+def _stage_candidates(B, D, pts_list, Z_list, seg_lists):
+    """Uploads of the sampling tail (call inside a staging block)."""
+    Xd, mv_dev, mv, m_pad = engine.upload_points(B, D, pts_list)
     Z = engine.pad_normals(Z_list, mv, m_pad, 1)
-    seg = np.asarray(seg_lists, dtype=np.int32)
+    seg = engine._h2d(np.asarray(seg_lists, dtype=np.int32), engine.I32)
+    return Xd, mv_dev, mv, m_pad, Z, seg
+
+
+def _enqueue_tail(post, staged):
+    """posterior at pts -> Sigma -> stable_cholesky (plain attempt + speculative rungs)
+    -> mu + L z -> segment max/argmax, all enqueued, no host round trip."""
+    Xd, mv_dev, mv, m_pad, Z, seg = staged
     V = post.solve_cross(Xd, mv_dev)
     mean = post.mean_from_v(V, mv_dev)
     Sigma = post.cov(Xd, mv_dev, V, True)
@@ -33,18 +38,35 @@ def _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post=False):
         Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
         return (Fm,) + engine.segment_argmax(Fm, 1, seg)
 
+    return mean, pend, tail
+
+
+def _sample_reduce(post, staged):
+    """Eager form: the first read-back is the step's one synchronisation; problems that
+    need more than the speculative rungs continue the ladder from the host.
+    Returns (seg_max [B, nseg], seg_arg [B, nseg], mean dev, F dev, mv, jit)."""
+    mean, pend, tail = _enqueue_tail(post, staged)
     Fm, mx, ag = tail()
     status = pend.status()
     if getattr(post, 'unchecked', False) and post.info.cpu().numpy().any():
         # a prior Gram matrix needed the ladder (rare): rebuild with the host-walked ladder, redo
         post.build()
-        return _sample_reduce(post, pts_list, Z_list, seg_lists, shared_post)
+        return _sample_reduce(post, staged)
+    jit = pend.resolve(status)
     if (status[0] > 0).any():
-        jit = pend.resolve(status)
         Fm, mx, ag = tail()
-    else:
-        jit = pend.resolve(status)
-    return mx[:, :, 0].cpu().numpy(), ag[:, :, 0].cpu().numpy(), mean, Fm, mv, jit
+    return mx[:, :, 0].cpu().numpy(), ag[:, :, 0].cpu().numpy(), mean, Fm, staged[2], jit
+
+
+def _rungs(rung_host):
+    return [None if r == engine.NO_RUNG else int(r) for r in rung_host]
+
+
+def _arena_bytes(B, n_pad, m_pad, D, nseg, with_posterior):
+    doubles = B * m_pad * (D + 1)
+    if with_posterior:
+        doubles += B * n_pad * (D + 1) + B * (3 + D)
+    return 8 * doubles + 4 * B * (nseg + 3) + 16 * engine.Staging.ALIGN
 
 
 def mts_step(gps, samp_pts_list, n_old_list, Z_list):
@@ -60,11 +82,44 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     out = [None] * T
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
-        post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
-                               np.asarray([c.theta() for c in cores]), kind, D).build(check=False, need_alpha=False)
+        Xs_ = [c.X_array() for c in cores]
+        ys_ = [c.Y for c in cores]
+        thetas = np.asarray([c.theta() for c in cores])
         pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
         segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
-        mx, ag, _, _, _, jit = _sample_reduce(post, pts, [Z_list[f] for f in members], segs)
+        Zs = [Z_list[f] for f in members]
+
+        def stage():
+            return (DevicePosterior.pack(Xs_, ys_, thetas, D),
+                    _stage_candidates(len(members), D, pts, Zs, segs))
+
+        mx = None
+        if engine.graphs_enabled():
+            B = len(members)
+            n_pad = engine.pad_to(max([len(y) for y in ys_] + [1]))
+            m_pad = engine.pad_to(max([len(q) for q in pts] + [1]))
+            plan = engine.StepPlan.get(('mts', kind, D, B, n_pad, m_pad),
+                                       _arena_bytes(B, n_pad, m_pad, D, 2, True))
+            with plan.staging():
+                st_now = stage()
+
+            def body(st, ext):
+                packed, staged_ = st
+                post_ = DevicePosterior.from_device(*packed, kind, D)
+                post_.build(check=False, need_alpha=False)
+                _, pend, tail = _enqueue_tail(post_, staged_)
+                _, mx_, ag_ = tail()
+                return [mx_, ag_, post_.info, pend.info, pend.rung]
+
+            mx_h, ag_h, info_k, info_s, rung = plan.run(st_now, [], body)
+            if not info_k.any() and not (info_s > 0).any():
+                mx, ag, jit = mx_h[:, :, 0], ag_h[:, :, 0], _rungs(rung)
+        if mx is None:  # graphs off, or a problem needs the host-continued ladder
+            with engine.staging():
+                packed, staged = stage()
+            post = DevicePosterior.from_device(*packed, kind, D)
+            post.build(check=False, need_alpha=False)
+            mx, ag, _, _, _, jit = _sample_reduce(post, staged)
         for k, f in enumerate(members):
             out[f] = (float(mx[k, 0]), int(ag[k, 1]), float(mx[k, 1]))
             gps[f].gp_core.last_sample_jitter = jit[k]
@@ -80,16 +135,38 @@ class SharedPosterior(object):
         self.B, self.D, self.kind, self.n_pad = B, post.D, post.kind, post.n_pad
         ex = lambda t: t.expand(B, *t.shape[1:])
         # operands addressed through an explicit batch stride are shared (stride 0) ...
-        self.X, self.y, self.theta = ex(post.X), ex(post.y), ex(post.theta)
-        self.L, self.alpha, self.w = ex(post.L), ex(post.alpha), ex(post.w)
+        self.X, self.theta, self.L, self.w = ex(post.X), ex(post.theta), ex(post.L), ex(post.w)
         # ... the per-problem arrays the kernels index as a[b] must be real
         self.nv = post.nv.repeat(B)
         self.info = torch.zeros((B,), dtype=engine.I32, device=post.L.device)
         self.invd = post.invd.repeat(B, 1, 1, 1)  # batch stride of invdiag is implicit in the ABI
-        self.nv_host = post.nv_host * B
+        self.nv_host = list(post.nv_host) * B
 
     upload_points = DevicePosterior.upload_points
-    mean = DevicePosterior.mean
+    mean_from_v = DevicePosterior.mean_from_v
+    solve_cross = DevicePosterior.solve_cross
+    cov = DevicePosterior.cov
+
+
+class _PostView(object):
+    """The operands of ONE built posterior that the sampling tail reads (optionally
+    re-pointed at a StepPlan's own copies); usable as a batch-1 posterior itself."""
+    FIELDS = ('X', 'theta', 'nv', 'L', 'invd', 'w')
+    B = 1
+
+    def __init__(self, post, tensors=None):
+        self.D, self.kind, self.n_pad, self.nv_host = post.D, post.kind, post.n_pad, post.nv_host
+        for name, t in zip(self.FIELDS, tensors or [getattr(post, f) for f in self.FIELDS]):
+            setattr(self, name, t)
+        self.info = post.info if tensors is None else None
+
+    def with_info(self):
+        self.info = torch.zeros((1,), dtype=engine.I32, device=self.L.device)
+        return self
+
+    def tensors(self):
+        return [getattr(self, f) for f in self.FIELDS]
+
     mean_from_v = DevicePosterior.mean_from_v
     solve_cross = DevicePosterior.solve_cross
     cov = DevicePosterior.cov
@@ -102,16 +179,43 @@ def profile_step(gp, act_sets, Z_list):
     core = gp.gp_core
     if core._post is None:
         core.build_posterior()
-    B = len(act_sets)
-    post = SharedPosterior(core._post, B)
+    base = core._post
+    B, D = len(act_sets), base.D
     segs = [[0, len(a)] for a in act_sets]
-    mx, ag, mean, Fm, mv, jit = _sample_reduce(post, act_sets, Z_list, segs)
-    mmx, mag = engine.segment_argmax(mean.unsqueeze(2), 1, np.asarray(segs, dtype=np.int32))
-    mmx, mag = mmx[:, 0, 0].cpu().numpy(), mag[:, 0, 0].cpu().numpy()
-    idx = torch.from_numpy(mag.astype(np.int64)).to(Fm.device)
-    s_at = Fm[:, :, 0].gather(1, idx[:, None])[:, 0].cpu().numpy()
-    core.last_sample_jitter = jit
-    return mx[:, 0], ag[:, 0], mmx, mag, s_at
+
+    def reduce_means(mean, Fm, seg):
+        mmx, mag = engine.segment_argmax(mean.unsqueeze(2), 1, seg)
+        s_at = Fm[:, :, 0].gather(1, mag[:, 0, :].long())[:, 0]
+        return mmx[:, 0, 0], mag[:, 0, 0], s_at
+
+    res = None
+    if engine.graphs_enabled():
+        m_pad = engine.pad_to(max([len(a) for a in act_sets] + [1]))
+        plan = engine.StepPlan.get(('cts', base.kind, D, B, base.n_pad, m_pad),
+                                   _arena_bytes(B, 0, m_pad, D, 1, False))
+        view = _PostView(base)
+        with plan.staging():
+            staged = _stage_candidates(B, D, act_sets, Z_list, segs)
+
+        def body(st, ext):
+            post = SharedPosterior(_PostView(base, ext), B)
+            mean, pend, tail = _enqueue_tail(post, st)
+            Fm, mx, ag = tail()
+            return [mx, ag] + list(reduce_means(mean, Fm, st[5])) + [pend.info, pend.rung]
+
+        mx, ag, mmx, mag, s_at, info_s, rung = plan.run(staged, view.tensors(), body)
+        if not (info_s > 0).any():
+            res = tuple(np.array(v) for v in (mx[:, 0, 0], ag[:, 0, 0], mmx, mag, s_at))
+            core.last_sample_jitter = _rungs(rung)
+    if res is None:
+        post = SharedPosterior(base, B)
+        with engine.staging():
+            staged = _stage_candidates(B, D, act_sets, Z_list, segs)
+        mx, ag, mean, Fm, mv, jit = _sample_reduce(post, staged)
+        mmx, mag, s_at = [t.cpu().numpy() for t in reduce_means(mean, Fm, staged[5])]
+        core.last_sample_jitter = jit
+        res = (mx[:, 0], ag[:, 0], mmx, mag, s_at)
+    return res
 
 
 # ---------------------------------------------------------------------------
@@ -146,7 +250,7 @@ def mei_step(gps, pts_list, best_list):
     out = [None] * T
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
-        post = DevicePosterior([np.asarray(c.X).reshape(-1, D) for c in cores], [c.Y for c in cores],
+        post = DevicePosterior([c.X_array() for c in cores], [c.Y for c in cores],
                                np.asarray([c.theta() for c in cores]), kind, D).build()
         best = engine._h2d(np.asarray([best_list[f] for f in members], dtype=np.float64))
         pts = [np.asarray(pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]

@@ -75,11 +75,173 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class Staging(object):
+    """One host->device copy for all the small operands of a step.
+
+    Inside ``with staging():`` every ``_h2d`` bump-allocates from a persistent pinned host
+    arena and returns a view of ONE device arena at the same offset; leaving the block
+    issues a single asynchronous copy of the used prefix.  The uploads of a small MTS step
+    (training sets, hyper-parameters, candidates, normals, segment offsets: 8 arrays) cost
+    ~35 us each as separate pageable copies -- more than the step's kernels.  Nothing may be
+    launched on the staged tensors before the block is left."""
+    ALIGN = 256
+    _host = None     # persistent pinned arena (grown on demand)
+    _done = None     # event: the last copy out of the arena has finished
+
+    def __init__(self, capacity=4 << 20):
+        self.capacity = int(capacity)
+        self.used = 0
+        self.dev = None
+
+    def __enter__(self):
+        require_cuda()
+        cls = Staging
+        if cls._host is None or cls._host.numel() < self.capacity:
+            cls._host = torch.empty(self.capacity, dtype=torch.uint8).pin_memory()
+        elif cls._done is not None:
+            cls._done.synchronize()  # the previous step's copy must have left the arena
+        self.capacity = cls._host.numel()
+        self.host = cls._host
+        self.dev = torch.empty(self.capacity, dtype=torch.uint8, device=device())
+        _ACTIVE.append(self)
+        return self
+
+    def take(self, t):
+        """Stage CPU tensor ``t``; returns its device view or None if it does not fit."""
+        nb = t.numel() * t.element_size()
+        off = self.used
+        if off + nb > self.capacity:
+            return None
+        self.used = off + ((nb + self.ALIGN - 1) // self.ALIGN) * self.ALIGN
+        self.host[off:off + nb].view(t.dtype).view(t.shape).copy_(t)
+        return self.dev[off:off + nb].view(t.dtype).view(t.shape)
+
+    def __exit__(self, *exc):
+        _ACTIVE.pop()
+        if self.used and exc[0] is None:
+            self.dev[:self.used].copy_(Staging._host[:self.used], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            Staging._done = ev
+        return False
+
+
+_ACTIVE = []
+
+
+def staging(capacity=4 << 20):
+    return Staging(capacity)
+
+
+class _PlanStaging(Staging):
+    """Staging into the persistent arenas of a StepPlan: no copy on exit (the copy is the
+    first node of the plan's graph) and a deterministic layout (same calls, same offsets)."""
+
+    def __init__(self, plan):
+        self.plan, self.capacity, self.used = plan, plan.capacity, 0
+        self.host, self.dev = plan.host, plan.dev
+
+    def __enter__(self):
+        _ACTIVE.append(self)
+        return self
+
+    def take(self, t):
+        d = Staging.take(self, t)
+        if d is None:
+            raise RuntimeError('StepPlan arena too small (%d bytes)' % self.capacity)
+        return d
+
+    def __exit__(self, *exc):
+        _ACTIVE.pop()
+        self.plan.used = self.used
+        return False
+
+
+def graphs_enabled():
+    import os
+    return os.environ.get('OCBO_GRAPHS', '1') != '0'
+
+
+class StepPlan(object):
+    """One decision step at fixed padded shapes as a CUDA graph.
+
+    A small MTS step is ~30 kernels of 5-40 us: launched one by one from Python its wall
+    time is the host's (0.9 ms for set2d against 0.38 ms of kernels).  The padded shapes
+    (batch, n_pad, m_pad) -- the only launch parameters -- stay fixed for ~100 BO steps, and
+    everything that changes (data, valid sizes, normals, segment offsets) lives in device
+    memory, so the whole step is captured once per shape key and replayed:
+        fill pinned arena -> [graph: H2D arena, kernels incl. the speculative ladder rungs,
+        D2H results] -> one stream synchronise.
+    ``ext`` tensors (a posterior built elsewhere) are copied into plan-owned buffers before
+    the replay.  Results are numpy views of pinned memory, valid until the next run."""
+    MAX_PLANS = 24
+    _plans = {}
+    _order = []
+
+    @classmethod
+    def get(cls, key, capacity):
+        plan = cls._plans.get(key)
+        if plan is None:
+            if len(cls._order) >= cls.MAX_PLANS:
+                cls._plans.pop(cls._order.pop(0), None)
+            plan = cls._plans[key] = StepPlan(capacity)
+            cls._order.append(key)
+        return plan
+
+    @classmethod
+    def clear(cls):
+        cls._plans.clear()
+        del cls._order[:]
+
+    def __init__(self, capacity):
+        require_cuda()
+        self.capacity = ((int(capacity) + 4095) // 4096) * 4096
+        self.host = torch.empty(self.capacity, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(self.capacity, dtype=torch.uint8, device=device())
+        self.used = 0
+        self.graph = None
+        self.replays = 0
+
+    def staging(self):
+        return _PlanStaging(self)
+
+    def run(self, staged, ext, body):
+        """body(staged, ext) -> list of device tensors; returns them as numpy arrays."""
+        stream = torch.cuda.current_stream()
+        if self.graph is None:
+            self.staged, self.used0 = staged, self.used
+            self.ext = [t.clone() for t in ext]
+            self.dev[:self.used].copy_(self.host[:self.used], non_blocking=True)
+            outs = body(self.staged, self.ext)  # eager warm-up: lazy kernel attributes, shapes
+            torch.cuda.synchronize()
+            self.outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.dev[:self.used].copy_(self.host[:self.used], non_blocking=True)
+                outs = body(self.staged, self.ext)
+                for h, o in zip(self.outs_host, outs):
+                    h.copy_(o, non_blocking=True)
+            self.graph = g
+        else:
+            if self.used != self.used0:
+                raise RuntimeError('StepPlan: staged layout changed under a fixed shape key')
+            for own, t in zip(self.ext, ext):
+                own.copy_(t, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        stream.synchronize()
+        return [h.numpy() for h in self.outs_host]
+
+
 def _h2d(arr, dtype=F64):
-    """Host ndarray -> device tensor through a pinned staging buffer."""
+    """Host ndarray -> device tensor (through the active ``staging()`` arena if there is one)."""
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if t.dtype != dtype:
         t = t.to(dtype)
+    if _ACTIVE:
+        d = _ACTIVE[-1].take(t)
+        if d is not None:
+            return d
     if t.numel() * t.element_size() < (1 << 20):
         # small operands (the option-file shapes): a pageable copy costs ~10 us, pinning
         # a fresh buffer costs a cudaHostAlloc (~100 us) per call
@@ -160,32 +322,56 @@ def chol_with_ladder(assemble, A, invd, info, nv_dev, nv_host):
     return jit
 
 
+def upload_points(B, D, pts_list):
+    """Candidate sets -> (Xs [B, m_pad, D], mv device, mv host, m_pad)."""
+    mv = [len(p) for p in pts_list]
+    m_pad = pad_to(max(mv + [1]))
+    Ph = np.zeros((B, m_pad, D))
+    for b, p in enumerate(pts_list):
+        if mv[b]:
+            Ph[b, :mv[b]] = np.asarray(p, dtype=np.float64).reshape(mv[b], D)
+    return _h2d(Ph), _h2d(np.asarray(mv, dtype=np.int32), I32), mv, m_pad
+
+
 class DevicePosterior(object):
     """B independent GP posteriors, padded to a common n_pad, resident in HBM."""
 
     def __init__(self, X_list, y_list, thetas, kind, dim):
         require_cuda()
-        self.B = len(X_list)
-        self.D = int(dim)
-        self.kind = int(kind)
-        if self.D < 1 or self.D > _lib.MAX_DIM:
+        X, y, theta, nv, nv_host = self.pack(X_list, y_list, thetas, dim)
+        self._attach(X, y, theta, nv, nv_host, kind, dim)
+
+    @staticmethod
+    def pack(X_list, y_list, thetas, dim):
+        """Pad and upload (through the active staging arena) -> X, y, theta, nv, nv_host."""
+        B, D = len(X_list), int(dim)
+        if D < 1 or D > _lib.MAX_DIM:
             raise ValueError('input dimension must be in [1, %d]' % _lib.MAX_DIM)
-        self.nv_host = [len(y) for y in y_list]
-        self.n_pad = pad_to(max(self.nv_host + [1]))
-        B, n_pad, D = self.B, self.n_pad, self.D
+        nv_host = [len(y) for y in y_list]
+        n_pad = pad_to(max(nv_host + [1]))
         Xh = np.zeros((B, n_pad, D))
         yh = np.zeros((B, n_pad))
         for b in range(B):
-            nb = self.nv_host[b]
+            nb = nv_host[b]
             if nb:
                 Xh[b, :nb] = np.asarray(X_list[b], dtype=np.float64).reshape(nb, D)
                 yh[b, :nb] = np.asarray(y_list[b], dtype=np.float64).ravel()
-        self.X = _h2d(Xh)
-        self.y = _h2d(yh)
-        self.theta_host = np.asarray(thetas, dtype=np.float64).reshape(B, 3 + D)
-        self.theta = _h2d(self.theta_host)
-        self.nv = _h2d(np.asarray(self.nv_host, dtype=np.int32), I32)
-        dev = self.X.device
+        theta_host = np.asarray(thetas, dtype=np.float64).reshape(B, 3 + D)
+        return (_h2d(Xh), _h2d(yh), _h2d(theta_host), _h2d(np.asarray(nv_host, dtype=np.int32), I32),
+                nv_host)
+
+    @classmethod
+    def from_device(cls, X, y, theta, nv, nv_host, kind, dim):
+        """Posterior over operands that already live on the device (a StepPlan's arena)."""
+        self = cls.__new__(cls)
+        self._attach(X, y, theta, nv, nv_host, kind, dim)
+        return self
+
+    def _attach(self, X, y, theta, nv, nv_host, kind, dim):
+        self.B, self.n_pad, self.D = X.shape[0], X.shape[1], int(dim)
+        self.kind = int(kind)
+        self.X, self.y, self.theta, self.nv, self.nv_host = X, y, theta, nv, nv_host
+        B, n_pad, dev = self.B, self.n_pad, X.device
         self.L = torch.empty((B, n_pad, n_pad), dtype=F64, device=dev)
         self.invd = torch.empty((B, n_pad // TILE, TILE, TILE), dtype=F64, device=dev)
         self.alpha = torch.empty((B, n_pad), dtype=F64, device=dev)
@@ -226,13 +412,7 @@ class DevicePosterior(object):
 
     # -- candidates -------------------------------------------------------------
     def upload_points(self, pts_list):
-        mv = [len(p) for p in pts_list]
-        m_pad = pad_to(max(mv + [1]))
-        Ph = np.zeros((self.B, m_pad, self.D))
-        for b, p in enumerate(pts_list):
-            if mv[b]:
-                Ph[b, :mv[b]] = np.asarray(p, dtype=np.float64).reshape(mv[b], self.D)
-        return _h2d(Ph), _h2d(np.asarray(mv, dtype=np.int32), I32), mv, m_pad
+        return upload_points(self.B, self.D, pts_list)
 
     def mean(self, Xs, mv_dev):
         B, m_pad, _ = Xs.shape
@@ -375,9 +555,13 @@ def philox_normals(B, m_pad, S, seed, trial_ids, dev):
 
 def segment_argmax(Fm, S, seg_ptr_host):
     """seg_ptr_host: int array [B, nseg + 1] -> (max [B, nseg, S], arg [B, nseg, S])."""
-    seg = np.asarray(seg_ptr_host, dtype=np.int32)
-    B, nseg = seg.shape[0], seg.shape[1] - 1
-    seg_d = _h2d(seg, I32)
+    if torch.is_tensor(seg_ptr_host):
+        seg_d = seg_ptr_host
+        B, nseg = seg_d.shape[0], seg_d.shape[1] - 1
+    else:
+        seg = np.asarray(seg_ptr_host, dtype=np.int32)
+        B, nseg = seg.shape[0], seg.shape[1] - 1
+        seg_d = _h2d(seg, I32)
     mx = torch.empty((B, nseg, S), dtype=F64, device=Fm.device)
     ag = torch.empty((B, nseg, S), dtype=I32, device=Fm.device)
     call('ocbo_segment_argmax', _p(Fm), S, Fm.stride(1), Fm.stride(0), _p(seg_d), nseg, _p(mx),

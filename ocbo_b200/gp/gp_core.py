@@ -108,6 +108,7 @@ class B200GPCore(object):
         self.X = [np.asarray(x, dtype=np.float64).ravel() for x in X]
         self.Y = [float(y) for y in Y]
         self._post = None
+        self._xarr = None
         self.chol_jitter = None
         if build_posterior:
             self.build_posterior()
@@ -130,6 +131,13 @@ class B200GPCore(object):
         n = self.num_tr_data
         return np.tril(self._post.L[0, :n, :n].cpu().numpy())
 
+    def X_array(self):
+        """Training inputs as one (n, dim) array (cached until a point is added)."""
+        n = len(self.X)
+        if self._xarr is None or self._xarr.shape[0] != n:
+            self._xarr = np.asarray(self.X, dtype=np.float64).reshape(n, self.dim)
+        return self._xarr
+
     def _mu0(self):
         return float(self.mean_func(np.zeros((1, self.dim)))[0])
 
@@ -146,8 +154,9 @@ class B200GPCore(object):
 
     # -- build_posterior / add_data_single (gp_interface.py:81-88) -----------
     def build_posterior(self):
-        post = DevicePosterior([np.asarray(self.X).reshape(-1, self.dim)], [self.Y],
-                               self.theta()[None, :], self.kernel.kind, self.dim)
+        with engine.staging():
+            post = DevicePosterior([self.X_array()], [self.Y],
+                                   self.theta()[None, :], self.kernel.kind, self.dim)
         post.build()
         self._post = post
         self.chol_jitter = post.jitter[0]
@@ -159,23 +168,69 @@ class B200GPCore(object):
         self.X.append(np.asarray(x, dtype=np.float64).ravel())
         self.Y.append(float(y))
         self._post = None
+        self._xarr = None
 
     def sample_and_pick(self, to_samp, seg_ptr, num_tasks):
         """One joint posterior sample at ``to_samp`` reduced ON THE DEVICE to the
         joint-MTS pick (src/strategies/joint_mts.py:42-57): ``seg_ptr`` holds the
         row offsets of the T old-point segments followed by the T grid segments.
         Returns (task, action index, gain)."""
-        Xd, mv_dev, mv, mean, V, Sigma = self._posterior_at(to_samp, True, True)
-        m, m_pad = mv[0], Sigma.shape[1]
-        Z = engine.pad_normals([rng.normals((m, 1))], mv, m_pad, 1)
-        seg = np.asarray(seg_ptr, dtype=np.int32)[None, :]
-        pend = engine.PendingCholesky(Sigma, mv_dev)
+        if self._post is None:
+            self.build_posterior()
+        base = self._post
+        Xs = np.asarray(to_samp, dtype=np.float64).reshape(-1, self.dim)
+        seg_h = np.asarray(seg_ptr, dtype=np.int32)[None, :]
+        D, T = self.dim, int(num_tasks)
 
-        def tail():
-            Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
-            mx, ag = engine.segment_argmax(Fm, 1, seg)
-            return engine.joint_pick(mx, ag, num_tasks, num_tasks)
+        def stage():
+            Xd, mv_dev, mv, m_pad = engine.upload_points(1, D, [Xs])
+            Z = engine.pad_normals([rng.normals((mv[0], 1))], mv, m_pad, 1)
+            return Xd, mv_dev, mv, m_pad, Z, engine._h2d(seg_h, engine.I32)
 
+        def enqueue(post, staged):
+            Xd, mv_dev, mv, m_pad, Z, seg = staged
+            V = post.solve_cross(Xd, mv_dev)
+            mean = post.mean_from_v(V, mv_dev)
+            Sigma = post.cov(Xd, mv_dev, V, True)
+            pend = engine.PendingCholesky(Sigma, mv_dev)
+
+            def tail():
+                Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
+                mx, ag = engine.segment_argmax(Fm, 1, seg)
+                return engine.joint_pick(mx, ag, T, T)
+            return pend, tail
+
+        if engine.graphs_enabled():
+            from ..batched import _PostView, _rungs
+            m_pad = engine.pad_to(len(Xs))
+            plan = engine.StepPlan.get(('joint', base.kind, D, base.n_pad, m_pad, seg_h.shape[1], T),
+                                       8 * m_pad * (D + 1) + 4 * seg_h.shape[1] + 4096)
+            view = _PostView(base)
+            with plan.staging():
+                staged = stage()
+
+            def body(st, ext):
+                pend, tail = enqueue(_PostView(base, ext).with_info(), st)
+                return list(tail()) + [pend.info, pend.rung]
+
+            task, act, gain, info_s, rung = plan.run(staged, view.tensors(), body)
+            if not (info_s > 0).any():
+                self.last_sample_jitter = _rungs(rung)[0]
+                return int(task[0, 0]), int(act[0, 0]), float(gain[0, 0])
+            # the ladder needs more than the speculative rungs: eager path below.  The normals
+            # were drawn already; reuse them (the global stream must be consumed once).
+            Zh = staged[4].cpu().numpy()[0, :len(Xs), :1]
+            rng_normals = lambda size: Zh.reshape(size)
+        else:
+            rng_normals = None
+        with engine.staging(max(4 << 20, 16 * Xs.size + (1 << 16))):
+            if rng_normals is None:
+                staged = stage()
+            else:
+                Xd, mv_dev, mv, m_pad = engine.upload_points(1, D, [Xs])
+                staged = (Xd, mv_dev, mv, m_pad, engine.pad_normals([rng_normals((mv[0], 1))], mv, m_pad, 1),
+                          engine._h2d(seg_h, engine.I32))
+        pend, tail = enqueue(base, staged)
         task, act, gain = tail()
         status = pend.status()
         self.last_sample_jitter = pend.resolve(status)[0]
