@@ -25,14 +25,14 @@ def _stage_candidates(B, D, pts_list, Z_list, seg_lists):
     return Xd, mv_dev, mv, m_pad, Z, seg
 
 
-def _enqueue_tail(post, staged):
+def _enqueue_tail(post, staged, spec=None):
     """posterior at pts -> Sigma -> stable_cholesky (plain attempt + speculative rungs)
     -> mu + L z -> segment max/argmax, all enqueued, no host round trip."""
     Xd, mv_dev, mv, m_pad, Z, seg = staged
     V = post.solve_cross(Xd, mv_dev)
     mean = post.mean_from_v(V, mv_dev)
     Sigma = post.cov(Xd, mv_dev, V, True)
-    pend = engine.PendingCholesky(Sigma, mv_dev)
+    pend = engine.PendingCholesky(Sigma, mv_dev, spec)
 
     def tail():
         Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
@@ -107,7 +107,7 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
                 packed, staged_ = st
                 post_ = DevicePosterior.from_device(*packed, kind, D)
                 post_.build(check=False, need_alpha=False)
-                _, pend, tail = _enqueue_tail(post_, staged_)
+                _, pend, tail = _enqueue_tail(post_, staged_, engine.GRAPH_SPEC_RUNGS)
                 _, mx_, ag_ = tail()
                 return [mx_, ag_, post_.info, pend.info, pend.rung]
 
@@ -177,9 +177,9 @@ def profile_step(gp, act_sets, Z_list):
     contexts at once.  Returns (sample_max, sample_argmax, mean_max, mean_argmax,
     sample_at_mean_argmax) as arrays over contexts."""
     core = gp.gp_core
-    if core._post is None:
+    if core._post_raw is None:
         core.build_posterior()
-    base = core._post
+    base = core._post_raw  # possibly unverified: checked with the results, below
     B, D = len(act_sets), base.D
     segs = [[0, len(a)] for a in act_sets]
 
@@ -199,11 +199,13 @@ def profile_step(gp, act_sets, Z_list):
 
         def body(st, ext):
             post = SharedPosterior(_PostView(base, ext), B)
-            mean, pend, tail = _enqueue_tail(post, st)
+            mean, pend, tail = _enqueue_tail(post, st, engine.GRAPH_SPEC_RUNGS)
             Fm, mx, ag = tail()
             return [mx, ag] + list(reduce_means(mean, Fm, st[5])) + [pend.info, pend.rung]
 
         mx, ag, mmx, mag, s_at, info_s, rung = plan.run(staged, view.tensors(), body)
+        if base.unchecked and not core._verify(base):
+            return profile_step(gp, act_sets, Z_list)  # K needed the ladder: redo on the rebuilt factor
         if not (info_s > 0).any():
             res = tuple(np.array(v) for v in (mx[:, 0, 0], ag[:, 0, 0], mmx, mag, s_at))
             core.last_sample_jitter = _rungs(rung)
@@ -212,6 +214,8 @@ def profile_step(gp, act_sets, Z_list):
         with engine.staging():
             staged = _stage_candidates(B, D, act_sets, Z_list, segs)
         mx, ag, mean, Fm, mv, jit = _sample_reduce(post, staged)
+        if base.unchecked and not core._verify(base):
+            return profile_step(gp, act_sets, Z_list)
         mmx, mag, s_at = [t.cpu().numpy() for t in reduce_means(mean, Fm, staged[5])]
         core.last_sample_jitter = jit
         res = (mx[:, 0], ag[:, 0], mmx, mag, s_at)

@@ -380,6 +380,7 @@ class DevicePosterior(object):
         self.info = torch.zeros((B,), dtype=I32, device=dev)
         self.jitter = [None] * B
         self.built = False
+        self.unchecked = False
 
     # -- build_posterior: K + noise I -> L -> alpha, LML  (gp_interface.py:85-88) --
     def _assemble_K(self, b0, b1):
@@ -465,6 +466,7 @@ class DevicePosterior(object):
         return out
 
 
+GRAPH_SPEC_RUNGS = 2    # rungs captured into a StepPlan's graph (a parked rung replays in ~1 us per kernel)
 NO_RUNG = -100          # rung[b] while no jitter has been needed
 LADDER = range(-11, 5)  # stable_cholesky's exponents
 

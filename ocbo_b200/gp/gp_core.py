@@ -107,11 +107,34 @@ class B200GPCore(object):
         self.dim = kernel.dim
         self.X = [np.asarray(x, dtype=np.float64).ravel() for x in X]
         self.Y = [float(y) for y in Y]
-        self._post = None
+        self._post_raw = None
         self._xarr = None
         self.chol_jitter = None
         if build_posterior:
             self.build_posterior()
+
+    # -- the device posterior; its Cholesky status is verified lazily -----------
+    @property
+    def _post(self):
+        p = self._post_raw
+        if p is not None and getattr(p, 'unchecked', False):
+            self._verify(p)
+        return p
+
+    @_post.setter
+    def _post(self, value):
+        self._post_raw = value
+
+    def _verify(self, post):
+        """First host read of a posterior built without a round trip: if the plain Cholesky
+        of K + noise I failed, walk stable_cholesky's ladder now.  Returns False in that
+        (rare) case, i.e. when whatever was enqueued on the unverified factor must be redone."""
+        failed = bool(post.info.cpu().numpy().any())
+        if failed:
+            post.build()
+        post.unchecked = False
+        self.chol_jitter = post.jitter[0]
+        return not failed
 
     # -- attributes the reference reads -------------------------------------
     @property
@@ -157,9 +180,9 @@ class B200GPCore(object):
         with engine.staging():
             post = DevicePosterior([self.X_array()], [self.Y],
                                    self.theta()[None, :], self.kernel.kind, self.dim)
-        post.build()
-        self._post = post
-        self.chol_jitter = post.jitter[0]
+        post.build(check=False)  # verified at the first host read (_verify)
+        self._post_raw = post
+        self.chol_jitter = None
 
     def add_data_single(self, x, y):
         """Append one observation.  Dragonfly rebuilds the posterior here; the
@@ -170,29 +193,34 @@ class B200GPCore(object):
         self._post = None
         self._xarr = None
 
-    def sample_and_pick(self, to_samp, seg_ptr, num_tasks):
+    def sample_and_pick(self, to_samp, seg_ptr, num_tasks, _normals=None):
         """One joint posterior sample at ``to_samp`` reduced ON THE DEVICE to the
         joint-MTS pick (src/strategies/joint_mts.py:42-57): ``seg_ptr`` holds the
         row offsets of the T old-point segments followed by the T grid segments.
         Returns (task, action index, gain)."""
-        if self._post is None:
+        if self._post_raw is None:
             self.build_posterior()
-        base = self._post
+        base = self._post_raw  # possibly unverified: checked with the results, below
         Xs = np.asarray(to_samp, dtype=np.float64).reshape(-1, self.dim)
         seg_h = np.asarray(seg_ptr, dtype=np.int32)[None, :]
         D, T = self.dim, int(num_tasks)
+        # the global normal stream is consumed exactly once per call, whatever path is taken
+        Zh = rng.normals((len(Xs), 1)) if _normals is None else _normals
 
         def stage():
             Xd, mv_dev, mv, m_pad = engine.upload_points(1, D, [Xs])
-            Z = engine.pad_normals([rng.normals((mv[0], 1))], mv, m_pad, 1)
+            Z = engine.pad_normals([Zh], mv, m_pad, 1)
             return Xd, mv_dev, mv, m_pad, Z, engine._h2d(seg_h, engine.I32)
 
-        def enqueue(post, staged):
+        def verified():
+            return not base.unchecked or self._verify(base)
+
+        def enqueue(post, staged, spec=None):
             Xd, mv_dev, mv, m_pad, Z, seg = staged
             V = post.solve_cross(Xd, mv_dev)
             mean = post.mean_from_v(V, mv_dev)
             Sigma = post.cov(Xd, mv_dev, V, True)
-            pend = engine.PendingCholesky(Sigma, mv_dev)
+            pend = engine.PendingCholesky(Sigma, mv_dev, spec)
 
             def tail():
                 Fm = engine.sample_from_factor(mean, Sigma, Z, pend.info)
@@ -210,29 +238,23 @@ class B200GPCore(object):
                 staged = stage()
 
             def body(st, ext):
-                pend, tail = enqueue(_PostView(base, ext).with_info(), st)
+                pend, tail = enqueue(_PostView(base, ext).with_info(), st, engine.GRAPH_SPEC_RUNGS)
                 return list(tail()) + [pend.info, pend.rung]
 
             task, act, gain, info_s, rung = plan.run(staged, view.tensors(), body)
+            if not verified():
+                return self.sample_and_pick(to_samp, seg_ptr, num_tasks, Zh)
             if not (info_s > 0).any():
                 self.last_sample_jitter = _rungs(rung)[0]
                 return int(task[0, 0]), int(act[0, 0]), float(gain[0, 0])
-            # the ladder needs more than the speculative rungs: eager path below.  The normals
-            # were drawn already; reuse them (the global stream must be consumed once).
-            Zh = staged[4].cpu().numpy()[0, :len(Xs), :1]
-            rng_normals = lambda size: Zh.reshape(size)
-        else:
-            rng_normals = None
+            # the ladder needs more than the speculative rungs: eager path below
         with engine.staging(max(4 << 20, 16 * Xs.size + (1 << 16))):
-            if rng_normals is None:
-                staged = stage()
-            else:
-                Xd, mv_dev, mv, m_pad = engine.upload_points(1, D, [Xs])
-                staged = (Xd, mv_dev, mv, m_pad, engine.pad_normals([rng_normals((mv[0], 1))], mv, m_pad, 1),
-                          engine._h2d(seg_h, engine.I32))
+            staged = stage()
         pend, tail = enqueue(base, staged)
         task, act, gain = tail()
         status = pend.status()
+        if not verified():
+            return self.sample_and_pick(to_samp, seg_ptr, num_tasks, Zh)
         self.last_sample_jitter = pend.resolve(status)[0]
         if status[0][0] > 0:
             task, act, gain = tail()

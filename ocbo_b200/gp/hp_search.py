@@ -17,6 +17,7 @@ median(Y) +- 3 std(Y), bw_j in std(X_j)*[1e-2, 1e2] (log-uniform where positive)
 """
 import numpy as np
 
+from .. import engine
 from ..engine import DevicePosterior
 
 
@@ -53,12 +54,19 @@ def hp_candidates(X, Y, num, uniforms=None):
 
 
 def batched_lml(X, Y, kind, thetas):
-    """LML of every theta row in one device batch.  Returns (lml ndarray, post)."""
+    """LML of every theta row in one device batch.  Returns (lml ndarray, post).  The data
+    set is uploaded once and shared by all candidates (batch stride 0); a candidate whose
+    Gram matrix needs the jitter ladder gets it (stable_cholesky), like any posterior."""
     X = np.asarray(X, dtype=np.float64)
     n, D = X.shape
+    thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, 3 + D)
     B = len(thetas)
-    post = DevicePosterior([X] * B, [Y] * B, thetas, kind, D)
-    post.build()
+    with engine.staging(16 * X.size + 8 * thetas.size + (1 << 16)):
+        Xd, yd, _, nv, nv_host = DevicePosterior.pack([X], [Y], thetas[:1], D)
+        th = engine._h2d(thetas)
+    post = DevicePosterior.from_device(Xd.expand(B, -1, -1), yd.expand(B, -1), th, nv.repeat(B),
+                                       nv_host * B, kind, D)
+    post.build(need_alpha=False)
     return post.lml.cpu().numpy(), post
 
 

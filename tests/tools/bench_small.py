@@ -24,6 +24,23 @@ def _timeit(f, reps, sync):
     return (time.perf_counter() - t0) / reps
 
 
+def _cpu_best(f, reps):
+    """Oracle steps/s at its best BLAS thread count: the option-file shapes are small, and
+    LAPACK on 16+ threads is several times SLOWER than on one for them (set2d: 25 vs 330
+    steps/s); the baseline gets whichever is faster.  Returns (steps/s, threads)."""
+    best = (0.0, None)
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        return 1.0 / _timeit(f, reps, lambda: None), 'default'
+    for limit in (1, None):
+        with threadpool_limits(limits=limit):
+            rate = 1.0 / _timeit(f, reps, lambda: None)
+        if rate > best[0]:
+            best = (rate, 1 if limit == 1 else (os.cpu_count() or 1))
+    return best
+
+
 def _hp(X, y):
     v = max(float(np.var(y)), 1e-6)
     return dict(scale=v, bw=0.3 * (X.max(0) - X.min(0) + 1e-3), noise=0.01 * v, mu0=float(np.median(y)))
@@ -36,7 +53,7 @@ def measure(gpu_reps=20, cpu_reps=3):
     from oracle import gp_numpy as o, picks
     sync = torch.cuda.synchronize
     nosync = lambda: None
-    out = {}
+    out, jobs = {}, []
     rs = np.random.RandomState(0)
     np.random.seed(0)
     # set2d (T=5, d=2, n_f=50 mid-run) and rand6d (T=30, d=6, n_f=55): independent GPs (mts.py)
@@ -49,20 +66,18 @@ def measure(gpu_reps=20, cpu_reps=3):
         go = [o.make_gp(X, y, 'se', h['scale'], h['bw'], h['noise'], h['mu0'])
               for X, y, h in zip(Xl, yl, hl)]
 
-        def gpu_step():
+        def gpu_step(Xl=Xl, gb=gb, T=T, d=d, nf=nf):
             pts = [np.vstack([X, np.random.uniform(size=(100, d))]) for X in Xl]
             Z = [np.random.normal(size=(len(p), 1)) for p in pts]
             return batched.mts_step(gb, pts, [nf] * T, Z)
 
-        def cpu_step():
+        def cpu_step(Xl=Xl, go=go, T=T, d=d, nf=nf):
             res = []
             for g, X in zip(go, Xl):
                 g.gp_core.build_posterior()  # get_next_gp always rebuilds (gp_interface.py:132)
                 res.append(g.draw_sample(samp_pts=np.vstack([X, np.random.uniform(size=(100, d))])))
             return picks.mts_pick(res, [nf] * T)
-        out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_step, gpu_reps, sync),
-                     'cpu_steps_per_s': 1 / _timeit(cpu_step, cpu_reps, nosync),
-                     'shape': 'T=%d, d=%d, n_f=%d, A=100' % (T, d, nf)}
+        jobs.append((name, gpu_step, cpu_step, 'T=%d, d=%d, n_f=%d, A=100' % (T, d, nf)))
     # jointbran (T=10, n=160, m=1160): joint GP (joint_mts.py)
     T, A, n = 10, 100, 160
     X = np.hstack([np.repeat(np.linspace(0, 1, T), n // T)[:, None], rs.uniform(size=(n, 1))])
@@ -74,17 +89,15 @@ def measure(gpu_reps=20, cpu_reps=3):
     mkgrid = lambda: np.hstack([np.repeat(np.linspace(0, 1, T), A)[:, None],
                                 np.random.uniform(size=(T * A, 1))])
 
-    def gpu_step():
+    def gpu_step(X=X, T=T):
         gbj.gp_core._post = None
         return gbj.gp_core.sample_and_pick(np.vstack([X, mkgrid()]), seg, T)
 
-    def cpu_step():
+    def cpu_step(X=X, T=T, n=n):
         goj.gp_core.build_posterior()
         s = goj.draw_sample(samp_pts=np.vstack([X, mkgrid()]))
         return picks.joint_mts_pick(s, [n // T] * T, T)
-    out['jointbran'] = {'b200_steps_per_s': 1 / _timeit(gpu_step, gpu_reps, sync),
-                        'cpu_steps_per_s': 1 / _timeit(cpu_step, cpu_reps, nosync),
-                        'shape': 'T=10, n=160, m=1160'}
+    jobs.append(('jointbran', gpu_step, cpu_step, 'T=10, n=160, m=1160'))
     # conth42 (n=755, 50 contexts x 100 actions): profile_cts.py
     n, P = 755, 50
     X = rs.uniform(size=(n, 6))
@@ -109,10 +122,46 @@ def measure(gpu_reps=20, cpu_reps=3):
             mu, cov = goc.eval(a, include_covar=True)
             res.append(picks.cmts_gain(goc.draw_sample(means=mu, covar=cov), mu)[1])
         return picks.profile_pick(res)
-    out['conth42'] = {'b200_steps_per_s': 1 / _timeit(gpu_step, gpu_reps, sync),
-                      'cpu_steps_per_s': 1 / _timeit(cpu_step, cpu_reps, nosync),
-                      'shape': 'n=755, 50 contexts x 100 actions, d=6'}
+    jobs.append(('conth42', gpu_step, cpu_step, 'n=755, 50 contexts x 100 actions, d=6'))
+    # device passes first, then the host loops: BLAS worker threads keep spinning after a LAPACK
+    # call and would steal the core that launches the next device step
+    for name, gpu_f, _, shape in jobs:
+        out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_f, gpu_reps, sync), 'shape': shape}
+    lml = measure_lml(gpu_reps, cpu_reps)
+    for name, _, cpu_f, _ in jobs:
+        out[name]['cpu_steps_per_s'], out[name]['cpu_threads'] = _cpu_best(cpu_f, cpu_reps)
+    for v in lml.values():
+        v['cpu_evals_per_s'], v['cpu_threads'] = _cpu_best(v.pop('_cpu'), cpu_reps)
+        v['cpu_evals_per_s'] *= 64
+    out['lml_evals'] = lml
     return out
+
+
+def measure_lml(gpu_reps=20, cpu_reps=3):
+    """LML evaluations/s over a batch of hyper-parameter candidates (SURVEY 8a row a7 / 8d:
+    "LML throughput reported separately"): 64 candidates x one data set per device pass
+    (Gram -> Cholesky -> solve -> LML for all candidates at once) vs the numpy oracle's loop."""
+    import torch
+    from ocbo_b200 import synth
+    from ocbo_b200.gp import hp_search
+    from oracle import gp_numpy as o
+    rs = np.random.RandomState(1)
+    res = {}
+    for name, n, d in (('rand6d_task', 55, 6), ('jointbran', 160, 2), ('conth42', 755, 6)):
+        X = rs.uniform(size=(n, d))
+        y = np.asarray([synth.hartmann6(x) for x in X]) if d == 6 else np.sin(3 * X.sum(1))
+        thetas = hp_search.hp_candidates(X, y, 64, uniforms=rs.uniform(size=(63, 3 + d)))
+        kind = 0  # SE
+
+        def gpu(X=X, y=y, thetas=thetas):
+            return hp_search.batched_lml(X, y, kind, thetas)[0]
+
+        def cpu(X=X, y=y, thetas=thetas):
+            return [o.log_marginal_likelihood(X, y, 'se', th) for th in thetas]
+        tg = _timeit(gpu, gpu_reps, torch.cuda.synchronize)
+        res[name] = {'b200_evals_per_s': 64 / tg, '_cpu': cpu,
+                     'shape': 'n=%d, d=%d, 64 candidates per pass' % (n, d)}
+    return res
 
 
 if __name__ == '__main__':
