@@ -283,9 +283,16 @@ int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* 
   cudaStream_t st = (cudaStream_t)stream;
   const int nt = n / TILE, ntc = nrhs / TN;
   const int64_t sInv = ocbo_invdiag_elems(n);
+  // Block forward substitution with the inverted diagonal blocks.  Left-looking (block row I
+  // gets ONE update of k = 128 I, then the multiply by inv(L_II)) launches ntc * batch CTAs per
+  // step: right for wide right-hand sides (the sweep: 128 column tiles per trial).  When that
+  // does not fill the GPU (conth42: 50 contexts x 2 column tiles on 148 SMs, k up to 640 per
+  // CTA) the right-looking form is used instead: finished block row I updates ALL rows below
+  // it in one launch of (nt - 1 - I) ntc batch CTAs with k = 128.
+  const bool right = nt >= 3 && (long long)ntc * batch < 296;
   for (int I = 0; I < nt; ++I) {
     double* BI = B + (size_t)I * TILE * ldb;
-    if (I > 0) {
+    if (!right && I > 0) {
       NnParams u{};
       u.P = L + (size_t)I * TILE * ldl; u.ldp = ldl; u.sP = s_l;
       u.R = B; u.ldr = ldb; u.sR = s_b;
@@ -299,6 +306,14 @@ int ocbo_trsm_lower(const double* L, int n, int ldl, int64_t s_l, const double* 
     m.C = BI; m.ldc = ldb; m.sC = s_b;
     m.ktiles = TILE / BK; m.ntr = 1; m.tri_k = 0; m.pair_rows = 0; m.mode = 0; m.info = info;
     CK(launch_gemm_nn(m, 1, ntc, batch, st), "trsm diag");
+    if (right && I + 1 < nt) {
+      NnParams u{};
+      u.P = L + (size_t)(I + 1) * TILE * ldl + (size_t)I * TILE; u.ldp = ldl; u.sP = s_l;
+      u.R = BI; u.ldr = ldb; u.sR = s_b;
+      u.C = B + (size_t)(I + 1) * TILE * ldb; u.ldc = ldb; u.sC = s_b;
+      u.ktiles = TILE / BK; u.ntr = 1; u.tri_k = 0; u.pair_rows = 0; u.mode = 1; u.info = info;
+      CK(launch_gemm_nn(u, nt - 1 - I, ntc, batch, st), "trsm trailing update");
+    }
   }
   return 0;
 }

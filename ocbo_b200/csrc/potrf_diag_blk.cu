@@ -18,7 +18,12 @@
 //   update   everyone: rank-16 update of its registers, A -= P P^T, W -= P W_J, operands
 //            read from shared memory (broadcast / conflict-free strides).
 //
-// Measured on B200 (profiles/): see DESIGN.md section 5.
+// Measured on B200 (tests/tools/bench_diag.py, diag_trace.cu): 40 us per block against 60 us for
+// the column-per-barrier kernel; per block step 4.35 k clocks in the factor+solve chain
+// (270 per column with all 8 warps riding), 2.5-4.3 k in the update, 8 k once for the final
+// stores.  Tried and dropped: a look-ahead variant (rest of the update interleaved with the next
+// block step's chain in one uniform loop) -- bit-identical too, but the loop form of the chain
+// (runtime pivot lane, full-width shuffles) cost 450 clocks per column: 53 us per block.
 #include "common.cuh"
 #include "kernels.h"
 

@@ -381,6 +381,7 @@ class DevicePosterior(object):
         self.jitter = [None] * B
         self.built = False
         self.unchecked = False
+        self.has_alpha = False
 
     # -- build_posterior: K + noise I -> L -> alpha, LML  (gp_interface.py:85-88) --
     def _assemble_K(self, b0, b1):
@@ -401,13 +402,10 @@ class DevicePosterior(object):
         else:
             self.info.zero_()
             potrf(self.L, self.invd, self.info, self.nv)
-        # alpha for the mean-only evaluations (K(Xs, X) alpha), w = L^{-1}(y - mu0) for the ones that
-        # have V = L^{-1} K(X, Xs) at hand anyway (mean = mu0 + V^T w: one pass over V, no kernel)
-        call('ocbo_solve_alpha_w_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
-             _p(self.invd), _p(self.y), self.y.stride(0), _p(self.nv), _p(self.theta),
-             self.theta.stride(0), _p(self.alpha) if need_alpha else None, self.alpha.stride(0),
-             _p(self.w), self.w.stride(0), _p(self.lml), _p(self.info), self.B, _stream())
-        _count(1)
+        # w = L^{-1}(y - mu0) and the LML always (mean = mu0 + V^T w wherever V = L^{-1} K(X, Xs) is
+        # at hand: one pass over V, no kernel evaluations); alpha = L^{-T} w, the back-substitution
+        # half of the single-CTA solve, only when asked for or on first use (ensure_alpha)
+        self._solve(need_alpha)
         self.built = True
         return self
 
@@ -415,7 +413,21 @@ class DevicePosterior(object):
     def upload_points(self, pts_list):
         return upload_points(self.B, self.D, pts_list)
 
+    def _solve(self, with_alpha):
+        call('ocbo_solve_alpha_w_lml', _p(self.L), self.n_pad, self.L.stride(1), self.L.stride(0),
+             _p(self.invd), _p(self.y), self.y.stride(0), _p(self.nv), _p(self.theta),
+             self.theta.stride(0), _p(self.alpha) if with_alpha else None, self.alpha.stride(0),
+             _p(self.w), self.w.stride(0), _p(self.lml), _p(self.info), self.B, _stream())
+        _count(1)
+        self.has_alpha = bool(with_alpha)
+
+    def ensure_alpha(self):
+        if not self.has_alpha:
+            self._solve(True)
+        return self.alpha
+
     def mean(self, Xs, mv_dev):
+        self.ensure_alpha()
         B, m_pad, _ = Xs.shape
         out = torch.empty((B, m_pad), dtype=F64, device=Xs.device)
         call('ocbo_post_mean', self.kind, self.D, _p(Xs), m_pad, Xs.stride(0), _p(mv_dev), _p(self.X),

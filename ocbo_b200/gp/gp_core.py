@@ -136,6 +136,9 @@ class B200GPCore(object):
         self.chol_jitter = post.jitter[0]
         return not failed
 
+    def has_posterior(self):
+        return self._post_raw is not None
+
     # -- attributes the reference reads -------------------------------------
     @property
     def num_tr_data(self):
@@ -145,7 +148,7 @@ class B200GPCore(object):
     def alpha(self):
         if self._post is None:
             return None
-        return self._post.alpha[0, :self.num_tr_data].cpu().numpy()
+        return self._post.ensure_alpha()[0, :self.num_tr_data].cpu().numpy()
 
     @property
     def L(self):
@@ -180,7 +183,7 @@ class B200GPCore(object):
         with engine.staging():
             post = DevicePosterior([self.X_array()], [self.Y],
                                    self.theta()[None, :], self.kernel.kind, self.dim)
-        post.build(check=False)  # verified at the first host read (_verify)
+        post.build(check=False, need_alpha=False)  # verified at the first host read (_verify)
         self._post_raw = post
         self.chol_jitter = None
 

@@ -80,7 +80,9 @@ class B200GP(GPWrapper):
         self.gp_core.add_data_single(pt, val)  # :81-83
 
     def build_posterior(self):
-        if self.gp_core.alpha is None:  # :85-88, idempotent
+        # :85-88 tests ``alpha is not None``; here alpha is materialised on first read, so the
+        # equivalent idempotence test is on the device posterior itself
+        if not self.gp_core.has_posterior():
             self.gp_core.build_posterior()
 
     def get_estimated_noise(self):
