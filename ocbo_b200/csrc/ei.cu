@@ -5,7 +5,7 @@
 // the reference's EI-family acquisitions (src/util/misc_util.py:368-385,
 // src/strategies/joint_mei.py:39-48, src/cstrats/profile_cts.py:54-67) without ever
 // forming the m x m covariance: O(m n) instead of O(m^2 n).  HBM-bound: V is read once,
-// coalesced (thread = candidate, rows of V are contiguous in the candidate index).
+// coalesced (lane = candidate, rows of V are contiguous in the candidate index).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,41 +23,54 @@ struct EiArgs {
   double* mean_out; int64_t sMeanOut;
 };
 
-__global__ void __launch_bounds__(128) post_var_ei_kernel(EiArgs a) {
+// One CTA = 32 candidates x 8 row slices: warp w walks rows k = w, w+8, ... of V (each row
+// access is one 256-byte line per warp), 8 loads in flight per thread; the 8 partial sums are
+// combined through shared memory in a fixed order, so results do not depend on scheduling.
+// (The first version used one thread per candidate and one CTA per 128 candidates: 64 CTAs
+// for the sweep's m = 8192 and 354 GB/s; this one keeps m/32 CTAs x 8 warps busy.)
+constexpr int EI_COLS = 32, EI_SLICES = 8;
+
+__global__ void __launch_bounds__(EI_COLS * EI_SLICES) post_var_ei_kernel(EiArgs a) {
+  __shared__ double ps[EI_SLICES][EI_COLS], pd[EI_SLICES][EI_COLS];
   const int b = blockIdx.y;
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= a.m) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * EI_COLS + lane;
   const int nv = a.nv ? a.nv[b] : a.n;
   const int mv = a.mv ? a.mv[b] : a.m;
-  const double* V = a.V + (size_t)b * a.sV + i;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  const bool in = i < a.m;
+  const double* V = a.V + (size_t)b * a.sV + (in ? i : 0);
   const double* w = a.w ? a.w + (size_t)b * a.sW : nullptr;
-  int k = 0;
-  for (; k + 3 < nv; k += 4) {
-    const double v0 = V[(size_t)k * a.ldv], v1 = V[(size_t)(k + 1) * a.ldv];
-    const double v2 = V[(size_t)(k + 2) * a.ldv], v3 = V[(size_t)(k + 3) * a.ldv];
-    s0 = fma(v0, v0, s0);
-    s1 = fma(v1, v1, s1);
-    s2 = fma(v2, v2, s2);
-    s3 = fma(v3, v3, s3);
-    if (w) {
-      d0 = fma(v0, w[k], d0);
-      d1 = fma(v1, w[k + 1], d1);
-      d2 = fma(v2, w[k + 2], d2);
-      d3 = fma(v3, w[k + 3], d3);
+  double s = 0.0, d = 0.0;
+  int k = slice;
+  for (; k + 7 * EI_SLICES < nv; k += 8 * EI_SLICES) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = in ? V[(size_t)(k + u * EI_SLICES) * a.ldv] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s = fma(v[u], v[u], s);
+      if (w) d = fma(v[u], w[k + u * EI_SLICES], d);
     }
   }
-  for (; k < nv; ++k) {
-    const double v = V[(size_t)k * a.ldv];
-    s0 = fma(v, v, s0);
-    if (w) d0 = fma(v, w[k], d0);
+  for (; k < nv; k += EI_SLICES) {
+    const double v = in ? V[(size_t)k * a.ldv] : 0.0;
+    s = fma(v, v, s);
+    if (w) d = fma(v, w[k], d);
+  }
+  ps[slice][lane] = s;
+  pd[slice][lane] = d;
+  __syncthreads();
+  if (slice != 0 || !in) return;
+#pragma unroll
+  for (int u = 1; u < EI_SLICES; ++u) {
+    s += ps[u][lane];
+    d += pd[u][lane];
   }
   if (a.mean_out)
     a.mean_out[(size_t)b * a.sMeanOut + i] =
-        (i < mv) ? a.theta[(size_t)b * a.sTheta + TH_MU0] + ((d0 + d1) + (d2 + d3)) : 0.0;
+        (i < mv) ? a.theta[(size_t)b * a.sTheta + TH_MU0] + d : 0.0;
   const double scale = a.theta[(size_t)b * a.sTheta + TH_SCALE];
-  const double var = (i < mv) ? scale - ((s0 + s1) + (s2 + s3)) : 1.0;
+  const double var = (i < mv) ? scale - s : 1.0;
   if (a.var) a.var[(size_t)b * a.sVar + i] = var;
   if (a.ei) {
     double ei = -CUDART_INF;  // padding never wins an arg-max
@@ -80,7 +93,7 @@ cudaError_t launch_post_var_ei(const double* V, int n, int ldv, int64_t sV, cons
                                int64_t sMeanOut) {
   EiArgs a{V, n, ldv, sV, nv, mean, sMean, theta, sTheta, best, m, mv, var, sVar, ei, sEi,
            w, sW, mean_out, sMeanOut};
-  post_var_ei_kernel<<<dim3((m + 127) / 128, batch), 128, 0, st>>>(a);
+  post_var_ei_kernel<<<dim3((m + EI_COLS - 1) / EI_COLS, batch), EI_COLS * EI_SLICES, 0, st>>>(a);
   return counted(cudaGetLastError());
 }
 

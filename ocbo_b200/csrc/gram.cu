@@ -16,6 +16,11 @@ struct GramArgs {
   int kind, dim, flags;
 };
 
+// KIND is a template parameter and every kernel value of the thread's 8 x 2 patch is evaluated
+// unconditionally (padding is selected afterwards): 16 independent exp() chains per thread in
+// straight-line code.  With the kind tested at run time inside the loop the compiler kept the
+// evaluations serial and the kernel sat at 20 % FP64-pipe utilisation (85 us for 1024 x 8192).
+template <int KIND>
 __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
   __shared__ double x1s[MAXD][GT];
   __shared__ __align__(16) double x2s[MAXD][GT];
@@ -53,10 +58,10 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
   const double noise = (a.flags & OCBO_GRAM_ADD_NOISE) ? th[TH_NOISE] : 0.0;
   double* K = a.K + (size_t)b * a.sK;
   const int gj = col0 + 2 * tx;
+  double kv[GT / 8][2];
 #pragma unroll
   for (int k = 0; k < GT / 8; ++k) {
     const int r = ty + 8 * k;
-    const int gi = row0 + r;
     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
     for (int d = 0; d < MAXD; ++d) {
@@ -67,19 +72,22 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
         d1 = fma(e1, e1, d1);
       }
     }
-    double o0, o1;
-    if (gi < nv1 && gj < nv2) {
-      o0 = kern_eval(a.kind, scale, d0);
-      if (sym && gi == gj) o0 += noise;
-    } else {
-      o0 = (sym && gi == gj) ? 1.0 : 0.0;
-    }
-    if (gi < nv1 && gj + 1 < nv2) {
-      o1 = kern_eval(a.kind, scale, d1);
-      if (sym && gi == gj + 1) o1 += noise;
-    } else {
-      o1 = (sym && gi == gj + 1) ? 1.0 : 0.0;
-    }
+    kv[k][0] = d0;
+    kv[k][1] = d1;
+  }
+#pragma unroll
+  for (int k = 0; k < GT / 8; ++k) {
+    kv[k][0] = kern_eval(KIND, scale, kv[k][0]);
+    kv[k][1] = kern_eval(KIND, scale, kv[k][1]);
+  }
+#pragma unroll
+  for (int k = 0; k < GT / 8; ++k) {
+    const int gi = row0 + ty + 8 * k;
+    const bool vr = gi < nv1;
+    double o0 = (vr && gj < nv2) ? kv[k][0] : 0.0;
+    double o1 = (vr && gj + 1 < nv2) ? kv[k][1] : 0.0;
+    if (sym && gi == gj) o0 = (vr && gj < nv2) ? o0 + noise : 1.0;
+    if (sym && gi == gj + 1) o1 = (vr && gj + 1 < nv2) ? o1 + noise : 1.0;
     *reinterpret_cast<double2*>(K + (size_t)gi * a.ldk + gj) = make_double2(o0, o1);
   }
 }
@@ -90,7 +98,12 @@ cudaError_t launch_gram(int kind, int dim, const double* X1, int n1, int64_t sX1
                         int batch, int flags, cudaStream_t st) {
   GramArgs a{X1, n1, sX1, nv1, X2, n2, sX2, nv2, theta, sTheta, K, ldk, sK, kind, dim, flags};
   dim3 grid(n2 / GT, n1 / GT, batch);
-  gram_kernel<<<grid, 256, 0, st>>>(a);
+  switch (kind) {
+    case OCBO_KERNEL_SE: gram_kernel<OCBO_KERNEL_SE><<<grid, 256, 0, st>>>(a); break;
+    case OCBO_KERNEL_MATERN12: gram_kernel<OCBO_KERNEL_MATERN12><<<grid, 256, 0, st>>>(a); break;
+    case OCBO_KERNEL_MATERN32: gram_kernel<OCBO_KERNEL_MATERN32><<<grid, 256, 0, st>>>(a); break;
+    default: gram_kernel<OCBO_KERNEL_MATERN52><<<grid, 256, 0, st>>>(a); break;
+  }
   return counted(cudaGetLastError());
 }
 

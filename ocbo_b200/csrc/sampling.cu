@@ -81,17 +81,32 @@ segment_argmax_kernel(const double* F, int S, int ldf, int64_t sF, const int32_t
                       double* out_max, int32_t* out_arg, int CS) {
   __shared__ double sv[256];
   __shared__ int si[256];
-  const int j = blockIdx.x, b = blockIdx.y;
+  const int j = blockIdx.x, b = blockIdx.z;
   const int32_t* seg = seg_ptr + (size_t)b * (nseg + 1);
   const int r0 = seg[j], r1 = seg[j + 1];
   const double* Fb = F + (size_t)b * sF;
   const int tx = threadIdx.x % CS, ty = threadIdx.x / CS, RL = 256 / CS;
-  for (int s0 = 0; s0 < S; s0 += CS) {
+  // one CTA per (segment, chunk of CS <= 32 sample columns, problem): for the sweep (64
+  // segments x 256 draws) that is 512 CTAs instead of 64, rows walked 4 at a time
+  {
+    const int s0 = blockIdx.y * CS;
     const int s = s0 + tx;
     double best = -CUDART_INF;
     int arg = -1;
     if (s < S) {
-      for (int i = r0 + ty; i < r1; i += RL) {
+      int i = r0 + ty;
+      for (; i + 3 * RL < r1; i += 4 * RL) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = Fb[(size_t)(i + u * RL) * ldf + s];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[u] > best || arg < 0) {
+            best = v[u];
+            arg = i + u * RL;
+          }
+      }
+      for (; i < r1; i += RL) {
         const double v = Fb[(size_t)i * ldf + s];
         if (v > best || arg < 0) {
           best = v;
@@ -128,9 +143,9 @@ cudaError_t launch_segment_argmax(const double* F, int S, int ldf, int64_t sF,
                                   const int32_t* seg_ptr, int nseg, double* out_max,
                                   int32_t* out_arg, int batch, cudaStream_t st) {
   int CS = 1;
-  while (CS * 2 <= S && CS < 256) CS *= 2;
-  segment_argmax_kernel<<<dim3(nseg, batch), 256, 0, st>>>(F, S, ldf, sF, seg_ptr, nseg, out_max,
-                                                           out_arg, CS);
+  while (CS * 2 <= S && CS < 32) CS *= 2;
+  segment_argmax_kernel<<<dim3(nseg, (S + CS - 1) / CS, batch), 256, 0, st>>>(
+      F, S, ldf, sF, seg_ptr, nseg, out_max, out_arg, CS);
   return counted(cudaGetLastError());
 }
 
@@ -143,19 +158,29 @@ __global__ void joint_pick_kernel(const double* seg_max, const int32_t* seg_arg,
   const int b = idx / S, s = idx % S;
   const double* mx = seg_max + (size_t)b * nseg * S;
   const int32_t* ag = seg_arg + (size_t)b * nseg * S;
+  // the gains are independent loads (8 in flight); the action index is fetched once, for the
+  // winner only (it used to sit inside the compare: a dependent load per task)
   double best = -CUDART_INF;
-  int bt = 0, ba = -1;
-  for (int t = 0; t < T; ++t) {
-    const double old = n_old_seg ? mx[(size_t)t * S + s] : 0.0;
-    const double gain = mx[(size_t)(n_old_seg + t) * S + s] - old;
-    if (gain > best || ba < 0) {
-      best = gain;
-      bt = t;
-      ba = ag[(size_t)(n_old_seg + t) * S + s];
+  int bt = -1;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    double gain[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u;
+      if (t < T) {
+        const double old = n_old_seg ? mx[(size_t)t * S + s] : 0.0;
+        gain[u] = mx[(size_t)(n_old_seg + t) * S + s] - old;
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (t0 + u < T && (gain[u] > best || bt < 0)) {
+        best = gain[u];
+        bt = t0 + u;
+      }
   }
   out_task[idx] = bt;
-  out_action[idx] = ba;
+  out_action[idx] = ag[(size_t)(n_old_seg + bt) * S + s];
   out_gain[idx] = best;
 }
 

@@ -12,7 +12,10 @@ WANT = [('gpu__time_duration.sum', 'dur'), ('launch__grid_size', 'grid'),
         ('smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'st_math'),
         ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'st_bar'),
         ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'st_short'),
-        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'st_wait')]
+        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'st_wait'),
+        ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'fp64_pct_active'),
+        ('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'xu_pct_active'),
+        ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_conflicts')]
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h, u = rows[0], rows[1]
@@ -23,4 +26,16 @@ for r in rows[2:]:
         if name in h:
             i = h.index(name)
             parts.append('%s=%s%s' % (short, r[i][:9], u[i] if short in ('dur', 'dram_rd', 'dram_wr') else ''))
+    try:  # achieved DRAM GB/s = (read + write bytes) / duration, in the units ncu printed
+        def val(name):
+            i = h.index(name)
+            x = float(r[i].replace(',', ''))
+            unit = u[i].lower()
+            scale = {'byte': 1.0, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9, 'ns': 1e-9, 'us': 1e-6,
+                     'usecond': 1e-6, 'ms': 1e-3, 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1.0}
+            return x * scale.get(unit, 1.0)
+        gbs = (val('dram__bytes_read.sum') + val('dram__bytes_write.sum')) / val('gpu__time_duration.sum') / 1e9
+        parts.append('dram_GBps=%.0f' % gbs)
+    except Exception:
+        pass
     print('  '.join(parts))
