@@ -5,6 +5,8 @@
 
 namespace ocbo {
 
+constexpr int TRI_BAND = 8;  // row tiles per band of the triangular tile order (gemm_core.cuh)
+
 // ---------------------------------------------------------------------------
 // C_tile (mode 0: =, mode 1: -=)  P_tile * Q_tile^T
 //   P: rows follow C rows, k contiguous;  Q: rows follow C cols, k contiguous.
@@ -21,7 +23,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(NtParams p) {
   if (p.info && p.info[b] != 0) return;
   int ti, tj;
   if (p.tri) {
-    tri_index_2to1(blockIdx.x, ti, tj);
+    tri_index_2to1_banded<TRI_BAND>(blockIdx.x, p.ntc / (TILE / TN), ti, tj);
   } else {
     ti = blockIdx.x / p.ntc;
     tj = blockIdx.x % p.ntc;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
   const int b = blockIdx.z;
   int ti, tj;
   if (p.tri) {
-    tri_index_2to1(blockIdx.x, ti, tj);
+    tri_index_2to1_banded<TRI_BAND>(blockIdx.x, p.ntc / (TILE / TN), ti, tj);
   } else {
     ti = blockIdx.x / p.ntc;
     tj = blockIdx.x % p.ntc;
