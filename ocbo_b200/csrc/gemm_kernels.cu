@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
 // The Gram term is evaluated in the epilogue from points staged (pre-scaled by
 // 1/bandwidth) in the drained cp.async ring, so K(Xs,Xs) never exists in HBM.
 // ---------------------------------------------------------------------------
-template <int BM, int BN, int WARPS_M, int WARPS_N>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
   using G = Gemm<BM, BN, false, false, WARPS_M, WARPS_N>;
   static_assert(G::SMEM_DOUBLES >= MAXD * (BM + BN), "ring too small for the point staging");
@@ -150,27 +150,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
   const int mav = p.mav ? p.mav[b] : p.ma;
   const int mbv = p.mbv ? p.mbv[b] : p.mb;
   const int row0 = ti * BM, col0 = tj * BN;
-  const int kind = p.kind, sym = p.sym, ldc = p.ldc;
-  G::foreach(acc, [&](int r, int c, double v0, double v1) {
-    double d0 = 0.0, d1 = 0.0;
+  const int sym = p.sym, ldc = p.ldc;
+  // Epilogue in three straight-line passes over the accumulators (KIND is a template
+  // parameter): squared distances, then all 32 kernel values of the thread unconditionally
+  // -- independent exp() chains the scheduler can interleave -- then padding select + store.
+  // (With the kind and the padding tested inside one loop the chains ran one after another
+  // and the epilogue cost about as much as 10 % of the k = 1024 main loop.)
+  // (two halves of the warp tile at a time: 16 values in flight keep the kernel at 128 registers)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int HM = G::MI / 2;
 #pragma unroll
-    for (int d = 0; d < MAXD; ++d) {
-      if (d < D) {
-        const double xr = xa[d * BM + r];
-        const double2 xc = *reinterpret_cast<const double2*>(xb + d * BN + c);
-        const double e0 = xr - xc.x, e1 = xr - xc.y;
-        d0 = fma(e0, e0, d0);
-        d1 = fma(e1, e1, d1);
-      }
+    for (int h = 0; h < 2; ++h) {
+      double kv[HM][G::NI][2];
+#pragma unroll
+      for (int mi = 0; mi < HM; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < G::NI; ++ni) {
+          const int r = wm * G::WM + (h * HM + mi) * 8 + g, c = wn * G::WN + ni * 8 + 2 * t;
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            if (d < D) {
+              const double xr = xa[d * BM + r];
+              const double2 xc = *reinterpret_cast<const double2*>(xb + d * BN + c);
+              const double e0 = xr - xc.x, e1 = xr - xc.y;
+              d0 = fma(e0, e0, d0);
+              d1 = fma(e1, e1, d1);
+            }
+          }
+          kv[mi][ni][0] = d0;
+          kv[mi][ni][1] = d1;
+        }
+#pragma unroll
+      for (int mi = 0; mi < HM; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < G::NI; ++ni) {
+          kv[mi][ni][0] = kern_eval(KIND, scale, kv[mi][ni][0]);
+          kv[mi][ni][1] = kern_eval(KIND, scale, kv[mi][ni][1]);
+        }
+#pragma unroll
+      for (int mi = 0; mi < HM; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < G::NI; ++ni) {
+          const int r = wm * G::WM + (h * HM + mi) * 8 + g, c = wn * G::WN + ni * 8 + 2 * t;
+          const int gi = row0 + r, gj = col0 + c;
+          const bool vr = gi < mav;
+          double o0 = (vr && gj < mbv) ? kv[mi][ni][0] - acc[h * HM + mi][ni][0] : 0.0;
+          double o1 = (vr && gj + 1 < mbv) ? kv[mi][ni][1] - acc[h * HM + mi][ni][1] : 0.0;
+          if (sym && gi == gj && !(vr && gj < mbv)) o0 = 1.0;
+          if (sym && gi == gj + 1 && !(vr && gj + 1 < mbv)) o1 = 1.0;
+          *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(o0, o1);
+        }
     }
-    const int gi = row0 + r, gj = col0 + c;
-    double o0, o1;
-    if (gi < mav && gj < mbv) o0 = kern_eval(kind, scale, d0) - v0;
-    else o0 = (sym && gi == gj) ? 1.0 : 0.0;
-    if (gi < mav && gj + 1 < mbv) o1 = kern_eval(kind, scale, d1) - v1;
-    else o1 = (sym && gi == gj + 1) ? 1.0 : 0.0;
-    *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(o0, o1);
-  });
+  }
 }
 
 // ------------------------------- launchers ---------------------------------
@@ -212,14 +247,24 @@ cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch,
   return counted(cudaGetLastError());
 }
 
-cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
+template <int KIND>
+static cudaError_t launch_postcov_kind(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
   using G = Gemm<TM, TN, false, false, 4, 2>;
   static bool init = false;
-  cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
+  cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2, KIND>, G::SMEM_BYTES, init);
   if (e != cudaSuccess) return e;
-  if (ntiles <= 0 || batch <= 0) return cudaSuccess;
-  postcov_kernel<TM, TN, 4, 2><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  postcov_kernel<TM, TN, 4, 2, KIND><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
   return counted(cudaGetLastError());
+}
+
+cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
+  if (ntiles <= 0 || batch <= 0) return cudaSuccess;
+  switch (p.kind) {
+    case OCBO_KERNEL_SE: return launch_postcov_kind<OCBO_KERNEL_SE>(p, ntiles, batch, st);
+    case OCBO_KERNEL_MATERN12: return launch_postcov_kind<OCBO_KERNEL_MATERN12>(p, ntiles, batch, st);
+    case OCBO_KERNEL_MATERN32: return launch_postcov_kind<OCBO_KERNEL_MATERN32>(p, ntiles, batch, st);
+    default: return launch_postcov_kind<OCBO_KERNEL_MATERN52>(p, ntiles, batch, st);
+  }
 }
 
 }  // namespace ocbo

@@ -177,6 +177,7 @@ struct MeanArgs {
   int kind, dim;
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
   __shared__ double xs[MAXD][128];
   __shared__ double al[128];
@@ -202,16 +203,24 @@ __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
     }
     al[threadIdx.x] = (j0 + threadIdx.x < nv) ? alpha[j0 + threadIdx.x] : 0.0;
     __syncthreads();
-    const int lim = min(128, nv - j0);
-    for (int j = 0; j < lim; ++j) {
-      double d2 = 0.0;
+    // padded training points carry alpha = 0, so whole groups of 4 are evaluated: four
+    // independent exp() chains per step instead of one (the sum order is unchanged)
+    const int lim = (min(128, nv - j0) + 3) & ~3;
+    for (int j = 0; j < lim; j += 4) {
+      double kv[4];
 #pragma unroll
-      for (int d = 0; d < MAXD; ++d)
-        if (d < D) {
-          const double e = xi[d] - xs[d][j];
-          d2 = fma(e, e, d2);
-        }
-      acc = fma(kern_eval(a.kind, scale, d2), al[j], acc);
+      for (int u = 0; u < 4; ++u) {
+        double d2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+          if (d < D) {
+            const double e = xi[d] - xs[d][j + u];
+            d2 = fma(e, e, d2);
+          }
+        kv[u] = kern_eval(KIND, scale, d2);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fma(kv[u], al[j + u], acc);
     }
   }
   if (i < a.m) a.mean[(size_t)b * a.sMean + i] = (i < mv) ? th[TH_MU0] + acc : 0.0;
@@ -223,7 +232,13 @@ cudaError_t launch_post_mean(int kind, int dim, const double* Xs, int m, int64_t
                              const double* alpha, int64_t sAlpha, double* mean, int64_t sMean,
                              int batch, cudaStream_t st) {
   MeanArgs a{Xs, m, sXs, mv, X, n, sX, nv, theta, sTheta, alpha, sAlpha, mean, sMean, kind, dim};
-  post_mean_kernel<<<dim3((m + 127) / 128, batch), 128, 0, st>>>(a);
+  const dim3 grid((m + 127) / 128, batch);
+  switch (kind) {
+    case OCBO_KERNEL_SE: post_mean_kernel<OCBO_KERNEL_SE><<<grid, 128, 0, st>>>(a); break;
+    case OCBO_KERNEL_MATERN12: post_mean_kernel<OCBO_KERNEL_MATERN12><<<grid, 128, 0, st>>>(a); break;
+    case OCBO_KERNEL_MATERN32: post_mean_kernel<OCBO_KERNEL_MATERN32><<<grid, 128, 0, st>>>(a); break;
+    default: post_mean_kernel<OCBO_KERNEL_MATERN52><<<grid, 128, 0, st>>>(a); break;
+  }
   return counted(cudaGetLastError());
 }
 
