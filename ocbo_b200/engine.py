@@ -409,6 +409,19 @@ class DevicePosterior(object):
         self.built = True
         return self
 
+    def build_device_ladder(self, spec=None, need_alpha=False):
+        """``build`` with stable_cholesky walked on the device (PendingCholesky: plain attempt and
+        ``spec`` speculative rungs, no host round trip).  Returns the pending factorisation: the
+        caller reads its status with its results and falls back to ``build()`` if a problem
+        still fails."""
+        self._assemble_K(0, self.B)
+        pend = PendingCholesky(self.L, self.nv, spec)
+        self.invd, self.info = pend.invd, pend.info
+        self.unchecked = True
+        self._solve(need_alpha)
+        self.built = True
+        return pend
+
     # -- candidates -------------------------------------------------------------
     def upload_points(self, pts_list):
         return upload_points(self.B, self.D, pts_list)

@@ -54,18 +54,44 @@ def hp_candidates(X, Y, num, uniforms=None):
 
 
 def batched_lml(X, Y, kind, thetas):
-    """LML of every theta row in one device batch.  Returns (lml ndarray, post).  The data
-    set is uploaded once and shared by all candidates (batch stride 0); a candidate whose
-    Gram matrix needs the jitter ladder gets it (stable_cholesky), like any posterior."""
+    """LML of every theta row in one device batch.  Returns (lml ndarray, post or None).  The
+    data set is uploaded once and shared by all candidates (batch stride 0); a candidate whose
+    Gram matrix needs the jitter ladder gets it (stable_cholesky), like any posterior.  At
+    fixed padded shapes the pass is a replayed CUDA graph (engine.StepPlan): hyper-parameters
+    are re-fitted after every evaluation (``tune_every 1`` in all option files), and for the
+    small data sets of set2d / rand6d the pass is a dozen ~10 us kernels."""
     X = np.asarray(X, dtype=np.float64)
     n, D = X.shape
     thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, 3 + D)
     B = len(thetas)
-    with engine.staging(16 * X.size + 8 * thetas.size + (1 << 16)):
+
+    def stage():
         Xd, yd, _, nv, nv_host = DevicePosterior.pack([X], [Y], thetas[:1], D)
-        th = engine._h2d(thetas)
-    post = DevicePosterior.from_device(Xd.expand(B, -1, -1), yd.expand(B, -1), th, nv.repeat(B),
-                                       nv_host * B, kind, D)
+        return Xd, yd, engine._h2d(thetas), nv, nv_host
+
+    def posterior(st):
+        Xd, yd, th, nv, nv_host = st
+        return DevicePosterior.from_device(Xd.expand(B, -1, -1), yd.expand(B, -1), th, nv.repeat(B),
+                                           nv_host * B, kind, D)
+
+    if engine.graphs_enabled():
+        n_pad = engine.pad_to(max(n, 1))
+        plan = engine.StepPlan.get(('lml', kind, D, B, n_pad),
+                                   8 * (n_pad * (D + 1) + 3 + D + thetas.size) + 16 * engine.Staging.ALIGN)
+        with plan.staging():
+            st = stage()
+
+        def body(st_, ext):
+            post = posterior(st_)
+            pend = post.build_device_ladder(engine.GRAPH_SPEC_RUNGS)
+            return [post.lml, pend.info]
+
+        lml, info = plan.run(st, [], body)
+        if not (info > 0).any():
+            return np.array(lml), None
+    with engine.staging(16 * X.size + 8 * thetas.size + (1 << 16)):
+        st = stage()
+    post = posterior(st)
     post.build(need_alpha=False)
     return post.lml.cpu().numpy(), post
 

@@ -100,3 +100,29 @@ def test_plan_falls_back_when_the_ladder_needs_the_host(monkeypatch):
     ref = batched.mts_step(gps, pts, [40], Z)
     assert got == ref and jit == gps[0].gp_core.last_sample_jitter
     assert jit is not None
+
+
+def test_lml_plan_equals_eager_and_handles_the_ladder(monkeypatch):
+    """Batched LML over hyper-parameter candidates: replayed graph == eager launches, also for
+    candidates whose Gram matrix only factors with jitter (duplicated inputs, vanishing noise)."""
+    from ocbo_b200 import engine
+    from ocbo_b200.gp import hp_search
+    from oracle import gp_numpy as o
+    rs = np.random.RandomState(4)
+    X = rs.uniform(size=(70, 3))
+    X[10:20] = X[:10]                       # duplicates: K is singular without the noise term
+    y = np.sin(4 * X.sum(1))
+    cands = hp_search.hp_candidates(X, y, 16, uniforms=rs.uniform(size=(15, 6)))
+    cands[3, 1] = 1e-18                     # noise far below the ladder's first rung
+    cands[7, 1] = 1e-18
+    engine.StepPlan.clear()
+    monkeypatch.setattr(engine, 'graphs_enabled', lambda: True)
+    a1 = hp_search.batched_lml(X, y, 0, cands)[0]
+    a2 = hp_search.batched_lml(X, y, 0, cands)[0]
+    monkeypatch.setattr(engine, 'graphs_enabled', lambda: False)
+    b = hp_search.batched_lml(X, y, 0, cands)[0]
+    assert np.array_equal(a1, a2) and np.array_equal(a1, b)
+    ref = np.asarray([o.log_marginal_likelihood(X, y, 'se', th) for th in cands])
+    ok = [i for i in range(16) if i not in (3, 7)]
+    assert np.max(np.abs(a1[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))) <= 1e-8
+    assert np.all(np.isfinite(a1))          # the jittered candidates got a factor too
