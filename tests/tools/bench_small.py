@@ -123,6 +123,13 @@ def measure(gpu_reps=20, cpu_reps=3):
             res.append(picks.cmts_gain(goc.draw_sample(means=mu, covar=cov), mu)[1])
         return picks.profile_pick(res)
     jobs.append(('conth42', gpu_step, cpu_step, 'n=755, 50 contexts x 100 actions, d=6'))
+    # A step here is ~1 ms of which half is Python: the interpreter's cyclic collector matters.
+    # Inside bench.py the heap holds ~180 k long-lived objects (sweep groups, clock samples ...)
+    # and every full collection triggered by a step's temporaries walks all of them (rand6d:
+    # 2.07 ms/step, 1.05 after freezing).  Freeze what exists now, as a long-running service would.
+    import gc
+    gc.collect()
+    gc.freeze()
     # device passes first, then the host loops: BLAS worker threads keep spinning after a LAPACK
     # call and would steal the core that launches the next device step
     for name, gpu_f, _, shape in jobs:
