@@ -122,8 +122,12 @@ def load_traffic(batch):
     try:
         with open(path) as fh:
             t = json.load(fh)
-        return {'dram_bytes': t['dram_bytes'] * batch, 'launches': t['launches'],
-                'scope': t['scope'], 'source': t['source']}
+        out = {'dram_bytes': t['dram_bytes'] * batch, 'launches': t['launches'],
+               'scope': t['scope'], 'source': t['source']}
+        if 'algorithmic_bytes' in t:
+            out['algorithmic_bytes'] = t['algorithmic_bytes'] * batch
+            out['dram_over_algorithmic'] = t['dram_bytes'] / t['algorithmic_bytes']
+        return out
     except Exception:
         return None
 
