@@ -356,6 +356,25 @@ def run_b200(args):
         gathered = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
         dist.gather(last, gathered, dst=0)
 
+    # ---- the option-file shapes at N > 1: every rank runs its own independent decisions ------
+    # (BO trials shard with no collective, SURVEY 8e: the aggregate is the sum of the ranks' rates)
+    small_multi = None
+    if world > 1 and not args.no_cpu_baseline:
+        try:
+            from tests.tools import bench_small
+            names = ['set2d', 'rand6d', 'jointbran', 'conth42']
+            barrier()
+            mine = bench_small.measure(cpu=False)
+            rates = torch.tensor([mine[k]['b200_steps_per_s'] for k in names], dtype=torch.float64,
+                                 device=dev)
+            lo = rates.clone()
+            dist.all_reduce(rates, op=dist.ReduceOp.SUM)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            small_multi = {k: {'b200_steps_per_s': float(rates[i]), 'slowest_rank_steps_per_s': float(lo[i]),
+                               'n_gpus': world, 'shape': mine[k]['shape']} for i, k in enumerate(names)}
+        except Exception as exc:
+            small_multi = {'error': repr(exc)}
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel: Cholesky trailing update (DMMA) ------
@@ -452,6 +471,8 @@ def run_b200(args):
                 line['mts_bo_steps'] = bench_small.measure()
             except Exception as exc:  # secondary figure: never lose the headline line
                 line['mts_bo_steps'] = {'error': repr(exc)}
+        elif small_multi is not None:
+            line['mts_bo_steps'] = small_multi
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -46,7 +46,7 @@ def _hp(X, y):
     return dict(scale=v, bw=0.3 * (X.max(0) - X.min(0) + 1e-3), noise=0.01 * v, mu0=float(np.median(y)))
 
 
-def measure(gpu_reps=20, cpu_reps=3):
+def measure(gpu_reps=20, cpu_reps=3, cpu=True):
     import torch
     from ocbo_b200 import batched, synth
     from ocbo_b200.gp.gp_interface import make_gp
@@ -134,6 +134,8 @@ def measure(gpu_reps=20, cpu_reps=3):
     # call and would steal the core that launches the next device step
     for name, gpu_f, _, shape in jobs:
         out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_f, gpu_reps, sync), 'shape': shape}
+    if not cpu:
+        return out
     lml = measure_lml(gpu_reps, cpu_reps)
     for name, _, cpu_f, _ in jobs:
         out[name]['cpu_steps_per_s'], out[name]['cpu_threads'] = _cpu_best(cpu_f, cpu_reps)
