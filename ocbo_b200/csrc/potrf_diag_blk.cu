@@ -118,13 +118,21 @@ __device__ __forceinline__ void blk_factor_solve(BlkSmem& sm, int J, int tid) {
 // ---- update (shared -> registers), block step J ---------------------------------------
 template <int J>
 __device__ __forceinline__ void blk_update(double (&a)[NBLK][NBLK], double (&w)[NBLK][NBLK],
-                                           const BlkSmem& sm, int tx, int ty) {
-  // finalised values of this block step owned by this thread
-  a[J][J] = sm.D[ty][tx];  // lower part meaningful (the upper part is never stored)
+                                           const BlkSmem& sm, int tx, int ty, double* Ab, int lda,
+                                           double* Inv) {
+  // Block column J of L and block row J of W are final now: they go out to global memory here
+  // (fire-and-forget stores that overlap the update below) instead of in one 8 k-clock burst of
+  // 128 stores per thread at the end of the kernel.
+  {
+    const int iJ = ty + G * J, jJ = tx + G * J;
+    const bool low = tx <= ty;
+    Ab[(size_t)iJ * lda + jJ] = low ? sm.D[ty][tx] : 0.0;
 #pragma unroll
-  for (int ia = J + 1; ia < NBLK; ++ia) a[ia][J] = sm.P[ty + G * ia][tx];
+    for (int ia = J + 1; ia < NBLK; ++ia) Ab[(size_t)(ty + G * ia) * lda + jJ] = sm.P[ty + G * ia][tx];
 #pragma unroll
-  for (int ib = 0; ib <= J; ++ib) w[J][ib] = sm.X[ty][tx + G * ib];
+    for (int ib = 0; ib < J; ++ib) Inv[iJ * NBR + tx + G * ib] = sm.X[ty][tx + G * ib];
+    Inv[iJ * NBR + jJ] = low ? sm.X[ty][tx + G * J] : 0.0;
+  }
   if (J + 1 >= NBLK) return;
 #pragma unroll 1
   for (int k = 0; k < G; ++k) {
@@ -180,6 +188,7 @@ potrf_diag_blk_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, i
   const int tx = tid & (G - 1), ty = tid >> 4;
   double* Ab = A + (size_t)b * sA + (size_t)j0 * lda + j0;
 
+  double* Inv = invdiag + (size_t)b * sInv + (size_t)(j0 / NBR) * NBR * NBR;
   double a[NBLK][NBLK];  // only ib <= ia used
   double w[NBLK][NBLK];
   BLK_MARK(64);
@@ -190,6 +199,14 @@ potrf_diag_blk_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, i
       const int i = ty + G * ia, j = tx + G * ib;
       a[ia][ib] = Ab[(size_t)i * lda + j];
       w[ia][ib] = (i == j) ? 1.0 : 0.0;
+    }
+  // blocks above the diagonal of L and of inv(L) are zero (consumers read full 128 x 128 tiles)
+#pragma unroll
+  for (int ia = 0; ia < NBLK; ++ia)
+#pragma unroll
+    for (int ib = ia + 1; ib < NBLK; ++ib) {
+      Ab[(size_t)(ty + G * ia) * lda + tx + G * ib] = 0.0;
+      Inv[(ty + G * ia) * NBR + tx + G * ib] = 0.0;
     }
   // identity padding: only the block steps that hold valid columns are run (bit-identical)
   int stages = NBLK;
@@ -214,29 +231,22 @@ potrf_diag_blk_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, i
     BLK_MARK(8 * J + 3);
     BLK_MARK(8 * J + 4);
     BLK_MARK(8 * J + 5);
-    OCBO_BLK_DISPATCH(blk_update, J, a, w, sm, tx, ty)
+    OCBO_BLK_DISPATCH(blk_update, J, a, w, sm, tx, ty, Ab, lda, Inv)
     BLK_MARK(8 * J + 6);
     __syncthreads();
     BLK_MARK(8 * J + 7);
   }
   BLK_MARK(65);
-  // L in place (strictly upper part zeroed) and inv(L) to the workspace
-  double* Inv = invdiag + (size_t)b * sInv + (size_t)(j0 / NBR) * NBR * NBR;
+  // block rows that only hold identity padding were not touched: L stays as it came in,
+  // inv(L) is the identity there
 #pragma unroll
-  for (int ia = 0; ia < NBLK; ++ia)
+  for (int ia = 0; ia < NBLK; ++ia) {
+    if (ia >= stages) {
 #pragma unroll
-    for (int ib = 0; ib < NBLK; ++ib) {
-      const int i = ty + G * ia, j = tx + G * ib;
-      double lv = 0.0, xv = 0.0;
-      if (ib <= ia) {
-        if (j <= i) {
-          lv = a[ia][ib];
-          xv = w[ia][ib];
-        }
-      }
-      Ab[(size_t)i * lda + j] = lv;
-      Inv[i * NBR + j] = xv;
+      for (int ib = 0; ib <= ia; ++ib)
+        Inv[(ty + G * ia) * NBR + tx + G * ib] = (ia == ib && tx == ty) ? 1.0 : 0.0;
     }
+  }
   BLK_MARK(66);
 }
 }  // namespace
