@@ -14,8 +14,8 @@ int main() {
   for (auto& g : G) g = rand() / (double)RAND_MAX - 0.5;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) {
-      double s = (i == j) ? 0.1 : 0.0;
-      for (int k = 0; k < n + 8; ++k) s += G[i * (n + 8) + k] * G[j * (n + 8) + k] / n;
+      double s = (i == j) ? 4.0 : 0.0;  // strongly diagonal: the factor is PD too (OCBO_BLK_REPS)
+      for (int k = 0; k < n + 8; ++k) s += 0.01 * G[i * (n + 8) + k] * G[j * (n + 8) + k] / n;
       A[i * n + j] = s;
     }
   double *dA, *dInv; int* dInfo;
@@ -29,12 +29,11 @@ int main() {
   long long t[68];
   cudaMemcpyFromSymbol(t, ocbo::g_blk_trace, sizeof(t));
   printf("load %lld clk, store %lld clk, total %lld clk\n", t[0] - t[64], t[66] - t[65], t[66] - t[64]);
-  const char* names[7] = {"gather+bar", "micro", "bar", "solve", "bar", "update", "bar"};
-  for (int J = 0; J < 8; ++J) {
-    printf("J=%d:", J);
-    for (int p = 0; p < 7; ++p) printf(" %s %lld", names[p], t[8 * J + p + 1] - t[8 * J + p]);
-    printf("  | step %lld\n", t[8 * J + 7] - t[8 * J]);
-  }
+  for (int J = 0; J < 8; ++J)
+    printf("J=%d: gather+bar %lld factor+solve %lld bar %lld stores %lld first-load %lld loop %lld bar %lld | step %lld\n",
+           J, t[8 * J + 1] - t[8 * J], t[8 * J + 2] - t[8 * J + 1], t[8 * J + 5] - t[8 * J + 2],
+           t[8 * J + 3] - t[8 * J + 5], J < 7 ? t[8 * J + 4] - t[8 * J + 3] : 0,
+           J < 7 ? t[8 * J + 6] - t[8 * J + 4] : 0, t[8 * J + 7] - t[8 * J + 6], t[8 * J + 7] - t[8 * J]);
   int info; cudaMemcpy(&info, dInfo, 4, cudaMemcpyDeviceToHost);
   printf("info %d\n", info);
   return 0;
