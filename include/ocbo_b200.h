@@ -107,6 +107,16 @@ int ocbo_ladder_restore(double* A, const double* A0, int n, int lda, int64_t s_a
                         double factor, int batch, ocbo_stream_t stream);
 int ocbo_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int batch,
                         ocbo_stream_t stream);
+/* Speculative first rung factored CONCURRENTLY with the plain attempt (on another stream, on a
+ * copy A1 = A0 + 10^p max(diag) I with its own invdiag1 / info1): problems whose plain attempt
+ * failed (info[b] > 0) while the speculative one succeeded (info1[b] == 0) adopt it --
+ * A[b], invdiag[b] <- A1[b], invdiag1[b]; info[b] = 0; rung[b] = p.  Same layout (lda, s_a) for
+ * A and A1.  MTS samples at the queried points, so the plain attempt fails on almost every step
+ * and the first rung almost always succeeds: the decision's latency is max, not sum. */
+int ocbo_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t s_a,
+                      double* invdiag, const double* invdiag1,
+                      int32_t* info, const int32_t* info1, int32_t* rung, int p, int batch,
+                      ocbo_stream_t stream);
 
 /* ocbo_potrf with CUDA events around every launch, summed per kernel class into
  * ms_host[4] = { diagonal-block, panel-solve, in-panel rank-128 update,

@@ -262,6 +262,23 @@ int ocbo_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int bat
   return 0;
 }
 
+int ocbo_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t s_a, double* invdiag,
+                      const double* invdiag1, int32_t* info, const int32_t* info1, int32_t* rung,
+                      int p, int batch, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (!A1) return fail_arg(2, "A1 null");
+  if (!tile_ok(n)) return fail_arg(3, "n must be a positive multiple of 128");
+  if (lda < n) return fail_arg(4, "lda");
+  if (!invdiag || !invdiag1) return fail_arg(6, "invdiag null");
+  if (!info || !info1) return fail_arg(8, "info null");
+  if (!rung) return fail_arg(10, "rung null");
+  if (batch <= 0) return fail_arg(12, "batch");
+  CK(launch_ladder_adopt(A, A1, n, lda, s_a, invdiag, invdiag1, ocbo_invdiag_elems(n), info, info1,
+                         rung, p, batch, (cudaStream_t)stream),
+     "ocbo_ladder_adopt");
+  return 0;
+}
+
 // Same factorisation, instrumented: CUDA events after every launch on `stream`,
 // summed per kernel class into ms_host[4] = {diag, panel, inner update, outer
 // update}.  Synchronous (bench.py's roofline leg only).

@@ -79,6 +79,10 @@ cudaError_t launch_ladder_restore(double* A, const double* A0, int n, int lda, i
                                   double factor, int batch, cudaStream_t st);
 cudaError_t launch_ladder_advance(int32_t* info, int32_t* rung, int p, int finish, int batch,
                                   cudaStream_t st);
+cudaError_t launch_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t sA, double* invd,
+                                const double* invd1, int64_t sInv, int32_t* info,
+                                const int32_t* info1, int32_t* rung, int p, int batch,
+                                cudaStream_t st);
 cudaError_t launch_solve_alpha_lml(const double* L, int n, int ldl, int64_t sL,
                                    const double* invdiag, int64_t sInv, const double* y, int64_t sY,
                                    const int32_t* nv, const double* theta, int64_t sTheta,

@@ -70,7 +70,55 @@ __global__ void ladder_advance_kernel(int32_t* info, int32_t* rung, int p, int f
     info[b] = -1;
   }
 }
+// Speculative first rung, run CONCURRENTLY with the plain attempt on a copy (A1 = A0 + jitter):
+// problems whose plain attempt failed (info > 0) while the speculative one succeeded
+// (info1 == 0) adopt the speculative factor.  ladder_adopt copies, ladder_adopt_mark updates the
+// status afterwards (two kernels: many CTAs of a problem read info while it must not change).
+__global__ void __launch_bounds__(256)
+ladder_adopt_kernel(double* A, const double* A1, int n, int lda, int64_t sA, double* invd,
+                    const double* invd1, int64_t sInv, const int32_t* info, const int32_t* info1) {
+  const int b = blockIdx.z;
+  if (!(info[b] > 0 && info1[b] == 0)) return;
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  if ((tj * RT) / TILE > (ti * RT) / TILE) return;
+  const double* S = A1 + (size_t)b * sA;
+  double* Dm = A + (size_t)b * sA;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < RT; k += 8) {
+    const int r = ti * RT + ty + k, c = tj * RT + tx;
+    Dm[(size_t)r * lda + c] = S[(size_t)r * lda + c];
+  }
+  if (ti == tj) {  // the inverted diagonal blocks: RT rows of the 128 x 128 block ti*RT/128
+    const int blk = (ti * RT) / TILE, r0 = (ti * RT) % TILE;
+    const double* Is = invd1 + (size_t)b * sInv + (size_t)blk * TILE * TILE + (size_t)r0 * TILE;
+    double* Id = invd + (size_t)b * sInv + (size_t)blk * TILE * TILE + (size_t)r0 * TILE;
+    for (int e = threadIdx.x; e < RT * TILE; e += 256) Id[e] = Is[e];
+  }
+}
+
+__global__ void ladder_adopt_mark_kernel(int32_t* info, const int32_t* info1, int32_t* rung, int p,
+                                         int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (info[b] > 0 && info1[b] == 0) {
+    info[b] = 0;
+    rung[b] = p;
+  }
+}
 }  // namespace
+
+cudaError_t launch_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t sA, double* invd,
+                                const double* invd1, int64_t sInv, int32_t* info,
+                                const int32_t* info1, int32_t* rung, int p, int batch,
+                                cudaStream_t st) {
+  ladder_adopt_kernel<<<dim3(n / RT, n / RT, batch), 256, 0, st>>>(A, A1, n, lda, sA, invd, invd1,
+                                                                    sInv, info, info1);
+  cudaError_t e = counted(cudaGetLastError());
+  if (e != cudaSuccess) return e;
+  ladder_adopt_mark_kernel<<<(batch + 127) / 128, 128, 0, st>>>(info, info1, rung, p, batch);
+  return counted(cudaGetLastError());
+}
 
 cudaError_t launch_ladder_restore(double* A, const double* A0, int n, int lda, int64_t sA, int lda0,
                                   int64_t sA0, const int32_t* nv, const int32_t* info,

@@ -415,7 +415,9 @@ class DevicePosterior(object):
         caller reads its status with its results and falls back to ``build()`` if a problem
         still fails."""
         self._assemble_K(0, self.B)
-        pend = PendingCholesky(self.L, self.nv, spec)
+        # prior Gram matrices carry the noise term and factor at the plain attempt: speculating
+        # the first rung side by side would only double the work (LML batches fill the GPU)
+        pend = PendingCholesky(self.L, self.nv, spec, concurrent_first=False)
         self.invd, self.info = pend.invd, pend.info
         self.unchecked = True
         self._solve(need_alpha)
@@ -512,13 +514,24 @@ def ladder_rungs(A, A0, invd, info, rung, nv, exponents):
     _count(1)
 
 
+_SIDE = {}
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 class PendingCholesky(object):
     """A batched stable_cholesky in flight: the plain attempt and the first ``spec`` rungs
     are enqueued without a host round trip (small problems hit the ladder routinely:
     MTS samples at the queried points, so Sigma is numerically singular); ``status`` is the
     one synchronisation, ``resolve`` walks the remaining rungs for whatever still fails."""
 
-    def __init__(self, A, nv_dev, spec=None):
+    def __init__(self, A, nv_dev, spec=None, concurrent_first=True):
         B, m_pad, _ = A.shape
         nt = m_pad // TILE
         self.A, self.nv = A, nv_dev
@@ -530,10 +543,48 @@ class PendingCholesky(object):
         if spec is None:
             # a parked rung still costs its (empty) launches: speculate only when a rung is cheap
             spec = 2 if nt <= 4 else 0
-        potrf(A, self.invd, self.info, nv_dev)
         self.next = LADDER[0] + spec
+        if spec and concurrent_first:
+            self._first_rung_concurrently()
+            if spec > 1:
+                ladder_rungs(A, self.A0, self.invd, self.info, self.rung, nv_dev, LADDER[1:spec])
+            return
+        potrf(A, self.invd, self.info, nv_dev)
         if spec:
             ladder_rungs(A, self.A0, self.invd, self.info, self.rung, nv_dev, LADDER[:spec])
+
+    def _first_rung_concurrently(self):
+        """The plain attempt on ``A`` and rung -11 on a copy, side by side on two streams
+        (include/ocbo_b200.h, ocbo_ladder_adopt): in MTS the first almost always fails and
+        the second almost always succeeds, so the factorisation's latency is max, not sum.
+        Same kernels on the same data as the sequential walk: same bits."""
+        A, A0, nv = self.A, self.A0, self.nv
+        B, n, _ = A.shape
+        p = LADDER[0]
+        cur, side = torch.cuda.current_stream(), _side_stream()
+        A1 = torch.empty_like(A)
+        invd1 = torch.empty_like(self.invd)
+        info1 = torch.zeros_like(self.info)
+        every = torch.ones_like(self.info)  # restore gate: all problems
+        if not torch.cuda.is_current_stream_capturing():  # (a graph's pool is never recycled)
+            for t in (A1, invd1, info1, every, A0) + ((nv,) if nv is not None else ()):
+                t.record_stream(side)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            call('ocbo_ladder_restore', _p(A1), _p(A0), n, A1.stride(1), A1.stride(0), A0.stride(1),
+                 A0.stride(0), _p(nv), _p(every), float(10.0 ** p), B, _stream())
+            _count(1)
+            potrf(A1, invd1, info1, nv)
+            join = torch.cuda.Event()
+            join.record(side)
+        potrf(A, self.invd, self.info, nv)
+        cur.wait_event(join)
+        call('ocbo_ladder_adopt', _p(A), _p(A1), n, A.stride(1), A.stride(0), _p(self.invd), _p(invd1),
+             _p(self.info), _p(info1), _p(self.rung), int(p), B, _stream())
+        _count(2)
+        self._spec_buffers = (A1, invd1, info1, every)  # alive until the adopt has been enqueued
 
     def status(self):
         return self.info.cpu().numpy(), self.rung.cpu().numpy()

@@ -244,6 +244,37 @@ def test_device_ladder_walks_each_problem_to_its_own_rung(mods):
         engine.PendingCholesky(Bd, engine._h2d(np.asarray([4], dtype=np.int32), engine.I32)).resolve()
 
 
+def test_concurrent_first_rung_equals_the_sequential_walk(mods):
+    """The speculative rung -11 factored on a second stream next to the plain attempt
+    (ocbo_ladder_adopt) must leave exactly what the sequential ladder leaves: factor, inverted
+    diagonal blocks, rung and status, for PD, singular and needs-a-larger-rung problems."""
+    torch, engine = mods['torch'], mods['engine']
+    rs = np.random.RandomState(12)
+    m_pad = 384
+
+    def psd(m, rank):
+        G = rs.normal(size=(m, rank))
+        return G.dot(G.T) / rank
+
+    mats = [psd(300, 600) + 1e-3 * np.eye(300), psd(384, 120), psd(200, 60) - 1e-6 * np.eye(200),
+            psd(30, 5), psd(129, 129) + 1e-6 * np.eye(129)]
+    mv = [len(M) for M in mats]
+    Sh = np.tile(np.eye(m_pad), (len(mats), 1, 1))
+    for b, M in enumerate(mats):
+        Sh[b, :mv[b], :mv[b]] = M
+    outs = []
+    for conc in (False, True):
+        Sd = engine._h2d(Sh)
+        mv_dev = engine._h2d(np.asarray(mv, dtype=np.int32), engine.I32)
+        pend = engine.PendingCholesky(Sd, mv_dev, spec=2, concurrent_first=conc)
+        jit = pend.resolve()
+        outs.append((np.tril(Sd.cpu().numpy()), pend.invd.cpu().numpy(), pend.info.cpu().numpy(), jit))
+    assert outs[0][3] == outs[1][3] and outs[0][3][0] is None and outs[0][3][1] is not None
+    assert outs[0][3][2] > -10
+    for k in range(3):
+        assert np.array_equal(outs[0][k], outs[1][k])
+
+
 def test_potrf_skips_identity_padding_bit_exactly(mods):
     """ocbo_potrf_nv == ocbo_potrf on identity-padded problems, bit for bit (L and the
     inverted diagonal blocks), for valid sizes on and off the 16-column stage boundaries."""
