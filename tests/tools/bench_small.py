@@ -136,6 +136,7 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
         out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_f, gpu_reps, sync), 'shape': shape}
     if not cpu:
         return out
+    out['bo_loop'] = measure_bo_loop()
     lml = measure_lml(gpu_reps, cpu_reps)
     for name, _, cpu_f, _ in jobs:
         out[name]['cpu_steps_per_s'], out[name]['cpu_threads'] = _cpu_best(cpu_f, cpu_reps)
@@ -144,6 +145,34 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
         v['cpu_evals_per_s'] *= 64
     out['lml_evals'] = lml
     return out
+
+
+def measure_bo_loop(capital=40):
+    """Whole BO iterations/s through the drivers that read the reference's option files
+    (ocbo_b200.ocbo / cts_ocbo): hyper-parameter re-fit (64-candidate LML pass) + posterior draw
+    + decision + objective evaluation + bookkeeping every iteration, one method, one trial.
+    Device-side only: the reference's own loop needs Dragonfly."""
+    import tempfile
+    import torch
+    from tests.tools.profile_driver import OPTS
+    res = {}
+    for name, (kind, text) in OPTS.items():
+        if kind == 'd':
+            from ocbo_b200 import ocbo as drv
+        else:
+            from ocbo_b200 import cts_ocbo as drv
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, 'o.txt')
+            with open(path, 'w') as fh:
+                fh.write(text % capital)
+            drv.run(argv=['--options', path])  # warm-up: step plans, kernels
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            drv.run(argv=['--options', path])
+            torch.cuda.synchronize()
+            res[name] = {'b200_iterations_per_s': capital / (time.perf_counter() - t0),
+                         'iterations': capital, 'what': text.replace('\n', ' ').strip() % capital}
+    return res
 
 
 def measure_lml(gpu_reps=20, cpu_reps=3):
