@@ -44,6 +44,10 @@ docbo_args = [
     get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
     get_option_specs('run_ei_after', False, None, 'Ignored (REVI only).'),
     get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
+    get_option_specs('chop_h4_2', False, False, 'Hartmann 4 contexts / 2 actions task set.'),
+    get_option_specs('chop_h2_2', False, False, 'Hartmann 2 contexts / 2 actions task set.'),
+    get_option_specs('chop_h3_1', False, False, 'Hartmann 3 contexts / 1 action task set.'),
+    get_option_specs('num_eval_pts', False, 100, 'Ignored (REVI only).'),
 ]
 rand_fs_args = [
     get_option_specs('easy_masses', False, 0, 'Easy random mass functions.'),
@@ -63,6 +67,13 @@ def assemble(options):
                                            options.hard_masses, options.massf_dim, scaling)
     if options.cts_f is not None:
         f_infos += synth.assemble_chopped_1d_functions(options.cts_f, options.num_chops)
+    # src/ocbo.py:84-89
+    if options.chop_h4_2:
+        f_infos += synth.get_chopped_h42()
+    if options.chop_h2_2:
+        f_infos += synth.get_chopped_h22()
+    if options.chop_h3_1:
+        f_infos += synth.get_chopped_h31()
     if not f_infos:
         raise ValueError('No functions specified')
     return f_infos

@@ -39,11 +39,38 @@ def hartmann6(x):
     return float(np.sum(_H6_ALPHA * np.exp(-np.sum(_H6_A * d ** 2, axis=1))))
 
 
+_H4_A = np.asarray([[10, 3, 17, 3.5], [0.05, 10, 17, 0.1], [3, 3.5, 1.7, 10], [17, 8, 0.05, 10]])
+_H4_P = 1e-4 * np.asarray([[1312, 1696, 5569, 124], [2329, 4135, 8307, 3736],
+                           [2348, 1451, 3522, 2883], [4047, 8828, 8732, 5743]], dtype=np.float64)
+_H3_A = np.asarray([[3, 10, 30], [0.1, 10, 35], [3, 10, 30], [0.1, 10, 35]])
+_H3_P = 1e-4 * np.asarray([[3689, 1170, 2673], [4699, 4387, 7470], [1091, 8732, 5547],
+                           [381, 5743, 8828]], dtype=np.float64)
+
+
+def hartmann4(x):
+    """twod.py:179-193: the rescaled 4-D Hartmann function (1.1 - sum_i alpha_i exp(-q_i)) / 0.839
+    (conth22 / conth31 and the chopped h2-2 / h3-1 task sets)."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x - _H4_P
+    return float((1.1 - np.sum(_H6_ALPHA * np.exp(-np.sum(_H4_A * d ** 2, axis=1)))) / 0.839)
+
+
+def hartmann3(x):
+    """twod.py:163-177."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x - _H3_P
+    return float(np.sum(_H6_ALPHA * np.exp(-np.sum(_H3_A * d ** 2, axis=1))))
+
+
 synth_functions = [
     Namespace(function=branin, domain=[[0, 1], [0, 1]], max_val=0.397887, name='branin'),
     Namespace(function=parabaloid, domain=[[-1, 1], [-1, 1]], max_val=1, name='parabaloid'),
     Namespace(function=hartmann6, domain=[[0, 1] for _ in range(6)], max_val=3.32237,
               name='hartmann6'),
+    Namespace(function=hartmann3, domain=[[0, 1] for _ in range(3)], max_val=3.86278,
+              name='hartmann3'),
+    Namespace(function=hartmann4, domain=[[0, 1] for _ in range(4)], max_val=None,
+              name='hartmann4'),
 ]
 
 
@@ -82,6 +109,38 @@ def assemble_chopped_1d_functions(f_name, num_divisions):
     return [Namespace(function=make_chop(div), domain=[full.domain[1]], max_val=None, f_loc=[div],
                       name='%s_%d' % (f_name, i))
             for i, div in enumerate(np.linspace(lo, hi, num_divisions))]
+
+
+def _chopped(full_f, locations, act_dim, name_fmt):
+    """Tasks = a function of (context, action) frozen at the given context locations
+    (continuous_2d.py:43-95): f_loc is the context, the domain the unit action box."""
+    def make_chop(z):
+        return lambda x: full_f(np.append(z, np.asarray(x, dtype=np.float64)))
+
+    return [Namespace(function=make_chop(np.asarray(loc)), domain=[[0, 1] for _ in range(act_dim)],
+                      max_val=None, f_loc=np.asarray(loc), name=name_fmt % i)
+            for i, loc in enumerate(locations)]
+
+
+def get_chopped_h42():
+    """16 tasks: Hartmann-6 with its 4 context coordinates at the corners of {0,1}^4 (binary
+    counting order), 2-D actions (jointh42.txt)."""
+    corners = [[(i >> s) & 1 for s in (3, 2, 1, 0)] for i in range(16)]
+    return _chopped(hartmann6, corners, 2, 'hartmann_%d')
+
+
+def get_chopped_h22():
+    """9 tasks: Hartmann-4 with 2 context coordinates on the 3 x 3 grid of {0, .5, 1} (first
+    coordinate slowest), 2-D actions (jointh22.txt)."""
+    g = np.linspace(0, 1, 3)
+    return _chopped(hartmann4, [[a, b] for a in g for b in g], 2, 'h2-2_%d')
+
+
+def get_chopped_h31():
+    """8 tasks: Hartmann-4 with 3 context coordinates at the corners of {0,1}^3 (first
+    coordinate slowest), 1-D actions (jointh31.txt)."""
+    g = np.linspace(0, 1, 2)
+    return _chopped(hartmann4, [[a, b, c] for a in g for b in g for c in g], 1, 'h3-1_%d')
 
 
 def create_mass_func(num_masses, band_bounds, scale_bounds, domain):

@@ -48,6 +48,55 @@ def test_reference_continuous_option_file_parses_unchanged():
     assert cts_ocbo.find_function(o.function).name == 'hartmann6'
 
 
+@pytest.mark.refsrc
+def test_every_reference_option_file_parses_and_assembles():
+    """All 15 option files of the reference (src/options/*.txt) load through the drivers'
+    option specs and assemble their task functions (f4: callers either side of the path)."""
+    from ocbo_b200 import cts_ocbo, ocbo
+    from ocbo_b200.cstrats.cts_opt import cts_opt_args
+    from ocbo_b200.cstrats.profile_cts import prof_args
+    from ocbo_b200.options import load_options
+    from ocbo_b200.strategies.multi_opt import multi_opt_args
+    expect = {'jointbran.txt': 10, 'jointh22.txt': 9, 'jointh31.txt': 8, 'jointh42.txt': 16,
+              'rand4d.txt': 30, 'rand6d.txt': 30, 'set2d.txt': 5}
+    names = sorted(os.listdir(REF_OPTS))
+    assert len(names) == 15
+    for name in names:
+        path = os.path.join(REF_OPTS, name)
+        if name.startswith('cont'):
+            o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args, cmd_line=True,
+                             argv=['--options', path])
+            f = cts_ocbo.find_function(o.function)
+            assert len(f.domain) - o.act_dim >= 1 and 'cmts' in o.methods
+        else:
+            o = load_options(ocbo.docbo_args + multi_opt_args + ocbo.rand_fs_args, cmd_line=True,
+                             argv=['--options', path])
+            np.random.seed(0)
+            assert len(ocbo.assemble(o)) == expect[name]
+
+
+@pytest.mark.refsrc
+def test_synthetic_functions_equal_the_reference_bit_for_bit():
+    """ocbo_b200.synth against the reference's own src/synth (imported where it lies)."""
+    from oracle import refshim
+    refshim.install()
+    from synth import continuous_2d as c2, sixd, twod
+    from ocbo_b200 import synth
+    rs = np.random.RandomState(0)
+    for ref_f, our_f, d in ((twod.hartmann4, synth.hartmann4, 4), (twod.hartmann3, synth.hartmann3, 3),
+                            (sixd.hartmann6, synth.hartmann6, 6), (twod.branin, synth.branin, 2)):
+        assert all(ref_f(x) == our_f(x) for x in rs.uniform(size=(500, d)))
+    for ref_set, our_set in ((c2.get_chopped_h42, synth.get_chopped_h42),
+                             (c2.get_chopped_h22, synth.get_chopped_h22),
+                             (c2.get_chopped_h31, synth.get_chopped_h31)):
+        r, o = ref_set(), our_set()
+        assert len(r) == len(o)
+        for a, b in zip(r, o):
+            assert a.name == b.name and [list(x) for x in a.domain] == [list(x) for x in b.domain]
+            assert np.array_equal(np.asarray(a.f_loc, dtype=float), np.asarray(b.f_loc, dtype=float))
+            assert all(a.function(x) == b.function(x) for x in rs.uniform(size=(10, len(a.domain))))
+
+
 def test_strict_methods_raise_like_the_reference():
     from argparse import Namespace
     from ocbo_b200 import ocbo
@@ -79,3 +128,33 @@ def test_continuous_driver_runs_an_option_file(tmp_path):
     res = cts_ocbo.run(argv=['--options', str(f)])
     assert set(res[0]) == {'cmts', 'cmts-pm'}
     assert len(res[0]['cmts'].query_history) == 2 and len(res[0]['cmts'].score_history) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('chop,T', [('chop_h2_2', 9), ('chop_h3_1', 8), ('chop_h4_2', 16)])
+def test_joint_driver_runs_the_chopped_hartmann_task_sets(tmp_path, chop, T):
+    """jointh22 / jointh31 / jointh42.txt: joint task x action GP over the chopped Hartmann sets."""
+    from ocbo_b200 import ocbo
+    f = tmp_path / 'mini.txt'
+    f.write_text('--run_id j_%s\n--trials 1\n--max_capital 3\n--init_capital 2\n--tune_every 1\n'
+                 '--tuning_methods ml\n--methods joint-mts,joint-mei,revi\n--num_eval_pts 250\n'
+                 '--risk_neutral 1\n--%s 1\n' % (chop, chop))
+    res = ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'joint-mts', 'joint-mei'}
+    tl = res[0]['joint-mts'].choice_timeline
+    assert len(tl) == 3 and all(0 <= c < T for c in tl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('extra', ['', '--hp_tune_samps 30\n'])
+def test_continuous_driver_runs_hartmann4(tmp_path, extra):
+    """conth22.txt / conth22_sethps.txt shapes (2 contexts + 2 actions), with and without
+    pre-tuned hyper-parameters."""
+    from ocbo_b200 import cts_ocbo
+    f = tmp_path / 'mini.txt'
+    f.write_text('--run_id c_h4\n--trials 1\n--max_capital 3\n--methods cmts,cmts-pm,pei\n'
+                 '--function hartmann4\n--act_dim 2\n--num_profiles 6\n--eval_ctx_fidel 5\n'
+                 '--eval_act_fidel 5\n' + extra)
+    res = cts_ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'cmts', 'cmts-pm', 'pei'}
+    assert len(res[0]['cmts'].query_history) == 3
