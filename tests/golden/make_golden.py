@@ -26,14 +26,40 @@ def main():
     from strategies.joint_mts import JointMTS
     from strategies.mei import MEI
     from strategies.joint_mei import JointMEI
+    from strategies.agnostic_opt import AgnEI, AgnThompson
+    from strategies.joint_agnostic_opt import JointAgnEI, JointAgnThompson
+    from strategies.random_strat import JointRandom, RandomOpt
     from cstrats.profile_cts import CMTSPM, ContinuousMultiTaskTS, ProfileEI
+    from cstrats.agn_cts import AgnEI as CtsAgnEI, AgnTS as CtsAgnTS
+    from cstrats.rand_cts import RandOpt
     from util.misc_util import assemble_functions
     from synth.continuous_2d import assemble_chopped_1d_functions
     from synth.function_generator import get_easy_mass_functions, get_hard_mass_functions, \
         get_med_mass_functions
     from synth.sixd import hartmann6
 
+    def discrete_functions(cfg):
+        if 'functions' in cfg:
+            return assemble_functions(cfg['functions'])
+        return assemble_chopped_1d_functions(cfg['cts_f'], cfg['num_chops'])
+
     out = {}
+    # baselines: picks only (no tie margins: the CPU host-logic test is their parity gate)
+    base_cls = {'agn-thomp': AgnThompson, 'agn-ei': AgnEI, 'Random': RandomOpt, 'ja-thomp': JointAgnThompson,
+                'ja-ei': JointAgnEI, 'joint-rand': JointRandom}
+    for name, cfg in sc.DISCRETE_BASELINES.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        f_infos = discrete_functions(cfg)
+        out[name] = sc.run_discrete(cfg, base_cls[cfg['kind']], f_infos, sc.discrete_options(cfg, 'dragonfly'))
+        print(name, out[name]['choice_timeline'])
+    for name, cfg in sc.CONTINUOUS_BASELINES.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        cls = {'rand': RandOpt, 'ts': CtsAgnTS, 'ei': CtsAgnEI}[cfg['kind']]
+        out[name] = sc.run_continuous(cfg, cls, hartmann6, [[0, 1] for _ in range(6)],
+                                      sc.continuous_options(cfg, 'dragonfly'))
+        print(name, np.round(out[name]['regret'], 4).tolist())
     for name, cfg in sc.DISCRETE.items():
         np.random.seed(sc.SEED)
         gp_numpy.EuclideanGPFitter._fit_counter = 0

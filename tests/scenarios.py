@@ -25,6 +25,31 @@ DISCRETE = {
     'jointbran-mei': dict(kind='joint-mei', cts_f='branin', num_chops=4, capital=8, init_capital=5,
                           tuning_methods='ml', hp_samples=3, risk_neutral=True),
 }
+# Baselines of the same option files (agnostic_opt.py, joint_agnostic_opt.py, random_strat.py,
+# rand_cts.py): host-logic parity only (tests/test_host_strategies.py) -- same loop, same
+# consumption of the global numpy stream, same picks on the same oracle engine.
+DISCRETE_BASELINES = {
+    'set2d-agn-thomp': dict(kind='agn-thomp', functions='branin,parabaloid,parabaloid', capital=8,
+                            init_capital=5, tuning_methods='ml', hp_samples=3, risk_neutral=False),
+    'set2d-agn-ei': dict(kind='agn-ei', functions='branin,parabaloid,parabaloid', capital=8,
+                         init_capital=5, tuning_methods='ml', hp_samples=3, risk_neutral=False),
+    'set2d-random': dict(kind='Random', functions='branin,parabaloid,parabaloid', capital=8,
+                         init_capital=5, tuning_methods='ml', hp_samples=3, risk_neutral=False),
+    'jointbran-ja-thomp': dict(kind='ja-thomp', cts_f='branin', num_chops=4, capital=6, init_capital=5,
+                               tuning_methods='ml', hp_samples=3, risk_neutral=True),
+    'jointbran-ja-ei': dict(kind='ja-ei', cts_f='branin', num_chops=4, capital=6, init_capital=5,
+                            tuning_methods='ml', hp_samples=3, risk_neutral=True),
+    'jointbran-rand': dict(kind='joint-rand', cts_f='branin', num_chops=4, capital=6, init_capital=5,
+                           tuning_methods='ml', hp_samples=3, risk_neutral=True),
+}
+CONTINUOUS_BASELINES = {
+    'conth42-rand': dict(kind='rand', act_dim=2, capital=5, init_capital=5, num_profiles=10,
+                         profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+    'conth42-agn-ts': dict(kind='ts', act_dim=2, capital=5, init_capital=5, num_profiles=10,
+                           profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+    'conth42-agn-ei': dict(kind='ei', act_dim=2, capital=5, init_capital=5, num_profiles=10,
+                           profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+}
 CONTINUOUS = {
     # conth42.txt: Hartmann-6 with 4 context + 2 action dims
     'conth42-cmts': dict(kind='cmts', act_dim=2, capital=6, init_capital=5, num_profiles=10,
@@ -47,7 +72,7 @@ def continuous_options(cfg, gp_engine):
                      add_max_group_size=6, hp_samples=3, eval_ctx_fidel=cfg['eval_ctx_fidel'],
                      eval_act_fidel=cfg['eval_act_fidel'], score_every=1, cand_size=100,
                      gp_engine=gp_engine, num_profiles=cfg['num_profiles'],
-                     profile_evals=cfg['profile_evals'])
+                     profile_evals=cfg['profile_evals'], agn_evals=100)
 
 
 def run_discrete(cfg, strategy_cls, f_infos, options):

@@ -126,6 +126,37 @@ def test_discrete_host_logic_matches_reference(oracle_engine, name):
     assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('name', sorted(sc.DISCRETE_BASELINES))
+def test_discrete_baselines_match_reference(oracle_engine, name):
+    """agn-thomp / agn-ei / Random / ja-thomp / ja-ei / joint-rand: same picks, points and values
+    as the reference's own classes on the same engine and seed."""
+    from ocbo_b200.strategies import strategies
+    cfg = sc.DISCRETE_BASELINES[name]
+    np.random.seed(sc.SEED)
+    f_infos = _functions(cfg)
+    cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
+    got = sc.run_discrete(cfg, cls, f_infos, sc.discrete_options(cfg, 'b200'))
+    ref = oracle_engine[name]
+    assert got['choice_timeline'] == ref['choice_timeline']
+    assert np.allclose(got['points'], ref['points'], rtol=0, atol=1e-12)
+    assert np.allclose(got['values'], ref['values'], rtol=0, atol=1e-12)
+    assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', sorted(sc.CONTINUOUS_BASELINES))
+def test_continuous_baselines_match_reference(oracle_engine, name):
+    from ocbo_b200 import synth
+    from ocbo_b200.cstrats import cstrats
+    cfg = sc.CONTINUOUS_BASELINES[name]
+    np.random.seed(sc.SEED)
+    cls = [s.impl for s in cstrats if s.name == cfg['kind']][0]
+    got = sc.run_continuous(cfg, cls, synth.hartmann6, [[0, 1] for _ in range(6)],
+                            sc.continuous_options(cfg, 'b200'))
+    ref = oracle_engine[name]
+    assert np.allclose(got['points'], ref['points'], rtol=0, atol=1e-12)
+    assert np.allclose(got['regret'], ref['regret'], rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize('name', sorted(sc.CONTINUOUS))
 def test_continuous_host_logic_matches_reference(oracle_engine, name):
     from ocbo_b200 import synth
@@ -143,8 +174,10 @@ def test_continuous_host_logic_matches_reference(oracle_engine, name):
 def test_registry_and_names():
     from ocbo_b200.cstrats import cstrats
     from ocbo_b200.strategies import strategies
-    assert {s.name for s in strategies} == {'mts', 'joint-mts', 'mei', 'joint-mei'}
-    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm', 'pei'}
+    # the reference's registries minus REVI (src/strategies/__init__.py:13-27, src/cstrats/__init__.py)
+    assert {s.name for s in strategies} == {'mts', 'joint-mts', 'mei', 'joint-mei', 'agn-ei', 'agn-thomp',
+                                            'ja-thomp', 'ja-ei', 'Random', 'joint-rand'}
+    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm', 'pei', 'rand', 'ei', 'ts'}
     for s in strategies:
         assert s.impl.get_opt_method_name() == s.name
     for s in cstrats:

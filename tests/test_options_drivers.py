@@ -113,7 +113,7 @@ def test_discrete_driver_runs_an_option_file(tmp_path):
                  '--methods agn-thomp,mts,random\n--functions branin,parabaloid\n'
                  '--write_dir %s\n' % tmp_path)
     res = ocbo.run(argv=['--options', str(f)])
-    assert len(res) == 2 and set(res[0]) == {'mts'}
+    assert len(res) == 2 and set(res[0]) == {'agn-thomp', 'mts', 'Random'}
     assert len(res[0]['mts'].choice_timeline) == 3
     assert os.path.exists(tmp_path / 'mini' / 'trial_1.pkl')
 
@@ -128,6 +128,29 @@ def test_continuous_driver_runs_an_option_file(tmp_path):
     res = cts_ocbo.run(argv=['--options', str(f)])
     assert set(res[0]) == {'cmts', 'cmts-pm'}
     assert len(res[0]['cmts'].query_history) == 2 and len(res[0]['cmts'].score_history) == 2
+
+
+@pytest.mark.gpu
+def test_every_method_of_the_option_files_but_revi_runs(tmp_path):
+    """set2d / jointbran / conth42 method lists: the MTS family plus the agnostic and random
+    baselines run through the same drivers; REVI is the one method skipped."""
+    from ocbo_b200 import cts_ocbo, ocbo
+    f = tmp_path / 'a.txt'
+    f.write_text('--run_id all_d\n--trials 1\n--max_capital 4\n--tune_every 1\n--tuning_methods ml\n'
+                 '--methods agn-thomp,agn-ei,mts,mei,random\n--functions branin,parabaloid\n')
+    res = ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'agn-thomp', 'agn-ei', 'mts', 'mei', 'Random'}
+    f.write_text('--run_id all_j\n--trials 1\n--max_capital 4\n--init_capital 3\n--tune_every 1\n'
+                 '--tuning_methods ml\n--methods joint-mts,joint-mei,ja-thomp,ja-ei,joint-rand,revi\n'
+                 '--cts_f branin\n--risk_neutral 1\n--num_chops 4\n')
+    res = ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'joint-mts', 'joint-mei', 'ja-thomp', 'ja-ei', 'joint-rand'}
+    assert all(len(h.choice_timeline) == 4 for h in res[0].values())
+    f.write_text('--run_id all_c\n--trials 1\n--max_capital 3\n--methods cmts,cmts-pm,pei,revi,rand\n'
+                 '--function branin\n--act_dim 1\n--num_profiles 6\n--eval_ctx_fidel 5\n--eval_act_fidel 5\n')
+    res = cts_ocbo.run(argv=['--options', str(f)])
+    assert set(res[0]) == {'cmts', 'cmts-pm', 'pei', 'rand'}
+    assert all(len(h.query_history) == 3 for h in res[0].values())
 
 
 @pytest.mark.gpu
