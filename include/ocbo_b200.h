@@ -258,6 +258,16 @@ int ocbo_joint_pick(const double* seg_max, const int32_t* seg_arg, int nseg,
                     int32_t* out_task, int32_t* out_action, double* out_gain,
                     int batch, ocbo_stream_t stream);
 
+/* Knowledge gradient of G x C sets of E lines (REVI):
+ *   kg[c][g] = E[max_i (a_gi + b_cgi Z)] - max_i a_gi,  Z ~ N(0,1),
+ *   a_gi = judge_means[g * ld_means + i],  b_cgi = inter[c * ld_inter + g * E + i] / sqrt(noise + cand_var[c]).
+ * Sort by (slope, intercept), upper envelope with a stack, segment sum in order -- the
+ * reference's knowledge_gradient (src/util/misc_util.py:180-212) as called from REVI's loops
+ * (src/strategies/corr_opt.py:103-119, src/cstrats/postmax_cts.py:147-160).  2 <= E <= 1024. */
+int ocbo_kg(const double* judge_means, int ld_means, const double* inter, int64_t ld_inter,
+            const double* cand_var, double noise, int C, int G, int E, double* kg,
+            ocbo_stream_t stream);
+
 /* FP64 throughput probes used by bench.py to measure the DMMA / DFMA rate the
  * roofline is quoted against (MEASURED_PEAKS.json has no FP64 row).
  * Each thread block runs `iters` dependent-free DMMA.8x8x4 / DFMA chains. */

@@ -43,6 +43,7 @@ _PROTOS = {
     'ocbo_sample': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _I, _L, _VP, _I, _VP]),
     'ocbo_segment_argmax': (_I, [_VP, _I, _I, _L, _VP, _I, _VP, _VP, _I, _VP]),
     'ocbo_joint_pick': (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP]),
+    'ocbo_kg': (_I, [_VP, _I, _VP, _L, _VP, ctypes.c_double, _I, _I, _I, _VP, _VP]),
     'ocbo_probe_dmma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dfma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dgemm_nt': (_I, [_VP, _VP, _VP, _I, _VP]),

@@ -277,3 +277,39 @@ def shared_ei_step(gp, pts_list, best_list=None, cap=None):
     else:
         best = engine._h2d(np.asarray(best_list, dtype=np.float64))
     return _ei_reduce(post, pts_list, best)
+
+
+# ---------------------------------------------------------------------------
+# REVI: knowledge gradient of every candidate over the judgement groups.
+# ---------------------------------------------------------------------------
+def revi_improvements(gp, cand_pts, judge_pts, num_groups, group_size):
+    """improvement[c] = sum_g KG(judge_means[g], cov(c, judge[g]) / sqrt(noise + var_c))
+    (src/strategies/corr_opt.py:92-119, src/cstrats/postmax_cts.py:139-160) for all C
+    candidates in one device pass: V for both point sets, posterior means of the judgement
+    points, the C x (G E) posterior cross-covariance (get_pt_relations, :112-119), the
+    candidates' variances, then ocbo_kg on C x G CTAs.  The sum over groups runs in group
+    order on the host (C x G doubles), like the reference's ``improvement +=``."""
+    core = gp.gp_core
+    if not core.has_posterior():
+        core.build_posterior()
+    post = core._post  # verified factor
+    D = post.D
+    cand = np.asarray(cand_pts, dtype=np.float64).reshape(-1, D)
+    judge = np.asarray(judge_pts, dtype=np.float64).reshape(-1, D)
+    C, G, E = len(cand), int(num_groups), int(group_size)
+    if len(judge) != G * E:
+        raise ValueError('judgement set must hold num_groups * group_size points')
+    with engine.staging(16 * (cand.size + judge.size) + (1 << 16)):
+        Xa, mav, _, _ = engine.upload_points(1, D, [cand])
+        Xb, mbv, _, _ = engine.upload_points(1, D, [judge])
+    Va, Vb = post.solve_cross(Xa, mav), post.solve_cross(Xb, mbv)
+    means_j = post.mean_from_v(Vb, mbv)
+    var_c = torch.empty((1, Xa.shape[1]), dtype=F64, device=Xa.device)
+    engine.call('ocbo_post_var_ei', engine._p(Va), post.n_pad, Va.stride(1), Va.stride(0),
+                engine._p(post.nv), None, 0, engine._p(post.theta), post.theta.stride(0), None,
+                Xa.shape[1], engine._p(mav), engine._p(var_c), var_c.stride(0), None, 0, 1,
+                engine._stream())
+    inter = post.cross_cov(Xa, mav, Va, Xb, mbv, Vb)
+    kg = engine.knowledge_gradients(means_j[0], E, inter[0], var_c[0], gp.get_estimated_noise(),
+                                    C, G, E)
+    return np.cumsum(kg.cpu().numpy(), axis=1)[:, -1]

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libocbo_b200.so')
-SOURCES = ['gemm_kernels.cu', 'gram.cu', 'potrf.cu', 'potrf_diag_reg.cu', 'potrf_diag_blk.cu', 'ladder.cu', 'sampling.cu', 'ei.cu',
+SOURCES = ['gemm_kernels.cu', 'gram.cu', 'potrf.cu', 'potrf_diag_reg.cu', 'potrf_diag_blk.cu', 'ladder.cu', 'sampling.cu', 'ei.cu', 'kg.cu',
            'capi.cu']
 HEADERS = ['common.cuh', 'gemm_core.cuh', 'kernels.h', 'philox.cuh',
            os.path.join('..', '..', 'include', 'ocbo_b200.h')]

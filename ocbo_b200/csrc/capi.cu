@@ -606,6 +606,25 @@ int ocbo_joint_pick(const double* seg_max, const int32_t* seg_arg, int nseg, int
   return 0;
 }
 
+int ocbo_kg(const double* judge_means, int ld_means, const double* inter, int64_t ld_inter,
+            const double* cand_var, double noise, int C, int G, int E, double* kg,
+            ocbo_stream_t stream) {
+  if (!judge_means) return fail_arg(1, "judge_means null");
+  if (!inter) return fail_arg(3, "inter null");
+  if (!cand_var) return fail_arg(5, "cand_var null");
+  if (!(noise >= 0.0)) return fail_arg(6, "noise must be >= 0");
+  if (C <= 0 || C > 65535) return fail_arg(7, "C must be in [1, 65535]");
+  if (G <= 0) return fail_arg(8, "G");
+  if (E < 2 || E > 1024) return fail_arg(9, "E must be in [2, 1024]");
+  if (ld_means < E) return fail_arg(2, "ld_means < E");
+  if (ld_inter < (int64_t)G * E) return fail_arg(4, "ld_inter < G * E");
+  if (!kg) return fail_arg(10, "kg null");
+  CK(launch_kg(judge_means, ld_means, inter, ld_inter, cand_var, noise, C, G, E, kg,
+               (cudaStream_t)stream),
+     "ocbo_kg");
+  return 0;
+}
+
 int ocbo_probe_dmma(double* sink, int blocks, int iters, ocbo_stream_t stream) {
   if (!sink) return fail_arg(1, "sink null");
   CK(launch_probe_dmma(sink, blocks, iters, (cudaStream_t)stream), "ocbo_probe_dmma");

@@ -95,6 +95,9 @@ cudaError_t launch_post_mean(int kind, int dim, const double* Xs, int m, int64_t
                              const double* alpha, int64_t sAlpha, double* mean, int64_t sMean,
                              int batch, cudaStream_t st);
 
+cudaError_t launch_kg(const double* means, int ldm, const double* inter, int64_t ldi,
+                      const double* cand_var, double noise, int C, int G, int E, double* out,
+                      cudaStream_t st);
 cudaError_t launch_philox_normal(double* Z, int m, int S, int ldz, int64_t sZ, uint64_t seed,
                                  const int32_t* trial_ids, int batch, cudaStream_t st);
 cudaError_t launch_sample_rowdot(const double* mean, int64_t sMean, const double* L, int m, int ldl,

@@ -15,6 +15,8 @@ import numpy as np
 from . import synth
 from .cstrats import cstrats
 from .cstrats.cts_opt import cts_opt_args
+from .cstrats.baselines import agn_args
+from .cstrats.postmax_cts import pm_args
 from .cstrats.profile_cts import prof_args
 from .options import get_option_specs, load_options
 from .util import uniform_draw
@@ -35,8 +37,6 @@ ocbo_args = [
     get_option_specs('write_fig', False, False, 'Ignored (no plotting).'),
     get_option_specs('description', False, None, 'Free-text description.'),
     get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
-    get_option_specs('judge_act_size', False, None, 'Ignored (REVI only).'),
-    get_option_specs('judge_ctx_size', False, None, 'Ignored (REVI only).'),
     get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
 ]
 SEED = 100826730
@@ -89,7 +89,8 @@ def run_single(methods, f_info, options):
 
 
 def run(argv=None):
-    options = load_options(ocbo_args + cts_opt_args + prof_args, cmd_line=True, argv=argv)
+    options = load_options(ocbo_args + cts_opt_args + prof_args + pm_args + agn_args, cmd_line=True,
+                           argv=argv)
     if options.set_seed:
         np.random.seed(SEED)
     if options.run_id is None:

@@ -659,6 +659,18 @@ def joint_pick(mx, ag, n_old_seg, T):
     return task, act, gain
 
 
+def knowledge_gradients(judge_means, ld_means, inter, cand_var, noise, C, G, E):
+    """kg[c, g] of REVI (include/ocbo_b200.h, ocbo_kg): ``judge_means`` holds G groups of E
+    values (group stride ``ld_means``), ``inter`` [C_pad, >= G*E] the posterior covariances
+    candidate x judgement point, ``cand_var`` [>= C] the candidates' posterior variances."""
+    out = torch.empty((C, G), dtype=F64, device=inter.device)
+    ld_inter = inter.stride(0) if inter.shape[0] > 1 else inter.shape[1]  # (a 1-row stride is arbitrary)
+    call('ocbo_kg', _p(judge_means), int(ld_means), _p(inter), int(ld_inter), _p(cand_var),
+         float(noise), int(C), int(G), int(E), _p(out), _stream())
+    _count(1)
+    return out
+
+
 def pad_normals(Z_list, mv, m_pad, S):
     """Host normals [(m_b, S)] -> device [B, m_pad, S_pad] (zero padded)."""
     S_pad = S if S <= 8 else pad_to(S, 64)

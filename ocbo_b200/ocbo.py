@@ -42,12 +42,13 @@ docbo_args = [
     get_option_specs('description', False, None, 'Free-text description.'),
     get_option_specs('max_opt_evals', False, 100, 'Candidate actions per task and step.'),
     get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
-    get_option_specs('run_ei_after', False, None, 'Ignored (REVI only).'),
+    get_option_specs('run_ei_after', False, None, 'REVI: switch to round-robin EI after this many steps.'),
     get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
     get_option_specs('chop_h4_2', False, False, 'Hartmann 4 contexts / 2 actions task set.'),
     get_option_specs('chop_h2_2', False, False, 'Hartmann 2 contexts / 2 actions task set.'),
     get_option_specs('chop_h3_1', False, False, 'Hartmann 3 contexts / 1 action task set.'),
-    get_option_specs('num_eval_pts', False, 100, 'Ignored (REVI only).'),
+    get_option_specs('num_eval_pts', False, 100, 'REVI: judgement actions per task.'),
+    get_option_specs('num_candidates', False, 100, 'REVI: candidate actions per task.'),
 ]
 rand_fs_args = [
     get_option_specs('easy_masses', False, 0, 'Easy random mass functions.'),

@@ -4,6 +4,7 @@ drivers (src/ocbo.py:176-177).  The MTS family is the accelerated hot path
 (SURVEY 8a); MEI / joint-MEI are the first "next" row (8f, f2) and share its kernels."""
 from argparse import Namespace
 
+from .corr_opt import REVI
 from .baselines import AgnEI, AgnThompson, JointAgnEI, JointAgnThompson, JointRandom, RandomOpt
 from .joint_mei import JointMEI
 from .joint_mts import JointMTS
@@ -22,4 +23,6 @@ strategies = [
     Namespace(impl=JointAgnEI, name=JointAgnEI.get_opt_method_name()),
     Namespace(impl=RandomOpt, name=RandomOpt.get_opt_method_name()),
     Namespace(impl=JointRandom, name=JointRandom.get_opt_method_name()),
+    # REVI: knowledge gradient over the joint GP
+    Namespace(impl=REVI, name=REVI.get_opt_method_name()),
 ]

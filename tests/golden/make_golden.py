@@ -32,6 +32,10 @@ def main():
     from cstrats.profile_cts import CMTSPM, ContinuousMultiTaskTS, ProfileEI
     from cstrats.agn_cts import AgnEI as CtsAgnEI, AgnTS as CtsAgnTS
     from cstrats.rand_cts import RandOpt
+    if not hasattr(np, 'float'):
+        np.float = float  # numpy >= 1.24 removed the alias misc_util.py:192 uses (REVI only)
+    from strategies.corr_opt import REVI
+    from cstrats.postmax_cts import REVI as CtsREVI
     from util.misc_util import assemble_functions
     from synth.continuous_2d import assemble_chopped_1d_functions
     from synth.function_generator import get_easy_mass_functions, get_hard_mass_functions, \
@@ -46,7 +50,7 @@ def main():
     out = {}
     # baselines: picks only (no tie margins: the CPU host-logic test is their parity gate)
     base_cls = {'agn-thomp': AgnThompson, 'agn-ei': AgnEI, 'Random': RandomOpt, 'ja-thomp': JointAgnThompson,
-                'ja-ei': JointAgnEI, 'joint-rand': JointRandom}
+                'ja-ei': JointAgnEI, 'joint-rand': JointRandom, 'revi': REVI}
     for name, cfg in sc.DISCRETE_BASELINES.items():
         np.random.seed(sc.SEED)
         gp_numpy.EuclideanGPFitter._fit_counter = 0
@@ -56,7 +60,7 @@ def main():
     for name, cfg in sc.CONTINUOUS_BASELINES.items():
         np.random.seed(sc.SEED)
         gp_numpy.EuclideanGPFitter._fit_counter = 0
-        cls = {'rand': RandOpt, 'ts': CtsAgnTS, 'ei': CtsAgnEI}[cfg['kind']]
+        cls = {'rand': RandOpt, 'ts': CtsAgnTS, 'ei': CtsAgnEI, 'revi': CtsREVI}[cfg['kind']]
         out[name] = sc.run_continuous(cfg, cls, hartmann6, [[0, 1] for _ in range(6)],
                                       sc.continuous_options(cfg, 'dragonfly'))
         print(name, np.round(out[name]['regret'], 4).tolist())

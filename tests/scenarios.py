@@ -39,6 +39,10 @@ DISCRETE_BASELINES = {
                                tuning_methods='ml', hp_samples=3, risk_neutral=True),
     'jointbran-ja-ei': dict(kind='ja-ei', cts_f='branin', num_chops=4, capital=6, init_capital=5,
                             tuning_methods='ml', hp_samples=3, risk_neutral=True),
+    # REVI (corr_opt.py): knowledge gradient over the joint GP; EI round robin after run_ei_after
+    'jointbran-revi': dict(kind='revi', cts_f='branin', num_chops=3, capital=5, init_capital=5,
+                           tuning_methods='ml', hp_samples=3, risk_neutral=True, num_eval_pts=30,
+                           num_candidates=12, run_ei_after=4),
     'jointbran-rand': dict(kind='joint-rand', cts_f='branin', num_chops=4, capital=6, init_capital=5,
                            tuning_methods='ml', hp_samples=3, risk_neutral=True),
 }
@@ -47,6 +51,9 @@ CONTINUOUS_BASELINES = {
                          profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
     'conth42-agn-ts': dict(kind='ts', act_dim=2, capital=5, init_capital=5, num_profiles=10,
                            profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+    'conth42-revi': dict(kind='revi', act_dim=2, capital=4, init_capital=40, num_profiles=10,
+                         profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8, cand_size=15,
+                         judge_ctx_size=6, judge_act_size=20),
     'conth42-agn-ei': dict(kind='ei', act_dim=2, capital=5, init_capital=5, num_profiles=10,
                            profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
 }
@@ -64,13 +71,17 @@ CONTINUOUS = {
 def discrete_options(cfg, gp_engine):
     return Namespace(tuning_methods=cfg['tuning_methods'], hp_samples=cfg['hp_samples'],
                      kernel_type='se', risk_neutral=cfg['risk_neutral'], rn_eval_size=50,
-                     gp_engine=gp_engine, tune_every=1, max_opt_evals=100)
+                     gp_engine=gp_engine, tune_every=1, max_opt_evals=100,
+                     num_eval_pts=cfg.get('num_eval_pts', 100), num_candidates=cfg.get('num_candidates', 100),
+                     run_ei_after=cfg.get('run_ei_after', float('inf')))
 
 
 def continuous_options(cfg, gp_engine):
     return Namespace(tuning_methods='ml', tune_every=1, kernel_type='se', use_additive_gp=False,
                      add_max_group_size=6, hp_samples=3, eval_ctx_fidel=cfg['eval_ctx_fidel'],
-                     eval_act_fidel=cfg['eval_act_fidel'], score_every=1, cand_size=100,
+                     eval_act_fidel=cfg['eval_act_fidel'], score_every=1, cand_size=cfg.get('cand_size', 100),
+                     judge_ctx_size=cfg.get('judge_ctx_size', 50), judge_act_size=cfg.get('judge_act_size', 50),
+                     judge_ctx_thresh=None, judge_act_thresh=None,
                      gp_engine=gp_engine, num_profiles=cfg['num_profiles'],
                      profile_evals=cfg['profile_evals'], agn_evals=100)
 

@@ -351,6 +351,47 @@ np.savez(sys.argv[1], **out)
                 assert np.array_equal(ok[good], got[good]), (variant, key)
 
 
+def test_kg_kernel_matches_the_reference_vectors(mods):
+    """ocbo_kg against tests/golden/kg_vectors.json, produced by the reference's OWN
+    knowledge_gradient (make_kg_golden.py): sort, envelope and segment sum follow it operation
+    for operation, only erf / erfc / exp come from another libm (a few ulp)."""
+    import json
+    import os
+    torch, engine = mods['torch'], mods['engine']
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'kg_vectors.json')) as fh:
+        vecs = json.load(fh)
+    assert len(vecs) >= 10
+    one = engine._h2d(np.ones(1))  # cand_var = 1, noise = 0: slopes are divided by exactly 1
+    for v in vecs:
+        a, b = np.asarray(v['a']), np.asarray(v['b'])
+        means = engine._h2d(a[None, :])
+        inter = engine._h2d(b[None, :])
+        kg = engine.knowledge_gradients(means, len(a), inter, one, 0.0, 1, 1, len(a))
+        got = float(kg.cpu().numpy()[0, 0])
+        assert abs(got - v['kg']) <= 1e-13 * max(1.0, abs(v['kg'])), (len(a), got, v['kg'])
+
+
+def test_revi_improvements_match_the_oracle(mods):
+    """The whole REVI scoring pass (V for both point sets, judgement means, posterior
+    cross-covariance, candidate variances, ocbo_kg, sum over groups) against the numpy
+    oracle + the pinned knowledge-gradient restatement."""
+    from oracle import kg
+    from ocbo_b200 import batched
+    X, y, og, bg = both_gps(mods, 17, 60, 3, noise=1e-2, bw=0.3)
+    rs = np.random.RandomState(2)
+    G, E, C = 5, 40, 37
+    cand = rs.uniform(size=(C, 3))
+    judge = rs.uniform(size=(G * E, 3))
+    got = batched.revi_improvements(bg, cand, judge, G, E)
+    means = og.eval(judge)[0].reshape(G, E)
+    inter = og.get_pt_relations(cand, judge)
+    cand_vars = og.eval(cand, include_covar=True)[1].diagonal()
+    ref = kg.revi_improvements(means, inter, cand_vars, og.get_estimated_noise())
+    assert got.shape == ref.shape == (C,)
+    assert rel_err(got, ref) <= TOL
+    assert int(np.argmax(got)) == int(np.argmax(ref))
+
+
 def test_dmma_sampling_path_many_draws(mods):
     """S = 256 draws go through the DMMA L*Z kernel; compare with numpy."""
     torch, engine = mods['torch'], mods['engine']

@@ -102,3 +102,40 @@ def test_reference_strategy_classes_drive_the_b200_engine():
     assert np.max(np.abs(bg.gp_core.alpha - og.gp_core.alpha)) <= 1e-8 * np.max(np.abs(og.gp_core.alpha))
     assert set(bg.get_kernel_hps()) == set(og.get_kernel_hps()) == {'scale', 'lengthscale'}
     assert bg.get_estimated_noise() == og.get_estimated_noise() == 1e-2
+
+
+EXACT_DISCRETE = ['jointbran-revi', 'set2d-agn-ei', 'jointbran-ja-ei', 'set2d-random', 'jointbran-rand']
+EXACT_CONTINUOUS = ['conth42-revi', 'conth42-rand', 'conth42-agn-ei']
+
+
+@pytest.mark.parametrize('name', EXACT_DISCRETE)
+def test_sampling_free_methods_reproduce_reference_selections(golden, name):
+    """REVI (knowledge gradient on the device) and the sampling-free baselines draw no normals:
+    their selections on the B200 engine must equal the reference's own classes' step for step."""
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    from ocbo_b200.strategies import strategies
+    cfg = sc.DISCRETE_BASELINES[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
+    got = sc.run_discrete(cfg, cls, _functions(cfg), sc.discrete_options(cfg, 'b200'))
+    ref = golden[name]
+    assert got['choice_timeline'] == ref['choice_timeline']
+    assert np.allclose(got['points'], ref['points'], rtol=0, atol=1e-12)
+    assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', EXACT_CONTINUOUS)
+def test_sampling_free_continuous_methods_reproduce_reference_selections(golden, name):
+    from ocbo_b200 import synth
+    from ocbo_b200.cstrats import cstrats
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    cfg = sc.CONTINUOUS_BASELINES[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    cls = [s.impl for s in cstrats if s.name == cfg['kind']][0]
+    got = sc.run_continuous(cfg, cls, synth.hartmann6, [[0, 1] for _ in range(6)],
+                            sc.continuous_options(cfg, 'b200'))
+    ref = golden[name]
+    assert np.allclose(got['points'], ref['points'], rtol=0, atol=1e-12)
+    assert np.allclose(got['regret'], ref['regret'], rtol=0, atol=1e-9)

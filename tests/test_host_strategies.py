@@ -84,6 +84,15 @@ def _fake_shared_ei_step(gp, pts_list, best_list=None, cap=None):
     return np.asarray([o[0] for o in out]), np.asarray([o[1] for o in out])
 
 
+def _fake_revi_improvements(gp, cand_pts, judge_pts, num_groups, group_size):
+    from oracle import kg
+    cand, judge = np.asarray(cand_pts), np.asarray(judge_pts)
+    means = gp.eval(judge)[0].reshape(num_groups, group_size)
+    inter = gp.get_pt_relations(cand, judge)
+    cand_vars = gp.eval(cand, include_covar=True)[1].diagonal()
+    return kg.revi_improvements(means, inter, cand_vars, gp.get_estimated_noise())
+
+
 @pytest.fixture
 def oracle_engine(monkeypatch):
     from ocbo_b200 import batched
@@ -96,6 +105,7 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(batched, 'profile_step', _fake_profile_step)
     monkeypatch.setattr(batched, 'mei_step', _fake_mei_step)
     monkeypatch.setattr(batched, 'shared_ei_step', _fake_shared_ei_step)
+    monkeypatch.setattr(batched, 'revi_improvements', _fake_revi_improvements)
     o.EuclideanGPFitter._fit_counter = 0
     with open(GOLDEN) as fh:
         return json.load(fh)
@@ -174,10 +184,10 @@ def test_continuous_host_logic_matches_reference(oracle_engine, name):
 def test_registry_and_names():
     from ocbo_b200.cstrats import cstrats
     from ocbo_b200.strategies import strategies
-    # the reference's registries minus REVI (src/strategies/__init__.py:13-27, src/cstrats/__init__.py)
+    # the reference's registries (src/strategies/__init__.py:13-27, src/cstrats/__init__.py:12-15)
     assert {s.name for s in strategies} == {'mts', 'joint-mts', 'mei', 'joint-mei', 'agn-ei', 'agn-thomp',
-                                            'ja-thomp', 'ja-ei', 'Random', 'joint-rand'}
-    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm', 'pei', 'rand', 'ei', 'ts'}
+                                            'ja-thomp', 'ja-ei', 'Random', 'joint-rand', 'revi'}
+    assert {s.name for s in cstrats} == {'cmts', 'cmts-pm', 'pei', 'rand', 'ei', 'ts', 'revi'}
     for s in strategies:
         assert s.impl.get_opt_method_name() == s.name
     for s in cstrats:

@@ -42,7 +42,8 @@ def test_reference_continuous_option_file_parses_unchanged():
     from ocbo_b200.cstrats.cts_opt import cts_opt_args
     from ocbo_b200.cstrats.profile_cts import prof_args
     from ocbo_b200.options import load_options
-    o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args, cmd_line=True,
+    from ocbo_b200.cstrats.postmax_cts import pm_args
+    o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args + pm_args, cmd_line=True,
                      argv=['--options', os.path.join(REF_OPTS, 'conth42.txt')])
     assert o.run_id == 'conth42' and o.max_capital == 750 and o.act_dim == 2
     assert cts_ocbo.find_function(o.function).name == 'hartmann6'
@@ -64,7 +65,8 @@ def test_every_reference_option_file_parses_and_assembles():
     for name in names:
         path = os.path.join(REF_OPTS, name)
         if name.startswith('cont'):
-            o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args, cmd_line=True,
+            from ocbo_b200.cstrats.postmax_cts import pm_args
+            o = load_options(cts_ocbo.ocbo_args + cts_opt_args + prof_args + pm_args, cmd_line=True,
                              argv=['--options', path])
             f = cts_ocbo.find_function(o.function)
             assert len(f.domain) - o.act_dim >= 1 and 'cmts' in o.methods
@@ -100,7 +102,7 @@ def test_synthetic_functions_equal_the_reference_bit_for_bit():
 def test_strict_methods_raise_like_the_reference():
     from argparse import Namespace
     from ocbo_b200 import ocbo
-    opts = Namespace(methods='revi', tunings=None, strict_methods=True)
+    opts = Namespace(methods='kg-ucb', tunings=None, strict_methods=True)
     with pytest.raises(ValueError, match='Invalid method'):
         ocbo.assemble_methods([], opts)
 
@@ -122,18 +124,18 @@ def test_discrete_driver_runs_an_option_file(tmp_path):
 def test_continuous_driver_runs_an_option_file(tmp_path):
     from ocbo_b200 import cts_ocbo
     f = tmp_path / 'mini.txt'
-    f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--methods cmts,cmts-pm,revi\n'
+    f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--init_capital 40\n--methods cmts,cmts-pm,revi\n'
                  '--function hartmann6\n--act_dim 2\n--num_profiles 5\n--eval_ctx_fidel 4\n'
-                 '--eval_act_fidel 4\n')
+                 '--eval_act_fidel 4\n--judge_ctx_size 5\n--judge_act_size 10\n--cand_size 20\n')
     res = cts_ocbo.run(argv=['--options', str(f)])
-    assert set(res[0]) == {'cmts', 'cmts-pm'}
+    assert set(res[0]) == {'cmts', 'cmts-pm', 'revi'}
     assert len(res[0]['cmts'].query_history) == 2 and len(res[0]['cmts'].score_history) == 2
 
 
 @pytest.mark.gpu
-def test_every_method_of_the_option_files_but_revi_runs(tmp_path):
-    """set2d / jointbran / conth42 method lists: the MTS family plus the agnostic and random
-    baselines run through the same drivers; REVI is the one method skipped."""
+def test_every_method_of_the_option_files_runs(tmp_path):
+    """set2d / jointbran / conth42 method lists: the MTS family, the EI family, the agnostic and
+    random baselines and REVI all run through the same drivers."""
     from ocbo_b200 import cts_ocbo, ocbo
     f = tmp_path / 'a.txt'
     f.write_text('--run_id all_d\n--trials 1\n--max_capital 4\n--tune_every 1\n--tuning_methods ml\n'
@@ -142,14 +144,15 @@ def test_every_method_of_the_option_files_but_revi_runs(tmp_path):
     assert set(res[0]) == {'agn-thomp', 'agn-ei', 'mts', 'mei', 'Random'}
     f.write_text('--run_id all_j\n--trials 1\n--max_capital 4\n--init_capital 3\n--tune_every 1\n'
                  '--tuning_methods ml\n--methods joint-mts,joint-mei,ja-thomp,ja-ei,joint-rand,revi\n'
-                 '--cts_f branin\n--risk_neutral 1\n--num_chops 4\n')
+                 '--cts_f branin\n--risk_neutral 1\n--num_chops 4\n--run_ei_after 3\n--num_eval_pts 40\n')
     res = ocbo.run(argv=['--options', str(f)])
-    assert set(res[0]) == {'joint-mts', 'joint-mei', 'ja-thomp', 'ja-ei', 'joint-rand'}
+    assert set(res[0]) == {'joint-mts', 'joint-mei', 'ja-thomp', 'ja-ei', 'joint-rand', 'revi'}
     assert all(len(h.choice_timeline) == 4 for h in res[0].values())
     f.write_text('--run_id all_c\n--trials 1\n--max_capital 3\n--methods cmts,cmts-pm,pei,revi,rand\n'
-                 '--function branin\n--act_dim 1\n--num_profiles 6\n--eval_ctx_fidel 5\n--eval_act_fidel 5\n')
+                 '--function branin\n--act_dim 1\n--num_profiles 6\n--eval_ctx_fidel 5\n--eval_act_fidel 5\n'
+                 '--judge_act_size 20\n--judge_ctx_size 10\n')
     res = cts_ocbo.run(argv=['--options', str(f)])
-    assert set(res[0]) == {'cmts', 'cmts-pm', 'pei', 'rand'}
+    assert set(res[0]) == {'cmts', 'cmts-pm', 'pei', 'rand', 'revi'}
     assert all(len(h.query_history) == 3 for h in res[0].values())
 
 
@@ -159,11 +162,11 @@ def test_joint_driver_runs_the_chopped_hartmann_task_sets(tmp_path, chop, T):
     """jointh22 / jointh31 / jointh42.txt: joint task x action GP over the chopped Hartmann sets."""
     from ocbo_b200 import ocbo
     f = tmp_path / 'mini.txt'
-    f.write_text('--run_id j_%s\n--trials 1\n--max_capital 3\n--init_capital 2\n--tune_every 1\n'
+    f.write_text('--run_id j_%s\n--trials 1\n--max_capital 3\n--init_capital 6\n--tune_every 1\n'
                  '--tuning_methods ml\n--methods joint-mts,joint-mei,revi\n--num_eval_pts 250\n'
                  '--risk_neutral 1\n--%s 1\n' % (chop, chop))
     res = ocbo.run(argv=['--options', str(f)])
-    assert set(res[0]) == {'joint-mts', 'joint-mei'}
+    assert set(res[0]) == {'joint-mts', 'joint-mei', 'revi'}
     tl = res[0]['joint-mts'].choice_timeline
     assert len(tl) == 3 and all(0 <= c < T for c in tl)
 

@@ -157,3 +157,19 @@ def test_hp_candidates_and_fitter_criteria():
     assert len(f.gpf_core.hp_list) == 3  # 'post_sampling'
     gp = f.get_next_gp()
     assert gp.gp_core.alpha is not None
+
+
+def test_knowledge_gradient_restatement_is_pinned_by_the_reference_function():
+    """oracle.kg.knowledge_gradient == the reference's util.misc_util.knowledge_gradient, bit for
+    bit, on the committed vectors (tests/golden/make_kg_golden.py ran the reference's function)."""
+    import json
+    import os
+    from oracle import kg
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'kg_vectors.json')) as fh:
+        vecs = json.load(fh)
+    assert len(vecs) >= 10
+    for v in vecs:
+        assert kg.knowledge_gradient(np.asarray(v['a']), np.asarray(v['b'])) == v['kg']
+    # closed form for two lines: E[max(0, d + s Z)] with d = a1 - a0 <= 0 shifted, s = |b1 - b0|
+    got = kg.knowledge_gradient(np.asarray([0.0, 0.0]), np.asarray([-1.0, 1.0]))
+    assert abs(got - 2.0 / np.sqrt(2.0 * np.pi)) <= 1e-15
