@@ -42,6 +42,7 @@ __device__ __forceinline__ bool kg_less(double b1, double a1, double b2, double 
 }
 
 __global__ void __launch_bounds__(256) kg_kernel(KgArgs p) {
+  const int NT = blockDim.x;  // NP / 2 threads (32 .. 256): no idle warps at the sort's barriers
   extern __shared__ double sm[];
   const int NP = p.NP, E = p.E;
   double* b = sm;             // NP
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) kg_kernel(KgArgs p) {
   const double denom = sqrt(p.noise + p.cand_var[c]);
   const double* mrow = p.means + (size_t)g * p.ldm;
   const double* irow = p.inter + (size_t)c * p.ldi + (size_t)g * E;
-  for (int i = tid; i < NP; i += 256) {
+  for (int i = tid; i < NP; i += NT) {
     b[i] = (i < E) ? irow[i] / denom : CUDART_INF;
     a[i] = (i < E) ? mrow[i] : CUDART_INF;
   }
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) kg_kernel(KgArgs p) {
   // 1. bitonic sort, ascending by (b, a)
   for (int k = 2; k <= NP; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < NP; t += 256) {
+      for (int t = tid; t < NP; t += NT) {
         const int partner = t ^ j;
         if (partner > t) {
           const bool up = (t & k) == 0;
@@ -80,14 +81,13 @@ __global__ void __launch_bounds__(256) kg_kernel(KgArgs p) {
   }
   // 2. a -= max(a)
   double m = -CUDART_INF;
-  for (int i = tid; i < E; i += 256) m = fmax(m, a[i]);
+  for (int i = tid; i < E; i += NT) m = fmax(m, a[i]);
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((tid & 31) == 0) red[tid >> 5] = m;
   __syncthreads();
   m = red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
-  for (int i = tid; i < E; i += 256) a[i] = a[i] - m;
+  for (int w = 1; w < (NT >> 5); ++w) m = fmax(m, red[w]);
+  for (int i = tid; i < E; i += NT) a[i] = a[i] - m;
   __syncthreads();
   // 3. upper envelope (one thread; the stack never underflows: zs[0] = -inf stops the pops)
   if (tid == 0) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) kg_kernel(KgArgs p) {
   __syncthreads();
   // 4. segment terms in parallel, running sum in order
   const int nseg = nseg_s;
-  for (int s = tid; s < nseg; s += 256) {
+  for (int s = tid; s < nseg; s += NT) {
     const int idx = stack[s];
     const double cdf_dif = __dadd_rn(kg_cdf(zs[s + 1]), -kg_cdf(zs[s]));
     const double pdf_dif = __dadd_rn(kg_pdf(zs[s]), -kg_pdf(zs[s + 1]));
@@ -136,7 +136,9 @@ cudaError_t launch_kg(const double* means, int ldm, const double* inter, int64_t
   while (NP < E) NP <<= 1;
   KgArgs p{means, ldm, inter, ldi, cand_var, noise, out, G, E, NP};
   const int smem = (4 * NP + 1) * 8 + NP * 4;
-  kg_kernel<<<dim3(G, C), 256, smem, st>>>(p);
+  int threads = NP / 2;
+  threads = threads < 32 ? 32 : (threads > 256 ? 256 : threads);
+  kg_kernel<<<dim3(G, C), threads, smem, st>>>(p);
   return counted(cudaGetLastError());
 }
 

@@ -137,6 +137,7 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
     if not cpu:
         return out
     out['bo_loop'] = measure_bo_loop()
+    out['revi'] = measure_revi(cpu_reps)
     lml = measure_lml(gpu_reps, cpu_reps)
     for name, _, cpu_f, _ in jobs:
         out[name]['cpu_steps_per_s'], out[name]['cpu_threads'] = _cpu_best(cpu_f, cpu_reps)
@@ -145,6 +146,42 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
         v['cpu_evals_per_s'] *= 64
     out['lml_evals'] = lml
     return out
+
+
+def measure_revi(cpu_reps=1):
+    """REVI decisions/s: all candidates' knowledge gradients over all
+    judgement groups in one device pass (batched.revi_improvements / ocbo_kg) against the numpy
+    oracle's restatement of the reference's loops (corr_opt.py:92-119, postmax_cts.py:139-160)
+    timed on a SAMPLE of the candidates and scaled (the full CPU decision takes ~10 s)."""
+    import torch
+    from ocbo_b200 import batched, synth
+    from ocbo_b200.gp.gp_interface import make_gp
+    from oracle import gp_numpy as o, kg
+    import gc
+    gc.collect()
+    gc.freeze()  # (see measure(): the driver loops before this leave a large heap behind)
+    rs = np.random.RandomState(3)
+    res = {}
+    for name, n, d, C, G, E in (('jointbran', 160, 2, 1000, 10, 100), ('conth42', 755, 6, 100, 100, 100)):
+        X = rs.uniform(size=(n, d))
+        y = np.asarray([synth.hartmann6(x) for x in X]) if d == 6 else np.asarray([synth.branin(x) for x in X])
+        h = _hp(X, y)
+        gb = make_gp(X, y, 'se', h['scale'], h['bw'], h['noise'], h['mu0'])
+        go = o.make_gp(X, y, 'se', h['scale'], h['bw'], h['noise'], h['mu0'])
+        cand, judge = rs.uniform(size=(C, d)), rs.uniform(size=(G * E, d))
+        tg = _timeit(lambda: batched.revi_improvements(gb, cand, judge, G, E), 10, torch.cuda.synchronize)
+        sample = max(C // 50, 2)
+
+        def cpu():
+            means = go.eval(judge)[0].reshape(G, E)
+            inter = go.get_pt_relations(cand[:sample], judge)
+            cv = go.eval(cand[:sample], include_covar=True)[1].diagonal()
+            return kg.revi_improvements(means, inter, cv, go.get_estimated_noise())
+        tc = _timeit(cpu, cpu_reps, lambda: None) * (C / float(sample))
+        res[name] = {'b200_decisions_per_s': 1 / tg, 'cpu_decisions_per_s': 1 / tc,
+                     'shape': 'n=%d, %d candidates x %d groups x %d judgement points' % (n, C, G, E),
+                     'cpu_sample': '%d of %d candidates, scaled' % (sample, C)}
+    return res
 
 
 def measure_bo_loop(capital=40):
