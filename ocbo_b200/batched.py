@@ -13,7 +13,7 @@ from collections import defaultdict
 import numpy as np
 import torch
 
-from . import engine
+from . import engine, inflight
 from .engine import DevicePosterior, F64
 
 
@@ -69,11 +69,32 @@ def _arena_bytes(B, n_pad, m_pad, D, nseg, with_posterior):
     return 8 * doubles + 4 * B * (nseg + 3) + 16 * engine.Staging.ALIGN
 
 
+def _many(flat):
+    """Lifts ``flat(list_a, list_b, ...) -> list`` (one entry per problem) to a merged pass
+    over several requests (ocbo_b200.inflight): the requests' lists are concatenated, the
+    device pass runs once, the results are split back."""
+    def run_many(requests):
+        sizes = [len(r[0]) for r in requests]
+        joined = [[x for r in requests for x in r[k]] for k in range(len(requests[0]))]
+        res = flat(*joined)
+        out, at = [], 0
+        for sz in sizes:
+            out.append(res[at:at + sz])
+            at += sz
+        return out
+    return run_many
+
+
 def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     """Independent-GP MTS reduction (src/strategies/mts.py:28-43) for all tasks
     at once.  ``gps[f]`` are B200GP objects (only their data and hyper-parameters
     are read: the batched posterior is rebuilt here, as ``get_next_gp`` would).
-    Returns per task (max_prev, best_new_idx_relative, best_new_val)."""
+    Returns per task (max_prev, best_new_idx_relative, best_new_val).  With trials in
+    flight (ocbo_b200.inflight) the tasks of all trials share the device pass."""
+    return inflight.merge('mts', (gps, samp_pts_list, n_old_list, Z_list), _many(_mts_flat))
+
+
+def _mts_flat(gps, samp_pts_list, n_old_list, Z_list):
     T = len(gps)
     groups = defaultdict(list)
     for f, gp in enumerate(gps):
@@ -83,7 +104,7 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
         Xs_ = [c.X_array() for c in cores]
-        ys_ = [c.Y for c in cores]
+        ys_ = [c.Y_array() for c in cores]
         thetas = np.asarray([c.theta() for c in cores])
         pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
         segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
@@ -247,6 +268,10 @@ def _ei_reduce(post, pts_list, best):
 def mei_step(gps, pts_list, best_list):
     """Independent-GP MEI (src/strategies/mei.py:29-46 via misc_util.py:368-385) for all
     tasks at once.  Returns per task (max EI, arg-max index)."""
+    return inflight.merge('mei', (gps, pts_list, best_list), _many(_mei_flat))
+
+
+def _mei_flat(gps, pts_list, best_list):
     T = len(gps)
     groups = defaultdict(list)
     for f, gp in enumerate(gps):
@@ -254,7 +279,7 @@ def mei_step(gps, pts_list, best_list):
     out = [None] * T
     for (D, kind), members in groups.items():
         cores = [gps[f].gp_core for f in members]
-        post = DevicePosterior([c.X_array() for c in cores], [c.Y for c in cores],
+        post = DevicePosterior([c.X_array() for c in cores], [c.Y_array() for c in cores],
                                np.asarray([c.theta() for c in cores]), kind, D).build()
         best = engine._h2d(np.asarray([best_list[f] for f in members], dtype=np.float64))
         pts = [np.asarray(pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]

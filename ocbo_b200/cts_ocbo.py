@@ -9,6 +9,7 @@ import pickle as pkl
 import sys
 import time
 from argparse import Namespace
+from copy import copy
 
 import numpy as np
 
@@ -25,6 +26,9 @@ ocbo_args = [
     get_option_specs('run_id', False, None, 'Unique ID for the run.'),
     get_option_specs('options', False, None, 'Path to options file.'),
     get_option_specs('trials', False, 3, 'Number of trials to run.'),
+    get_option_specs('trials_in_flight', False, 1,
+                     'Trials advanced in lockstep on the GPU, their device passes merged (1 = the '
+                     'sequential loop of the reference).'),
     get_option_specs('max_capital', False, 50, 'Evaluations per trial after the initial ones.'),
     get_option_specs('init_capital', False, 5, 'Initial evaluations.'),
     get_option_specs('methods', False, None, 'Methods to run, comma separated.'),
@@ -40,6 +44,7 @@ ocbo_args = [
     get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
 ]
 SEED = 100826730
+LAST_MERGE_STATS = [None]  # per kind (merged device passes, requests served) of the last in-flight run
 
 
 def find_function(name):
@@ -109,12 +114,24 @@ def run(argv=None):
             with open(os.path.join(created, name), 'wb') as fh:
                 pkl.dump(obj, fh, protocol=2)
     all_results = []
+    width = max(1, int(options.trials_in_flight or 1))
+    if width > 1:
+        # trials advance in lockstep and share their device passes (ocbo_b200/inflight.py)
+        from . import inflight
+        from .gp.gp_interface import B200GPFitter
+
+        def make_trial(t_id):
+            own = [copy(m) for m in methods]  # set_clean() gives every copy its own run state
+            return lambda: run_single(own, f_info, options)
+        all_results, LAST_MERGE_STATS[0] = inflight.run_waves(
+            options.trials, width, SEED, make_trial, [(B200GPFitter, '_fit_counter')])
     for t_id in range(options.trials):
-        results = run_single(methods, f_info, options)
+        results = all_results[t_id] if width > 1 else run_single(methods, f_info, options)
         if created is not None:
             with open(os.path.join(created, 'trial_%d.pkl' % t_id), 'wb') as fh:
                 pkl.dump(results, fh, protocol=2)
-        all_results.append(results)
+        if width == 1:
+            all_results.append(results)
     return all_results
 
 

@@ -102,19 +102,27 @@ class Staging(object):
             cls._done.synchronize()  # the previous step's copy must have left the arena
         self.capacity = cls._host.numel()
         self.host = cls._host
+        self.host_np = cls._host.numpy()
         self.dev = torch.empty(self.capacity, dtype=torch.uint8, device=device())
         _ACTIVE.append(self)
         return self
 
-    def take(self, t):
-        """Stage CPU tensor ``t``; returns its device view or None if it does not fit."""
-        nb = t.numel() * t.element_size()
+    def take(self, arr, dtype):
+        """Stage contiguous ndarray ``arr``; returns its device view (torch ``dtype``) or None
+        if it does not fit.  The host side is a numpy view of the pinned arena (a slice
+        assignment, ~1 us; the torch spelling of the same copy is four tensor ops, ~8 us --
+        a dozen operands per step made that a fifth of a small step's host time)."""
+        nb = arr.nbytes
         off = self.used
         if off + nb > self.capacity:
             return None
         self.used = off + ((nb + self.ALIGN - 1) // self.ALIGN) * self.ALIGN
-        self.host[off:off + nb].view(t.dtype).view(t.shape).copy_(t)
-        return self.dev[off:off + nb].view(t.dtype).view(t.shape)
+        if nb:
+            self.host_np[off:off + nb].view(arr.dtype).reshape(arr.shape)[...] = arr
+        return self._dev_view(off, nb, arr.shape, dtype)
+
+    def _dev_view(self, off, nb, shape, dtype):
+        return self.dev[off:off + nb].view(dtype).view(shape)
 
     def __exit__(self, *exc):
         _ACTIVE.pop()
@@ -139,16 +147,24 @@ class _PlanStaging(Staging):
 
     def __init__(self, plan):
         self.plan, self.capacity, self.used = plan, plan.capacity, 0
-        self.host, self.dev = plan.host, plan.dev
+        self.host, self.dev, self.host_np = plan.host, plan.dev, plan.host_np
 
     def __enter__(self):
         _ACTIVE.append(self)
         return self
 
-    def take(self, t):
-        d = Staging.take(self, t)
+    def take(self, arr, dtype):
+        d = Staging.take(self, arr, dtype)
         if d is None:
             raise RuntimeError('StepPlan arena too small (%d bytes)' % self.capacity)
+        return d
+
+    def _dev_view(self, off, nb, shape, dtype):
+        # same calls, same offsets: the device views of a plan are made once
+        key = (off, shape, dtype)
+        d = self.plan.views.get(key)
+        if d is None:
+            d = self.plan.views[key] = Staging._dev_view(self, off, nb, shape, dtype)
         return d
 
     def __exit__(self, *exc):
@@ -198,6 +214,8 @@ class StepPlan(object):
         self.capacity = ((int(capacity) + 4095) // 4096) * 4096
         self.host = torch.empty(self.capacity, dtype=torch.uint8).pin_memory()
         self.dev = torch.empty(self.capacity, dtype=torch.uint8, device=device())
+        self.host_np = self.host.numpy()
+        self.views = {}
         self.used = 0
         self.graph = None
         self.replays = 0
@@ -233,15 +251,17 @@ class StepPlan(object):
         return [h.numpy() for h in self.outs_host]
 
 
+_NP_OF = {F64: np.float64, I32: np.int32}
+
+
 def _h2d(arr, dtype=F64):
     """Host ndarray -> device tensor (through the active ``staging()`` arena if there is one)."""
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    if t.dtype != dtype:
-        t = t.to(dtype)
+    arr = np.ascontiguousarray(arr, dtype=_NP_OF[dtype])
     if _ACTIVE:
-        d = _ACTIVE[-1].take(t)
+        d = _ACTIVE[-1].take(arr, dtype)
         if d is not None:
             return d
+    t = torch.from_numpy(arr)
     if t.numel() * t.element_size() < (1 << 20):
         # small operands (the option-file shapes): a pageable copy costs ~10 us, pinning
         # a fresh buffer costs a cudaHostAlloc (~100 us) per call
@@ -322,15 +342,29 @@ def chol_with_ladder(assemble, A, invd, info, nv_dev, nv_host):
     return jit
 
 
+def pack_rows(arrs, width, n_pad=None):
+    """Ragged list of (n_b, width) arrays -> zero-padded [B, n_pad, width] + the lengths.
+    One concatenate and one scatter whatever B is: with R trials in flight a pass stages
+    hundreds of small problems, and a Python loop of slice assignments (~3 us each, four
+    per problem) was most of the pass."""
+    B = len(arrs)
+    lens = np.fromiter((len(a) for a in arrs), dtype=np.int64, count=B)
+    if n_pad is None:
+        n_pad = pad_to(max(int(lens.max()) if B else 0, 1))
+    out = np.zeros((B * n_pad, width))
+    total = int(lens.sum())
+    if total:
+        flat = np.concatenate([a for a in arrs if len(a)], axis=0)
+        starts = np.cumsum(lens) - lens
+        dest = np.repeat(np.arange(B) * n_pad - starts, lens) + np.arange(total)
+        out[dest] = flat.reshape(total, width)
+    return out.reshape(B, n_pad, width), lens, n_pad
+
+
 def upload_points(B, D, pts_list):
     """Candidate sets -> (Xs [B, m_pad, D], mv device, mv host, m_pad)."""
-    mv = [len(p) for p in pts_list]
-    m_pad = pad_to(max(mv + [1]))
-    Ph = np.zeros((B, m_pad, D))
-    for b, p in enumerate(pts_list):
-        if mv[b]:
-            Ph[b, :mv[b]] = np.asarray(p, dtype=np.float64).reshape(mv[b], D)
-    return _h2d(Ph), _h2d(np.asarray(mv, dtype=np.int32), I32), mv, m_pad
+    Ph, lens, m_pad = pack_rows([np.asarray(p, dtype=np.float64).reshape(-1, D) for p in pts_list], D)
+    return _h2d(Ph), _h2d(lens.astype(np.int32), I32), lens.tolist(), m_pad
 
 
 class DevicePosterior(object):
@@ -347,15 +381,10 @@ class DevicePosterior(object):
         B, D = len(X_list), int(dim)
         if D < 1 or D > _lib.MAX_DIM:
             raise ValueError('input dimension must be in [1, %d]' % _lib.MAX_DIM)
-        nv_host = [len(y) for y in y_list]
-        n_pad = pad_to(max(nv_host + [1]))
-        Xh = np.zeros((B, n_pad, D))
-        yh = np.zeros((B, n_pad))
-        for b in range(B):
-            nb = nv_host[b]
-            if nb:
-                Xh[b, :nb] = np.asarray(X_list[b], dtype=np.float64).reshape(nb, D)
-                yh[b, :nb] = np.asarray(y_list[b], dtype=np.float64).ravel()
+        Xh, lens, n_pad = pack_rows([np.asarray(x, dtype=np.float64).reshape(-1, D) for x in X_list], D)
+        yh = pack_rows([np.asarray(y, dtype=np.float64).reshape(-1, 1) for y in y_list], 1, n_pad)[0]
+        yh = yh.reshape(B, n_pad)
+        nv_host = lens.tolist()
         theta_host = np.asarray(thetas, dtype=np.float64).reshape(B, 3 + D)
         return (_h2d(Xh), _h2d(yh), _h2d(theta_host), _h2d(np.asarray(nv_host, dtype=np.int32), I32),
                 nv_host)
@@ -674,7 +703,9 @@ def knowledge_gradients(judge_means, ld_means, inter, cand_var, noise, C, G, E):
 def pad_normals(Z_list, mv, m_pad, S):
     """Host normals [(m_b, S)] -> device [B, m_pad, S_pad] (zero padded)."""
     S_pad = S if S <= 8 else pad_to(S, 64)
-    Zh = np.zeros((len(Z_list), m_pad, S_pad))
-    for b, z in enumerate(Z_list):
-        Zh[b, :mv[b], :S] = np.asarray(z, dtype=np.float64).reshape(mv[b], S)
+    Zh = pack_rows([np.asarray(z, dtype=np.float64).reshape(-1, S) for z in Z_list], S, m_pad)[0]
+    if S_pad != S:
+        Zp = np.zeros((len(Z_list), m_pad, S_pad))
+        Zp[:, :, :S] = Zh
+        Zh = Zp
     return _h2d(Zh)

@@ -105,10 +105,19 @@ class B200GPCore(object):
         self.mean_func = mean_func
         self.noise_var = float(noise_var)
         self.dim = kernel.dim
-        self.X = [np.asarray(x, dtype=np.float64).ravel() for x in X]
-        self.Y = [float(y) for y in Y]
+        self._xarr = self._yarr = None
+        if isinstance(X, np.ndarray) and X.ndim == 2 and X.dtype == np.float64 and \
+                isinstance(Y, np.ndarray) and Y.dtype == np.float64:
+            # a fitter hands its own arrays to every GP it draws (one per task and step):
+            # rows as views and the arrays themselves as the caches, nothing is copied
+            # (``add_data_single`` appends to the lists and drops the caches)
+            self.X, self.Y = list(X), Y.tolist()
+            if X.shape[1] == self.dim:
+                self._xarr, self._yarr = X, Y.ravel()
+        else:
+            self.X = [np.asarray(x, dtype=np.float64).ravel() for x in X]
+            self.Y = [float(y) for y in Y]
         self._post_raw = None
-        self._xarr = None
         self.chol_jitter = None
         if build_posterior:
             self.build_posterior()
@@ -164,8 +173,18 @@ class B200GPCore(object):
             self._xarr = np.asarray(self.X, dtype=np.float64).reshape(n, self.dim)
         return self._xarr
 
+    def Y_array(self):
+        """Observations as one (n,) array (cached until a point is added)."""
+        n = len(self.Y)
+        if self._yarr is None or self._yarr.shape[0] != n:
+            self._yarr = np.asarray(self.Y, dtype=np.float64)
+        return self._yarr
+
     def _mu0(self):
-        return float(self.mean_func(np.zeros((1, self.dim)))[0])
+        mf = self.mean_func
+        if type(mf) is ConstMean:
+            return mf.value
+        return float(mf(np.zeros((1, self.dim)))[0])
 
     def theta(self):
         return self.kernel.theta(self.noise_var, self._mu0())
@@ -194,7 +213,7 @@ class B200GPCore(object):
         self.X.append(np.asarray(x, dtype=np.float64).ravel())
         self.Y.append(float(y))
         self._post = None
-        self._xarr = None
+        self._xarr = self._yarr = None
 
     def sample_and_pick(self, to_samp, seg_ptr, num_tasks, _normals=None):
         """One joint posterior sample at ``to_samp`` reduced ON THE DEVICE to the

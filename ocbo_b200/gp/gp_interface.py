@@ -140,7 +140,7 @@ class B200GPFitter(GPFitterWrapper):
         D = self.dim
         kern = make_kernel(self.options.kernel_type, D, theta[0], theta[3:3 + D],
                            getattr(self.options, 'matern_nu', 2.5))
-        return B200GPCore(list(self._X), list(self._Y), kern, ConstMean(theta[2]), theta[1],
+        return B200GPCore(self._X, self._Y, kern, ConstMean(theta[2]), theta[1],
                           build_posterior=build)
 
     def get_next_gp(self):

@@ -15,9 +15,11 @@ theta = (scale, noise_var, mu0, bw_1..bw_D); the box follows SURVEY Appendix A:
 scale in Var(Y)*[0.1, 10], noise in Var(Y)*[5e-3, 2e-1], mu0 in
 median(Y) +- 3 std(Y), bw_j in std(X_j)*[1e-2, 1e2] (log-uniform where positive).
 """
+from collections import defaultdict
+
 import numpy as np
 
-from .. import engine
+from .. import engine, inflight
 from ..engine import DevicePosterior
 
 
@@ -59,10 +61,85 @@ def batched_lml(X, Y, kind, thetas):
     Gram matrix needs the jitter ladder gets it (stable_cholesky), like any posterior.  At
     fixed padded shapes the pass is a replayed CUDA graph (engine.StepPlan): hyper-parameters
     are re-fitted after every evaluation (``tune_every 1`` in all option files), and for the
-    small data sets of set2d / rand6d the pass is a dozen ~10 us kernels."""
+    small data sets of set2d / rand6d the pass is a dozen ~10 us kernels.  With trials in
+    flight (ocbo_b200.inflight) the fits of all trials share the pass (``_lml_group``)."""
     X = np.asarray(X, dtype=np.float64)
+    thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, 3 + X.shape[1])
+    return inflight.merge('lml', (X, np.asarray(Y, dtype=np.float64).ravel(), int(kind), thetas),
+                          _lml_many)
+
+
+def _lml_many(jobs):
+    """Merged LML pass: jobs (X, Y, kind, thetas) with the same kernel kind, input dimension
+    and candidate count form one batch of sum(B_j) problems."""
+    out = [None] * len(jobs)
+    groups = defaultdict(list)
+    for j, (X, Y, kind, thetas) in enumerate(jobs):
+        groups[(kind, X.shape[1], len(thetas))].append(j)
+    for (kind, D, B), members in groups.items():
+        if len(members) == 1:
+            out[members[0]] = _lml_single(*jobs[members[0]])
+            continue
+        # factor + pristine copy + workspace: ~3 n_pad^2 doubles per problem in HBM
+        n_pad = engine.pad_to(max(len(jobs[j][1]) for j in members))
+        chunk = max(1, int(MERGED_LML_BYTES // (24 * B * n_pad * n_pad)))
+        for c0 in range(0, len(members), chunk):
+            part = members[c0:c0 + chunk]
+            if len(part) == 1:
+                out[part[0]] = _lml_single(*jobs[part[0]])
+                continue
+            for j, lml in zip(part, _lml_group([jobs[j] for j in part], kind, D, B)):
+                out[j] = (lml, None)
+    return out
+
+
+MERGED_LML_BYTES = 32 << 30  # HBM budget of one merged LML pass (180 GB per B200)
+
+
+def _lml_group(jobs, kind, D, B):
+    """J data sets x B candidates each as ONE batch of J*B posteriors.  The data sets are
+    uploaded once each; the device replicates them per candidate (the C ABI addresses a batch
+    through ONE stride, so "stride 0 inside groups of B" is a copy -- J*B*n_pad*(D+1) doubles,
+    device to device)."""
+    J = len(jobs)
+    Xs, Ys = [j[0] for j in jobs], [j[1] for j in jobs]
+    thetas = np.concatenate([j[3] for j in jobs], axis=0)
+
+    def stage():
+        Xd, yd, _, nv, nv_host = DevicePosterior.pack(Xs, Ys, thetas[:J], D)
+        return Xd, yd, engine._h2d(thetas), nv, nv_host
+
+    def posterior(st):
+        Xd, yd, th, nv, nv_host = st
+        return DevicePosterior.from_device(Xd.repeat_interleave(B, dim=0), yd.repeat_interleave(B, dim=0),
+                                           th, nv.repeat_interleave(B),
+                                           [n for n in nv_host for _ in range(B)], kind, D)
+
+    n_pad = engine.pad_to(max([len(y) for y in Ys] + [1]))
+    if engine.graphs_enabled():
+        plan = engine.StepPlan.get(('lml-group', kind, D, J, B, n_pad),
+                                   8 * (J * (n_pad * (D + 1) + 3 + D) + thetas.size) + 4 * J
+                                   + 16 * engine.Staging.ALIGN)
+        with plan.staging():
+            st = stage()
+
+        def body(st_, ext):
+            post = posterior(st_)
+            pend = post.build_device_ladder(engine.GRAPH_SPEC_RUNGS)
+            return [post.lml, pend.info]
+
+        lml, info = plan.run(st, [], body)
+        if not (info > 0).any():
+            return list(np.array(lml).reshape(J, B))
+    with engine.staging(16 * sum(x.size for x in Xs) + 8 * thetas.size + 16 * J * n_pad + (1 << 16)):
+        st = stage()
+    post = posterior(st)
+    post.build(need_alpha=False)
+    return list(post.lml.cpu().numpy().reshape(J, B))
+
+
+def _lml_single(X, Y, kind, thetas):
     n, D = X.shape
-    thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, 3 + D)
     B = len(thetas)
 
     def stage():

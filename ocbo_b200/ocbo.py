@@ -14,7 +14,7 @@ reference (:187).  Plotting is out of scope.
 import os
 import pickle as pkl
 import sys
-from copy import deepcopy
+from copy import copy, deepcopy
 
 import numpy as np
 
@@ -27,6 +27,9 @@ docbo_args = [
     get_option_specs('run_id', False, None, 'Unique ID for the run.'),
     get_option_specs('options', False, None, 'Path to options file.'),
     get_option_specs('trials', False, 10, 'Number of trials to run.'),
+    get_option_specs('trials_in_flight', False, 1,
+                     'Trials advanced in lockstep on the GPU, their device passes merged (1 = the '
+                     'sequential loop of the reference).'),
     get_option_specs('max_capital', False, 50, 'Evaluations per trial after the initial ones.'),
     get_option_specs('init_capital', False, 5, 'Initial evaluations per task.'),
     get_option_specs('methods', False, None, 'Methods to run, comma separated.'),
@@ -58,6 +61,7 @@ rand_fs_args = [
     get_option_specs('massf_dim', False, 2, 'Dimension of the mass functions.'),
 ]
 SEED = 100826730
+LAST_MERGE_STATS = [None]  # per kind (merged device passes, requests served) of the last in-flight run
 
 
 def assemble(options):
@@ -142,12 +146,24 @@ def run(argv=None):
             with open(os.path.join(created, name), 'wb') as fh:
                 pkl.dump(obj, fh, protocol=2)
     all_results = []
+    width = max(1, int(options.trials_in_flight or 1))
+    if width > 1:
+        # trials advance in lockstep and share their device passes (ocbo_b200/inflight.py)
+        from . import inflight
+        from .gp.gp_interface import B200GPFitter
+
+        def make_trial(t_id):
+            own = [copy(m) for m in methods]  # set_clean() gives every copy its own run state
+            return lambda: run_single(own, f_infos, options)
+        all_results, LAST_MERGE_STATS[0] = inflight.run_waves(
+            options.trials, width, SEED, make_trial, [(B200GPFitter, '_fit_counter')])
     for t_id in range(options.trials):
-        results = run_single(methods, f_infos, options)
+        results = all_results[t_id] if width > 1 else run_single(methods, f_infos, options)
         if created is not None:
             with open(os.path.join(created, 'trial_%d.pkl' % t_id), 'wb') as fh:
                 pkl.dump(results, fh, protocol=2)
-        all_results.append(results)
+        if width == 1:
+            all_results.append(results)
     return all_results
 
 

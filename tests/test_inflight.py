@@ -1,0 +1,229 @@
+"""Trials in flight (ocbo_b200/inflight.py): the lockstep scheduler on the CPU.  A trial run
+in a pool must see exactly what it would see alone -- its own numpy stream, its own
+criterion counter, its own results -- while the requests of all trials reach the merged
+pass together."""
+import os
+
+import numpy as np
+import pytest
+
+from ocbo_b200 import inflight
+from tests import scenarios as sc
+
+
+class _Counter(object):
+    value = 0
+
+
+def _toy_trial(steps, log):
+    def run_many(payloads):
+        log.append(len(payloads))
+        return [float(np.sum(p)) for p in payloads]
+
+    def trial():
+        acc = []
+        for _ in range(steps):
+            x = np.random.uniform(size=3)
+            _Counter.value += 1
+            acc.append(inflight.merge('sum', x, run_many) + _Counter.value)
+            acc.append(float(np.random.normal()))
+        return acc
+    return trial
+
+
+def test_pool_isolates_streams_and_merges_requests():
+    seeds = [11, 12, 13, 14]
+    states = [np.random.RandomState(s).get_state() for s in seeds]
+    alone = []
+    for st in states:
+        np.random.set_state(st)
+        _Counter.value = 0
+        alone.append(_toy_trial(5, [])())
+    np.random.seed(99)
+    before = np.random.get_state()
+    _Counter.value = 0
+    log = []
+    pool = inflight.TrialPool([(_Counter, 'value')])
+    got = pool.run([_toy_trial(5, log) for _ in seeds], states)
+    assert got == alone
+    assert log == [4] * 5 and pool.stats == {'sum': (5, 20)}
+    # the caller's own stream and globals are untouched
+    after = np.random.get_state()
+    assert before[0] == after[0] and np.array_equal(before[1], after[1]) and before[2:] == after[2:]
+    assert _Counter.value == 0
+
+
+def test_pool_handles_trials_of_different_lengths_and_kinds():
+    log = []
+
+    def run_a(payloads):
+        log.append(('a', len(payloads)))
+        return [p + 1 for p in payloads]
+
+    def run_b(payloads):
+        log.append(('b', len(payloads)))
+        return [p * 2 for p in payloads]
+
+    def trial(k):
+        def f():
+            v = k
+            for i in range(k + 1):
+                v = inflight.merge('a', v, run_a)
+                if i % 2:
+                    v = inflight.merge('b', v, run_b)
+            return v
+        return f
+    states = [np.random.RandomState(i).get_state() for i in range(3)]
+    got = inflight.TrialPool().run([trial(k) for k in range(3)], states)
+    want = [inflight.merge('a', 0, run_a), None, None]  # outside a pool: direct call
+    for k in (1, 2):
+        want[k] = trial(k)()
+    assert got == want
+    assert ('a', 3) in log  # the first request of all three trials ran as one pass
+
+
+def test_errors_propagate():
+    def bad_pass(payloads):
+        raise ValueError('no device')
+
+    def t_bad():
+        return inflight.merge('x', 1, bad_pass)
+
+    def t_raises():
+        raise KeyError('trial bug')
+    st = [np.random.RandomState(0).get_state()] * 2
+    with pytest.raises(ValueError, match='no device'):
+        inflight.TrialPool().run([t_bad, t_bad], st)
+    with pytest.raises(KeyError):
+        inflight.TrialPool().run([t_raises, lambda: 3], st)
+    assert not inflight.in_flight()
+
+
+def test_trial_states_and_waves():
+    np.random.seed(5)
+    st = inflight.trial_rng_states(3, 100)
+    now = np.random.get_state()
+    assert np.array_equal(st[0][1], now[1]) and st[0][2] == now[2]
+    assert np.array_equal(st[2][1], np.random.RandomState(102).get_state()[1])
+    res, stats = inflight.run_waves(5, 2, 7, lambda t: (lambda: (t, float(np.random.uniform()))))
+    assert [r[0] for r in res] == [0, 1, 2, 3, 4]
+    assert res[3][1] == float(np.random.RandomState(10).uniform())
+
+
+@pytest.mark.parametrize('name', ['set2d', 'rand6d'])
+def test_mts_trials_in_flight_equal_the_trials_alone(monkeypatch, name):
+    """The MTS host mirror on the numpy oracle engine (as in test_host_strategies): three trials
+    in flight -- their decisions merged into one ``_mts_flat`` call per step -- reproduce the three
+    trials run one by one from the same stream states."""
+    from ocbo_b200 import batched, synth
+    from ocbo_b200.strategies import multi_opt, strategies
+    from oracle import gp_numpy as o
+    from tests.test_host_strategies import _Fitter, _fake_mts_step
+    monkeypatch.setattr(multi_opt, 'get_gp_fitter', lambda engine, x, y, opts: _Fitter(x, y, opts))
+    sizes = []
+
+    def flat(gps, pts, n_old, Z):
+        sizes.append(len(gps))
+        return _fake_mts_step(gps, pts, n_old, Z)
+    monkeypatch.setattr(batched, '_mts_flat', flat)
+    cfg = dict(sc.DISCRETE[name], capital=4)
+    np.random.seed(sc.SEED)
+    if 'functions' in cfg:
+        f_infos = synth.assemble_functions(cfg['functions'])
+    else:
+        f_infos = synth.random_mass_functions(*cfg['masses'], cfg['massf_dim'])
+    cls = [s.impl for s in strategies if s.name == 'mts'][0]
+    opts = sc.discrete_options(cfg, 'b200')
+    states = [np.random.RandomState(40 + t).get_state() for t in range(3)]
+    alone = []
+    for st in states:
+        np.random.set_state(st)
+        o.EuclideanGPFitter._fit_counter = 0
+        alone.append(sc.run_discrete(cfg, cls, f_infos, opts))
+    T = len(f_infos)
+    assert sizes == [T] * (3 * cfg['capital'])
+    del sizes[:]
+    o.EuclideanGPFitter._fit_counter = 0
+    pool = inflight.TrialPool([(o.EuclideanGPFitter, '_fit_counter')])
+    got = pool.run([lambda: sc.run_discrete(cfg, cls, f_infos, opts)] * 3, states)
+    assert got == alone
+    assert sizes == [3 * T] * cfg['capital']
+
+
+def test_pack_rows_pads_ragged_inputs():
+    """Staging of many small problems: one concatenate + one scatter, same layout as the loop."""
+    from ocbo_b200 import engine
+    rs = np.random.RandomState(0)
+    arrs = [rs.uniform(size=(n, 3)) for n in (5, 0, 130, 1, 77)]
+    out, lens, n_pad = engine.pack_rows(arrs, 3)
+    assert n_pad == 256 and lens.tolist() == [5, 0, 130, 1, 77] and out.shape == (5, 256, 3)
+    for b, a in enumerate(arrs):
+        assert np.array_equal(out[b, :len(a)], a) and not out[b, len(a):].any()
+    out1, _, n1 = engine.pack_rows([np.zeros((0, 2))], 2)
+    assert out1.shape == (1, 128, 2) and n1 == 128 and not out1.any()
+    out2 = engine.pack_rows([a[:, :1] for a in arrs], 1, 384)[0]
+    assert out2.shape == (5, 384, 1) and np.array_equal(out2[2, :130, 0], arrs[2][:, 0])
+
+
+def _timeline(hist, names):
+    pts = {n: [[float(v) for v in np.ravel(q.pt)] for q in hist.query_history[n]] for n in names}
+    return [int(c) for c in hist.choice_timeline], pts, [float(v) for v in hist.total_best]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('methods,tuning', [('mts', 'ml'), ('mts,mei', 'ml-post_sampling')])
+def test_discrete_driver_in_flight_equals_the_trials_alone(tmp_path, methods, tuning):
+    """``--trials_in_flight 3`` through the option-file driver on the B200 engine: every trial's
+    choices, points and values are those of the same trial run alone from the same stream state
+    (merged MTS / MEI / LML passes give each problem the bits it gets in its own batch)."""
+    from ocbo_b200 import ocbo
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    f = tmp_path / 'fl.txt'
+    f.write_text('--run_id fl\n--trials 3\n--max_capital 6\n--tune_every 1\n--tuning_methods %s\n'
+                 '--hp_samples 3\n--methods %s\n--functions branin,parabaloid,parabaloid\n'
+                 '--write_dir %s\n' % (tuning, methods, tmp_path))
+    argv = ['--options', str(f)]
+    B200GPFitter._fit_counter = 0
+    got = ocbo.run(argv=argv + ['--trials_in_flight', '3'])
+    stats = ocbo.LAST_MERGE_STATS[0]
+    assert os.path.exists(tmp_path / 'fl' / 'trial_2.pkl')
+    n_methods = len(methods.split(','))
+    assert stats['mts'] == (6, 18)                      # one merged decision per step for the 3 trials
+    assert stats['lml'][1] == 3 * n_methods * (3 + 6)   # 3 initial fits + one refit per step, per trial
+    assert stats['lml'][0] == n_methods * (3 + 6)
+    # the same trials one by one, from the same states
+    from ocbo_b200.options import load_options
+    from ocbo_b200.strategies.multi_opt import multi_opt_args
+    options = load_options(ocbo.docbo_args + multi_opt_args + ocbo.rand_fs_args, cmd_line=True, argv=argv)
+    np.random.seed(ocbo.SEED)
+    f_infos = ocbo.assemble(options)
+    meths = ocbo.assemble_methods(f_infos, options)
+    names = [fi.name for fi in f_infos]
+    for t, st in enumerate(inflight.trial_rng_states(3, ocbo.SEED)):
+        np.random.set_state(st)
+        B200GPFitter._fit_counter = 0
+        alone = ocbo.run_single(meths, f_infos, options)
+        for key in alone:
+            assert _timeline(got[t][key], names) == _timeline(alone[key], names), (t, key)
+
+
+@pytest.mark.gpu
+def test_continuous_driver_in_flight(tmp_path):
+    """cts_ocbo with two trials in flight: only the hyper-parameter fits merge (the profile step
+    shares ONE posterior over its 50 contexts and stays per trial); results equal the trials alone."""
+    from ocbo_b200 import cts_ocbo
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    f = tmp_path / 'cfl.txt'
+    f.write_text('--run_id cfl\n--trials 2\n--max_capital 3\n--init_capital 30\n--methods cmts\n'
+                 '--function hartmann6\n--act_dim 2\n--num_profiles 5\n--eval_ctx_fidel 4\n'
+                 '--eval_act_fidel 4\n')
+    argv = ['--options', str(f)]
+    B200GPFitter._fit_counter = 0
+    got = cts_ocbo.run(argv=argv + ['--trials_in_flight', '2'])
+    assert cts_ocbo.LAST_MERGE_STATS[0]['lml'][1] == 2 * cts_ocbo.LAST_MERGE_STATS[0]['lml'][0]
+    B200GPFitter._fit_counter = 0
+    alone0 = cts_ocbo.run(argv=argv + ['--trials', '1'])
+    a = [np.ravel(q.pt).tolist() + [q.reward] for q in got[0]['cmts'].query_history]
+    b = [np.ravel(q.pt).tolist() + [q.reward] for q in alone0[0]['cmts'].query_history]
+    assert a == b
+    assert len(got[1]['cmts'].query_history) == 3

@@ -134,6 +134,13 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
     # call and would steal the core that launches the next device step
     for name, gpu_f, _, shape in jobs:
         out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_f, gpu_reps, sync), 'shape': shape}
+    # the same decisions with R independent trials in flight: the R x T problems share ONE device
+    # pass (ocbo_b200/inflight.py; aggregate decisions/s over the R trials)
+    from tests.tools import bench_inflight
+    for name, R in (('set2d', 64), ('rand6d', 16)):
+        step = bench_inflight.make_step(name, R, np.random.RandomState(5))
+        out[name]['b200_steps_per_s_in_flight'] = R / _timeit(step, max(gpu_reps // 2, 3), sync)
+        out[name]['trials_in_flight'] = R
     if not cpu:
         return out
     out['bo_loop'] = measure_bo_loop()
@@ -184,11 +191,14 @@ def measure_revi(cpu_reps=1):
     return res
 
 
-def measure_bo_loop(capital=40):
+def measure_bo_loop(capital=40, in_flight=(8, 32)):
     """Whole BO iterations/s through the drivers that read the reference's option files
     (ocbo_b200.ocbo / cts_ocbo): hyper-parameter re-fit (64-candidate LML pass) + posterior draw
-    + decision + objective evaluation + bookkeeping every iteration, one method, one trial.
-    Device-side only: the reference's own loop needs Dragonfly."""
+    + decision + objective evaluation + bookkeeping every iteration, one method, one trial -- and,
+    for the independent-GP files, with R trials in flight (``--trials R --trials_in_flight R``:
+    the trials' decisions and hyper-parameter fits share their device passes, ocbo_b200/inflight.py;
+    aggregate iterations/s over the R trials).  Device-side only: the reference's own loop needs
+    Dragonfly."""
     import tempfile
     import torch
     from tests.tools.profile_driver import OPTS
@@ -202,13 +212,21 @@ def measure_bo_loop(capital=40):
             path = os.path.join(tmp, 'o.txt')
             with open(path, 'w') as fh:
                 fh.write(text % capital)
-            drv.run(argv=['--options', path])  # warm-up: step plans, kernels
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            drv.run(argv=['--options', path])
-            torch.cuda.synchronize()
-            res[name] = {'b200_iterations_per_s': capital / (time.perf_counter() - t0),
+
+            def timed(extra):
+                argv = ['--options', path] + extra
+                drv.run(argv=argv)  # warm-up: step plans, kernels
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                drv.run(argv=argv)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            res[name] = {'b200_iterations_per_s': capital / timed([]),
                          'iterations': capital, 'what': text.replace('\n', ' ').strip() % capital}
+            if name in ('set2d', 'rand6d'):
+                for R in in_flight:
+                    dt = timed(['--trials', str(R), '--trials_in_flight', str(R)])
+                    res[name]['b200_iterations_per_s_%d_in_flight' % R] = R * capital / dt
     return res
 
 
