@@ -100,11 +100,16 @@ def run(argv=None):
         np.random.seed(SEED)
     if options.run_id is None:
         raise ValueError('run_id not specified.')
+    # One process per GPU under a launcher (torchrun): trial t runs on rank t mod W, no collective
+    # inside a trial, ONE gather of the per-trial results; rank 0 writes the pickles.  Every rank
+    # assembles the same functions and methods from the same seed (``set_seed``).
+    from . import dist as _dist
+    rank, world_size = _dist.init_from_env()
     rand_state = np.random.get_state()
     f_info = find_function(options.function)
     methods = assemble_methods(f_info, options)
     created = None
-    if options.write_dir is not None:
+    if options.write_dir is not None and rank == 0:
         created = os.path.join(options.write_dir, options.run_id)
         if os.path.isdir(created):
             raise ValueError('Run ID already exists: %s' % options.run_id)
@@ -113,25 +118,30 @@ def run(argv=None):
                           ('eval_set.pkl', methods[0].get_eval_set())):
             with open(os.path.join(created, name), 'wb') as fh:
                 pkl.dump(obj, fh, protocol=2)
-    all_results = []
     width = max(1, int(options.trials_in_flight or 1))
-    if width > 1:
-        # trials advance in lockstep and share their device passes (ocbo_b200/inflight.py)
+    if width > 1 or world_size > 1:
+        # trials advance in lockstep and share their device passes (ocbo_b200/inflight.py);
+        # their numpy streams are keyed by trial, so the shard a rank runs does not matter
         from . import inflight
         from .gp.gp_interface import B200GPFitter
 
         def make_trial(t_id):
             own = [copy(m) for m in methods]  # set_clean() gives every copy its own run state
             return lambda: run_single(own, f_info, options)
-        all_results, LAST_MERGE_STATS[0] = inflight.run_waves(
-            options.trials, width, SEED, make_trial, [(B200GPFitter, '_fit_counter')])
+        mine = _dist.shard_trials(options.trials, rank, world_size)
+        local, LAST_MERGE_STATS[0] = inflight.run_waves(
+            options.trials, width, SEED, make_trial, [(B200GPFitter, '_fit_counter')], trial_ids=mine)
+        all_results = _dist.gather_trials(local, mine, options.trials)
+        if all_results is None:
+            return None  # not rank 0
+    else:
+        all_results = []
     for t_id in range(options.trials):
-        results = all_results[t_id] if width > 1 else run_single(methods, f_info, options)
+        if t_id == len(all_results):
+            all_results.append(run_single(methods, f_info, options))  # the reference's sequential loop
         if created is not None:
             with open(os.path.join(created, 'trial_%d.pkl' % t_id), 'wb') as fh:
-                pkl.dump(results, fh, protocol=2)
-        if width == 1:
-            all_results.append(results)
+                pkl.dump(all_results[t_id], fh, protocol=2)
     return all_results
 
 

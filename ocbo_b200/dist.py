@@ -13,6 +13,36 @@ def world():
     return 0, 1
 
 
+def init_from_env():
+    """Join the process group a launcher (torchrun) described in the environment, one process
+    per GPU; a no-op for a plain ``python`` run.  Returns (rank, world size)."""
+    import os
+    if dist.is_available() and not dist.is_initialized() and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl' if cuda else 'gloo')
+    return world()
+
+
+def gather_trials(local, trial_ids, num_trials):
+    """Per-trial result objects of every rank -> list indexed by global trial id on rank 0
+    (None elsewhere).  The one collective of a sharded driver run."""
+    rank, W = world()
+    if W == 1:
+        parts = [list(zip(trial_ids, local))]
+    else:
+        parts = [None] * W if rank == 0 else None
+        dist.gather_object(list(zip(trial_ids, local)), parts, dst=0)
+        if rank != 0:
+            return None
+    out = [None] * int(num_trials)
+    for part in parts:
+        for t, res in part:
+            out[t] = res
+    return out
+
+
 def shard_trials(num_trials, rank=None, world_size=None):
     """Trial r lives on rank r mod W; results are keyed by trial, so a sweep's
     output does not depend on the world size (trial-indexed Philox)."""

@@ -201,14 +201,17 @@ def trial_rng_states(num_trials, seed):
     return states
 
 
-def run_waves(num_trials, width, seed, make_trial, trial_globals=()):
+def run_waves(num_trials, width, seed, make_trial, trial_globals=(), trial_ids=None):
     """``num_trials`` trials, ``width`` of them in flight at a time (they all take the same
     number of steps, so waves lose nothing).  ``make_trial(t)`` returns trial t's callable.
-    Returns (results in trial order, per-kind (merged passes, requests served))."""
+    ``trial_ids`` restricts the run to a rank's shard (ocbo_b200.dist.shard_trials): a trial's
+    stream is keyed by its GLOBAL id, so results do not depend on the world size.
+    Returns (results in the order of the ids, per-kind (merged passes, requests served))."""
     states = trial_rng_states(num_trials, seed)
+    ids_all = list(range(int(num_trials))) if trial_ids is None else list(trial_ids)
     results, stats = [], {}
-    for w0 in range(0, int(num_trials), int(width)):
-        ids = range(w0, min(w0 + int(width), int(num_trials)))
+    for w0 in range(0, len(ids_all), int(width)):
+        ids = ids_all[w0:w0 + int(width)]
         pool = TrialPool(trial_globals)
         results += pool.run([make_trial(t) for t in ids], [states[t] for t in ids])
         for k, (a, b) in pool.stats.items():

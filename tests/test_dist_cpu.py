@@ -59,3 +59,65 @@ def test_single_process_gather_and_sharding():
     t, a, g = gather_picks([2, 0, 1], np.arange(6).reshape(3, 2), np.arange(6).reshape(3, 2) + 10,
                            np.arange(6.0).reshape(3, 2), 3, device=torch.device('cpu'))
     assert t.tolist() == [[2, 3], [4, 5], [0, 1]] and a[0].tolist() == [12, 13]
+
+
+# ---------------------------------------------------------------------------
+# option-file driver, trials sharded over two ranks (gloo), numpy oracle engine
+# ---------------------------------------------------------------------------
+def _oracle_engine():
+    """What tests/test_host_strategies.py's fixture does, without pytest (spawned workers)."""
+    from ocbo_b200 import batched
+    from ocbo_b200.strategies import multi_opt
+    from oracle import gp_numpy as o
+    from tests.test_host_strategies import _Fitter, _fake_mts_step
+    multi_opt.get_gp_fitter = lambda engine, x, y, opts: _Fitter(x, y, opts)
+    batched._mts_flat = _fake_mts_step
+    o.EuclideanGPFitter._fit_counter = 0  # 'ml' only below: the criterion never alternates
+
+
+_DRIVER_ARGV = ['--run_id', 'shard', '--trials', '5', '--max_capital', '3', '--tune_every', '1',
+                '--tuning_methods', 'ml', '--methods', 'mts', '--functions', 'branin,parabaloid',
+                '--trials_in_flight', '2']
+
+
+def _summary(results):
+    return [[int(c) for c in r['mts'].choice_timeline] + [float(v) for v in r['mts'].total_best]
+            for r in results]
+
+
+def _driver_worker(rank, world, port, out_path, write_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    _oracle_engine()
+    from ocbo_b200 import ocbo
+    res = ocbo.run(argv=_DRIVER_ARGV + ['--write_dir', write_dir])
+    if rank == 0:
+        import json
+        with open(out_path, 'w') as fh:
+            json.dump(_summary(res), fh)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_driver_shards_trials_over_two_ranks(tmp_path, monkeypatch):
+    """``torchrun -m ocbo_b200.ocbo`` semantics on CPU: 5 trials, 2 in flight per rank, world size 2;
+    rank 0 gathers every trial and writes trial_%d.pkl; the results equal the single-process run
+    (a trial's stream is keyed by its global id)."""
+    import json
+    out = str(tmp_path / 'w2.json')
+    mp.spawn(_driver_worker, args=(2, _free_port(), out, str(tmp_path / 'w2')), nprocs=2, join=True)
+    with open(out) as fh:
+        got = json.load(fh)
+    assert sorted(os.listdir(tmp_path / 'w2' / 'shard'))[-5:] == ['trial_%d.pkl' % t for t in range(5)]
+    from ocbo_b200 import batched, ocbo
+    from ocbo_b200.strategies import multi_opt
+    from oracle import gp_numpy as o
+    from tests.test_host_strategies import _Fitter, _fake_mts_step
+    monkeypatch.setattr(multi_opt, 'get_gp_fitter', lambda engine, x, y, opts: _Fitter(x, y, opts))
+    monkeypatch.setattr(batched, '_mts_flat', _fake_mts_step)
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    o.EuclideanGPFitter._fit_counter = 0
+    ref = _summary(ocbo.run(argv=_DRIVER_ARGV))
+    assert got == ref
