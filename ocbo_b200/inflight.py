@@ -31,6 +31,7 @@ imported BEFORE the run (``from numpy.random import uniform``) would still draw
 from the process-wide stream.
 """
 import threading
+import time
 from collections import deque
 
 import numpy as np
@@ -98,6 +99,7 @@ class TrialPool(object):
         self.trial_globals = list(trial_globals)
         self._back = threading.Event()
         self.stats = {}
+        self.seconds = {}  # wall time inside the merged passes per kind, and 'trials' (host code)
 
     def _enter_thread(self, trial, device, stream):
         """Thread body: CUDA's current device and torch's current stream are per thread."""
@@ -157,7 +159,9 @@ class TrialPool(object):
             while runnable or parked:
                 if runnable:
                     t = runnable.popleft()
+                    t0 = time.perf_counter()
                     self._resume(t)
+                    self.seconds['trials'] = self.seconds.get('trials', 0.0) + time.perf_counter() - t0
                     if not t.done:
                         parked.setdefault(t.request[0], []).append(t)
                     continue
@@ -166,6 +170,7 @@ class TrialPool(object):
                 run_many = group[0].request[2]
                 n_pass, n_req = self.stats.get(kind, (0, 0))
                 self.stats[kind] = (n_pass + 1, n_req + len(group))
+                t0 = time.perf_counter()
                 try:
                     replies = run_many([t.request[1] for t in group])
                     if len(replies) != len(group):
@@ -173,6 +178,7 @@ class TrialPool(object):
                                            % (kind, len(replies), len(group)))
                 except Exception as exc:
                     replies = [_Failure(exc)] * len(group)
+                self.seconds[kind] = self.seconds.get(kind, 0.0) + time.perf_counter() - t0
                 for t, r in zip(group, replies):
                     t.request, t.reply = None, r
                 runnable.extend(group)
@@ -206,14 +212,18 @@ def run_waves(num_trials, width, seed, make_trial, trial_globals=(), trial_ids=N
     number of steps, so waves lose nothing).  ``make_trial(t)`` returns trial t's callable.
     ``trial_ids`` restricts the run to a rank's shard (ocbo_b200.dist.shard_trials): a trial's
     stream is keyed by its GLOBAL id, so results do not depend on the world size.
-    Returns (results in the order of the ids, per-kind (merged passes, requests served))."""
+    Returns (results in the order of the ids, stats): stats[kind] = (merged passes, requests
+    served), stats['seconds'] = wall time per kind and in the trials' own host code."""
     states = trial_rng_states(num_trials, seed)
     ids_all = list(range(int(num_trials))) if trial_ids is None else list(trial_ids)
     results, stats = [], {}
+    seconds = stats.setdefault('seconds', {})
     for w0 in range(0, len(ids_all), int(width)):
         ids = ids_all[w0:w0 + int(width)]
         pool = TrialPool(trial_globals)
         results += pool.run([make_trial(t) for t in ids], [states[t] for t in ids])
         for k, (a, b) in pool.stats.items():
             stats[k] = (stats.get(k, (0, 0))[0] + a, stats.get(k, (0, 0))[1] + b)
+        for k, v in pool.seconds.items():
+            seconds[k] = seconds.get(k, 0.0) + v
     return results, stats

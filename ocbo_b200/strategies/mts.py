@@ -13,6 +13,7 @@ import numpy as np
 
 from .multi_opt import MultiOpt
 from .. import batched, rng
+from ..util import uniform_box
 
 
 class MTS(MultiOpt):
@@ -23,8 +24,8 @@ class MTS(MultiOpt):
         for f_idx, f_name in enumerate(self.f_names):
             f_qs = queries[f_name]
             low, high = zip(*self.domains[f_idx])
-            rand_pts = np.random.uniform(low, high, (self.options.max_opt_evals, len(low)))
-            pts = np.vstack([f_qs, rand_pts])
+            rand_pts = uniform_box(low, high, self.options.max_opt_evals)
+            pts = np.concatenate([f_qs.reshape(-1, len(low)), rand_pts], axis=0)
             samp_pts.append(pts)
             n_old.append(len(f_qs))
             normals.append(rng.normals((len(pts), 1)))

@@ -151,12 +151,12 @@ def test_mts_trials_in_flight_equal_the_trials_alone(monkeypatch, name):
 
 
 def test_pack_rows_pads_ragged_inputs():
-    """Staging of many small problems: one concatenate + one scatter, same layout as the loop."""
+    """Staging of many ragged problems into one zero-padded block."""
     from ocbo_b200 import engine
     rs = np.random.RandomState(0)
     arrs = [rs.uniform(size=(n, 3)) for n in (5, 0, 130, 1, 77)]
     out, lens, n_pad = engine.pack_rows(arrs, 3)
-    assert n_pad == 256 and lens.tolist() == [5, 0, 130, 1, 77] and out.shape == (5, 256, 3)
+    assert n_pad == 256 and list(lens) == [5, 0, 130, 1, 77] and out.shape == (5, 256, 3)
     for b, a in enumerate(arrs):
         assert np.array_equal(out[b, :len(a)], a) and not out[b, len(a):].any()
     out1, _, n1 = engine.pack_rows([np.zeros((0, 2))], 2)

@@ -51,7 +51,7 @@ def main():
         torch.cuda.synchronize()
         pr.disable()
         s = io.StringIO()
-        pstats.Stats(pr, stream=s).sort_stats('cumulative').print_stats(45)
+        pstats.Stats(pr, stream=s).sort_stats(os.environ.get('SORT', 'cumulative')).print_stats(45)
         print('\n'.join(l[:160] for l in s.getvalue().splitlines()[4:] if l.strip()))
 
 
