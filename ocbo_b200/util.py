@@ -41,6 +41,12 @@ def sample_grid(f_locs, function_domain, num_pts):
     hstack U(lows, highs, (T*A, d)); JointMTS reshapes the sample to (T, A)."""
     lows, highs = zip(*function_domain)
     num_funcs = len(f_locs)
+    if num_funcs == 1:  # one context (continuous strategies, 50 calls per step): no tile / hstack
+        c = len(f_locs[0])
+        out = np.empty((num_pts, c + len(lows)))
+        out[:, :c] = f_locs[0]
+        out[:, c:] = uniform_box(lows, highs, num_pts)
+        return out
     locs = np.tile(np.asarray(f_locs), num_pts).reshape(-1, len(f_locs[0]))
     f_pts = uniform_box(lows, highs, num_funcs * num_pts)
     return np.hstack([locs, f_pts])

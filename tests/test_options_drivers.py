@@ -184,3 +184,11 @@ def test_continuous_driver_runs_hartmann4(tmp_path, extra):
     res = cts_ocbo.run(argv=['--options', str(f)])
     assert set(res[0]) == {'cmts', 'cmts-pm', 'pei'}
     assert len(res[0]['cmts'].query_history) == 3
+
+
+def test_vectorised_objective_is_bitwise_equal():
+    """synth.hartmann6.batch (used by the continuous drivers' policy score) equals the per-point
+    function bit for bit."""
+    from ocbo_b200 import synth
+    X = np.random.RandomState(3).uniform(size=(5000, 6))
+    assert np.array_equal(synth.hartmann6.batch(X), np.asarray([synth.hartmann6(x) for x in X]))
