@@ -147,6 +147,88 @@ def _mts_flat(gps, samp_pts_list, n_old_list, Z_list):
     return out
 
 
+def joint_many(requests):
+    """Joint-MTS steps (B200GPCore.sample_and_pick) of one or several trials.  One request runs
+    on the GP's own posterior (the tuned batch-1 path); several are grouped by kernel, input
+    dimension and task count and go through ONE batched pass that rebuilds the trials'
+    posteriors side by side, like ``_mts_flat``."""
+    out = [None] * len(requests)
+    groups = defaultdict(list)
+    for i, (core, Xs, seg, T, Zh) in enumerate(requests):
+        groups[(core.kernel.kind, core.dim, T, len(seg))].append(i)
+    for (kind, D, T, _), members in groups.items():
+        res = None
+        if len(members) > 1:
+            res = _joint_group([requests[i] for i in members], kind, D, T)
+        for k, i in enumerate(members):
+            core, Xs, seg, T_, Zh = requests[i]
+            out[i] = res[k] if res is not None else core._sample_and_pick_alone(Xs, seg, T_, Zh)
+    return out
+
+
+def _joint_group(reqs, kind, D, T):
+    """-> [(task, action, gain)] per request, or None when a problem needs the host-continued
+    ladder (the callers then run alone, each on its own posterior)."""
+    if not engine.graphs_enabled():
+        return None
+    cores = [r[0] for r in reqs]
+    B = len(reqs)
+    Xs_, ys_ = [c.X_array() for c in cores], [c.Y_array() for c in cores]
+    thetas = np.asarray([c.theta() for c in cores])
+    pts, Zs = [r[1] for r in reqs], [r[4] for r in reqs]
+    segs = np.asarray([r[2] for r in reqs], dtype=np.int32)
+    n_pad = engine.pad_to(max([len(y) for y in ys_] + [1]))
+    m_pad = engine.pad_to(max([len(q) for q in pts] + [1]))
+    plan = engine.StepPlan.get(('joint-group', kind, D, B, n_pad, m_pad, segs.shape[1], T),
+                               _arena_bytes(B, n_pad, m_pad, D, segs.shape[1], True))
+    with plan.staging():
+        st_now = (DevicePosterior.pack(Xs_, ys_, thetas, D), _stage_candidates(B, D, pts, Zs, segs))
+
+    def body(st, ext):
+        packed, staged_ = st
+        post_ = DevicePosterior.from_device(*packed, kind, D)
+        post_.build(check=False, need_alpha=False)
+        _, pend, tail = _enqueue_tail(post_, staged_, engine.GRAPH_SPEC_RUNGS)
+        _, mx_, ag_ = tail()
+        return list(engine.joint_pick(mx_, ag_, T, T)) + [post_.info, pend.info, pend.rung]
+
+    task, act, gain, info_k, info_s, rung = plan.run(st_now, [], body)
+    if info_k.any() or (info_s > 0).any():
+        return None
+    jit = _rungs(rung)
+    for k, c in enumerate(cores):
+        c.last_sample_jitter = jit[k]
+    return [(int(task[k, 0]), int(act[k, 0]), float(gain[k, 0])) for k in range(B)]
+
+
+def mean_many(requests):
+    """Posterior means (B200GPCore.eval, mean only: the risk-neutral pick of every BO step) of
+    one or several trials' GPs at their own point sets.  One request runs on the GP's own
+    posterior; several share one batched pass (posteriors rebuilt side by side)."""
+    out = [None] * len(requests)
+    groups = defaultdict(list)
+    for i, (core, Xs) in enumerate(requests):
+        groups[(core.kernel.kind, core.dim)].append(i)
+    for (kind, D), members in groups.items():
+        res = None
+        if len(members) > 1:
+            cores = [requests[i][0] for i in members]
+            pts = [requests[i][1] for i in members]
+            with engine.staging(16 * sum(c.X_array().size + len(c.Y) for c in cores)
+                                + 16 * sum(p.size for p in pts) + (1 << 16)):
+                post = DevicePosterior([c.X_array() for c in cores], [c.Y_array() for c in cores],
+                                       np.asarray([c.theta() for c in cores]), kind, D)
+                Xd, mv_dev, mv, _ = post.upload_points(pts)
+            post.build(check=False, need_alpha=True)
+            mean = post.mean(Xd, mv_dev)
+            if not post.info.cpu().numpy().any():  # (a prior Gram matrix needing the ladder: alone)
+                mean_h = mean.cpu().numpy()
+                res = [mean_h[k, :mv[k]].copy() for k in range(len(members))]
+        for k, i in enumerate(members):
+            out[i] = res[k] if res is not None else requests[i][0]._mean_alone(requests[i][1])
+    return out
+
+
 class SharedPosterior(object):
     """View of ONE built posterior replicated (stride 0) over B candidate sets --
     the continuous strategies evaluate the same GP at 50 contexts

@@ -220,14 +220,23 @@ class B200GPCore(object):
         joint-MTS pick (src/strategies/joint_mts.py:42-57): ``seg_ptr`` holds the
         row offsets of the T old-point segments followed by the T grid segments.
         Returns (task, action index, gain)."""
+        Xs = np.asarray(to_samp, dtype=np.float64).reshape(-1, self.dim)
+        # the global normal stream is consumed exactly once per call, whatever path is taken
+        Zh = rng.normals((len(Xs), 1)) if _normals is None else _normals
+        if _normals is None:
+            # with trials in flight the joint steps of all trials share one device pass
+            from .. import batched, inflight
+            return inflight.merge('joint', (self, Xs, np.asarray(seg_ptr, dtype=np.int32),
+                                            int(num_tasks), Zh), batched.joint_many)
+        return self._sample_and_pick_alone(Xs, seg_ptr, num_tasks, Zh)
+
+    def _sample_and_pick_alone(self, Xs, seg_ptr, num_tasks, Zh):
         if self._post_raw is None:
             self.build_posterior()
         base = self._post_raw  # possibly unverified: checked with the results, below
-        Xs = np.asarray(to_samp, dtype=np.float64).reshape(-1, self.dim)
+        to_samp = Xs
         seg_h = np.asarray(seg_ptr, dtype=np.int32)[None, :]
         D, T = self.dim, int(num_tasks)
-        # the global normal stream is consumed exactly once per call, whatever path is taken
-        Zh = rng.normals((len(Xs), 1)) if _normals is None else _normals
 
         def stage():
             Xd, mv_dev, mv, m_pad = engine.upload_points(1, D, [Xs])
@@ -301,6 +310,10 @@ class B200GPCore(object):
         Sigma = post.cov(Xd, mv_dev, V, lower_only)
         return Xd, mv_dev, mv, mean, V, Sigma
 
+    def _mean_alone(self, Xs):
+        _, _, mv, mean, _, _ = self._posterior_at(Xs, False, False)
+        return mean[0, :mv[0]].cpu().numpy()
+
     def eval(self, X_test, uncert_form='none'):
         if uncert_form not in ('none', 'std', 'covar'):
             raise ValueError('uncert_form must be none, std or covar.')
@@ -316,11 +329,13 @@ class B200GPCore(object):
                         engine._stream())
             m = mv[0]
             return mean[0, :m].cpu().numpy(), np.sqrt(var[0, :m].cpu().numpy())
-        _, _, mv, mean, _, Sigma = self._posterior_at(X_test, uncert_form != 'none', False)
+        if uncert_form == 'none':
+            from .. import batched, inflight  # with trials in flight, mean-only evaluations merge
+            Xs = np.asarray(X_test, dtype=np.float64).reshape(-1, self.dim)
+            return inflight.merge('mean', (self, Xs), batched.mean_many), None
+        _, _, mv, mean, _, Sigma = self._posterior_at(X_test, True, False)
         m = mv[0]
         mu = mean[0, :m].cpu().numpy()
-        if uncert_form == 'none':
-            return mu, None
         cov = Sigma[0, :m, :m].cpu().numpy()
         if uncert_form == 'covar':
             return mu, cov

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import hp_search
 from .gp_core import B200GPCore, ConstMean, make_kernel
-from .. import engine
+from .. import engine, inflight
 
 
 class GPWrapper(object):
@@ -81,8 +81,10 @@ class B200GP(GPWrapper):
 
     def build_posterior(self):
         # :85-88 tests ``alpha is not None``; here alpha is materialised on first read, so the
-        # equivalent idempotence test is on the device posterior itself
-        if not self.gp_core.has_posterior():
+        # equivalent idempotence test is on the device posterior itself.  With trials in flight
+        # the build is left to the first reader: the merged passes rebuild all trials'
+        # posteriors side by side and never look at the per-GP one.
+        if not self.gp_core.has_posterior() and not inflight.in_flight():
             self.gp_core.build_posterior()
 
     def get_estimated_noise(self):
@@ -108,9 +110,13 @@ class B200GPFitter(GPFitterWrapper):
     _fit_counter = 0
 
     def _init_gpf(self):
-        X = [np.asarray(x, dtype=np.float64).ravel() for x in self.x_data]
-        self.dim = len(X[0]) if len(X) else int(self.options.dim)
-        self._X = np.asarray(X, dtype=np.float64).reshape(-1, self.dim)
+        if isinstance(self.x_data, np.ndarray) and self.x_data.ndim == 2 and len(self.x_data):
+            self._X = np.ascontiguousarray(self.x_data, dtype=np.float64)  # (n, D) array: as is
+            self.dim = self._X.shape[1]
+        else:
+            X = [np.asarray(x, dtype=np.float64).ravel() for x in self.x_data]
+            self.dim = len(X[0]) if len(X) else int(self.options.dim)
+            self._X = np.asarray(X, dtype=np.float64).reshape(-1, self.dim)
         self._Y = np.asarray(self.y_data, dtype=np.float64).ravel()
         self.kind = engine.kernel_kind(self.options.kernel_type,
                                        getattr(self.options, 'matern_nu', 2.5))

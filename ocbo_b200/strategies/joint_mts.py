@@ -13,7 +13,8 @@ ocbo_joint_pick), so (task, action index, gain) is all that comes back.
 """
 import numpy as np
 
-from .joint_opt import JointOpt
+from .joint_opt import JointOpt, located_rows
+from .. import inflight
 from ..util import sample_grid
 
 
@@ -22,10 +23,10 @@ def joint_layout(f_locs, per_task_points, grid):
     order) followed by T grid segments of equal length."""
     T = len(f_locs)
     counts = [len(p) for p in per_task_points]
-    old_rows = [np.append(f_locs[t], pt) for t in range(T) for pt in per_task_points[t]]
     n_old = sum(counts)
     width = grid.shape[1]
-    rows = np.vstack([np.asarray(old_rows, dtype=np.float64).reshape(n_old, width), grid])
+    blocks = [located_rows(f_locs[t], per_task_points[t]) for t in range(T) if counts[t]]
+    rows = np.concatenate([b.reshape(-1, width) for b in blocks] + [grid], axis=0)
     per_task = len(grid) // T
     bounds = np.concatenate([[0], np.cumsum(counts), n_old + per_task * np.arange(1, T + 1)])
     return rows, bounds.astype(np.int32)
@@ -38,7 +39,8 @@ class JointMTS(JointOpt):
         return 'joint-mts'
 
     def decide_next_query(self):
-        self.gps[0].build_posterior()
+        if not inflight.in_flight():  # (in flight the merged pass rebuilds all trials' posteriors)
+            self.gps[0].build_posterior()
         return self._find_best_query()
 
     def _find_best_query(self):

@@ -15,6 +15,20 @@ from ..gp.gp_util import get_gp_fitter
 from ..util import sample_grid
 
 
+def located_rows(f_loc, pts):
+    """[f_loc (+) pt for pt in pts] as one (len(pts), c + d) array (np.append per point was
+    a third of a joint step's host time at n = 160)."""
+    f_loc = np.asarray(f_loc, dtype=np.float64).ravel()
+    c = f_loc.size
+    if not len(pts):
+        return np.zeros((0, c))
+    P = np.asarray(pts, dtype=np.float64).reshape(len(pts), -1)
+    rows = np.empty((len(pts), c + P.shape[1]))
+    rows[:, :c] = f_loc
+    rows[:, c:] = P
+    return rows
+
+
 class JointOpt(MultiOpt):
 
     def __init__(self, f_infos, options, pre_tuned_gps=None, rn_info=None):
@@ -40,11 +54,12 @@ class JointOpt(MultiOpt):
         return np.append(self.f_locs[f_idx], pt)
 
     def _refit(self, f_idx):
-        xs, ys = [], []
+        blocks, ys = [], []
         for t_idx in range(len(self.f_names)):
             pts, vals = self._ledger.observations(t_idx)
-            xs += [self._gp_input(t_idx, p) for p in pts]
+            blocks.append(located_rows(self.f_locs[t_idx], pts))
             ys += vals
+        xs = np.concatenate(blocks, axis=0)  # rows = _gp_input(task, pt), task by task
         fitter = get_gp_fitter(self.gp_engine, xs, ys, self.gp_options)
         fitter.fit_gp()
         self.gp_fitters = [fitter]

@@ -227,3 +227,31 @@ def test_continuous_driver_in_flight(tmp_path):
     b = [np.ravel(q.pt).tolist() + [q.reward] for q in alone0[0]['cmts'].query_history]
     assert a == b
     assert len(got[1]['cmts'].query_history) == 3
+
+
+@pytest.mark.gpu
+def test_joint_driver_in_flight_equals_the_trials_alone(tmp_path):
+    """joint-MTS (jointbran.txt's method) with three trials in flight: the trials' joint posterior
+    samples share one batched pass (batched.joint_many) and each trial reproduces itself alone."""
+    from ocbo_b200 import ocbo
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    from ocbo_b200.options import load_options
+    from ocbo_b200.strategies.multi_opt import multi_opt_args
+    f = tmp_path / 'jfl.txt'
+    f.write_text('--run_id jfl\n--trials 3\n--max_capital 5\n--init_capital 5\n--tune_every 1\n'
+                 '--tuning_methods ml\n--methods joint-mts\n--cts_f branin\n--risk_neutral 1\n--num_chops 4\n')
+    argv = ['--options', str(f)]
+    B200GPFitter._fit_counter = 0
+    got = ocbo.run(argv=argv + ['--trials_in_flight', '3'])
+    stats = ocbo.LAST_MERGE_STATS[0]
+    assert stats['joint'] == (5, 15)
+    options = load_options(ocbo.docbo_args + multi_opt_args + ocbo.rand_fs_args, cmd_line=True, argv=argv)
+    np.random.seed(ocbo.SEED)
+    f_infos = ocbo.assemble(options)
+    meths = ocbo.assemble_methods(f_infos, options)
+    names = [fi.name for fi in f_infos]
+    for t, st in enumerate(inflight.trial_rng_states(3, ocbo.SEED)):
+        np.random.set_state(st)
+        B200GPFitter._fit_counter = 0
+        alone = ocbo.run_single(meths, f_infos, options)
+        assert _timeline(got[t]['joint-mts'], names) == _timeline(alone['joint-mts'], names), t

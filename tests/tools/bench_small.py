@@ -223,7 +223,7 @@ def measure_bo_loop(capital=40, in_flight=(8, 32)):
                 return time.perf_counter() - t0
             res[name] = {'b200_iterations_per_s': capital / timed([]),
                          'iterations': capital, 'what': text.replace('\n', ' ').strip() % capital}
-            if name in ('set2d', 'rand6d'):
+            if name in ('set2d', 'rand6d', 'jointbran'):
                 for R in in_flight:
                     dt = timed(['--trials', str(R), '--trials_in_flight', str(R)])
                     res[name]['b200_iterations_per_s_%d_in_flight' % R] = R * capital / dt

@@ -7,7 +7,7 @@ from ocbo_b200 import ocbo as drv
 MODE = os.environ.get('GC', 'default')
 if MODE == 'off':
     gc.disable()
-for name in ('set2d', 'rand6d'):
+for name in ('set2d', 'rand6d', 'jointbran'):
     kind, text = OPTS[name]
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, 'o.txt')
