@@ -94,6 +94,19 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     return inflight.merge('mts', (gps, samp_pts_list, n_old_list, Z_list), _many(_mts_flat))
 
 
+PIPELINE_MIN = 64  # problems per chunk: a larger pass is split so that staging overlaps the device
+
+
+def _chunks(members):
+    """A merged pass of hundreds of problems is host-bound (staging ~6 us per problem, then the
+    device runs while the host waits): split it, enqueue chunk k and stage chunk k + 1 meanwhile."""
+    n = min(3, len(members) // PIPELINE_MIN) if engine.graphs_enabled() else 1
+    if n < 2:
+        return [members]
+    step = (len(members) + n - 1) // n
+    return [members[i:i + step] for i in range(0, len(members), step)]
+
+
 def _mts_flat(gps, samp_pts_list, n_old_list, Z_list):
     T = len(gps)
     groups = defaultdict(list)
@@ -101,38 +114,14 @@ def _mts_flat(gps, samp_pts_list, n_old_list, Z_list):
         core = gp.gp_core
         groups[(core.dim, core.kernel.kind)].append(f)
     out = [None] * T
-    for (D, kind), members in groups.items():
-        cores = [gps[f].gp_core for f in members]
-        Xs_ = [c.X_array() for c in cores]
-        ys_ = [c.Y_array() for c in cores]
-        thetas = np.asarray([c.theta() for c in cores])
-        pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
-        segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
-        Zs = [Z_list[f] for f in members]
-
-        def stage():
-            return (DevicePosterior.pack(Xs_, ys_, thetas, D),
-                    _stage_candidates(len(members), D, pts, Zs, segs))
-
+    launched = []
+    for (D, kind), all_members in groups.items():
+        for c, members in enumerate(_chunks(all_members)):
+            launched.append(_mts_launch(gps, samp_pts_list, n_old_list, Z_list, members, D, kind, c))
+    for members, D, kind, stage, plan in launched:
         mx = None
-        if engine.graphs_enabled():
-            B = len(members)
-            n_pad = engine.pad_to(max([len(y) for y in ys_] + [1]))
-            m_pad = engine.pad_to(max([len(q) for q in pts] + [1]))
-            plan = engine.StepPlan.get(('mts', kind, D, B, n_pad, m_pad),
-                                       _arena_bytes(B, n_pad, m_pad, D, 2, True))
-            with plan.staging():
-                st_now = stage()
-
-            def body(st, ext):
-                packed, staged_ = st
-                post_ = DevicePosterior.from_device(*packed, kind, D)
-                post_.build(check=False, need_alpha=False)
-                _, pend, tail = _enqueue_tail(post_, staged_, engine.GRAPH_SPEC_RUNGS)
-                _, mx_, ag_ = tail()
-                return [mx_, ag_, post_.info, pend.info, pend.rung]
-
-            mx_h, ag_h, info_k, info_s, rung = plan.run(st_now, [], body)
+        if plan is not None:
+            mx_h, ag_h, info_k, info_s, rung = plan.results()
             if not info_k.any() and not (info_s > 0).any():
                 mx, ag, jit = mx_h[:, :, 0], ag_h[:, :, 0], _rungs(rung)
         if mx is None:  # graphs off, or a problem needs the host-continued ladder
@@ -145,6 +134,43 @@ def _mts_flat(gps, samp_pts_list, n_old_list, Z_list):
             out[f] = (float(mx[k, 0]), int(ag[k, 1]), float(mx[k, 1]))
             gps[f].gp_core.last_sample_jitter = jit[k]
     return out
+
+
+def _mts_launch(gps, samp_pts_list, n_old_list, Z_list, members, D, kind, chunk):
+    """Stage one chunk and enqueue its step plan (no synchronisation)."""
+    cores = [gps[f].gp_core for f in members]
+    Xs_ = [c.X_array() for c in cores]
+    ys_ = [c.Y_array() for c in cores]
+    thetas = np.asarray([c.theta() for c in cores])
+    pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
+    segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
+    Zs = [Z_list[f] for f in members]
+
+    def stage():
+        return (DevicePosterior.pack(Xs_, ys_, thetas, D),
+                _stage_candidates(len(members), D, pts, Zs, segs))
+
+    if not engine.graphs_enabled():
+        return members, D, kind, stage, None
+    B = len(members)
+    n_pad = engine.pad_to(max([len(y) for y in ys_] + [1]))
+    m_pad = engine.pad_to(max([len(q) for q in pts] + [1]))
+    # (the chunk index keeps the plans -- arenas, result buffers -- of equal-sized chunks apart)
+    plan = engine.StepPlan.get(('mts', kind, D, B, n_pad, m_pad, chunk),
+                               _arena_bytes(B, n_pad, m_pad, D, 2, True))
+    with plan.staging():
+        st_now = stage()
+
+    def body(st, ext):
+        packed, staged_ = st
+        post_ = DevicePosterior.from_device(*packed, kind, D)
+        post_.build(check=False, need_alpha=False)
+        _, pend, tail = _enqueue_tail(post_, staged_, engine.GRAPH_SPEC_RUNGS)
+        _, mx_, ag_ = tail()
+        return [mx_, ag_, post_.info, pend.info, pend.rung]
+
+    plan.run(st_now, [], body, wait=False)
+    return members, D, kind, stage, plan
 
 
 def joint_many(requests):

@@ -232,8 +232,10 @@ class StepPlan(object):
     def staging(self):
         return _PlanStaging(self)
 
-    def run(self, staged, ext, body):
-        """body(staged, ext) -> list of device tensors; returns them as numpy arrays."""
+    def run(self, staged, ext, body, wait=True):
+        """body(staged, ext) -> list of device tensors; returns them as numpy arrays.  With
+        ``wait=False`` the replay is only enqueued (the caller stages its next chunk while this
+        one runs) and ``results()`` synchronises later."""
         stream = torch.cuda.current_stream()
         if self.graph is None:
             self.staged, self.used0 = staged, self.used
@@ -256,7 +258,10 @@ class StepPlan(object):
                 own.copy_(t, non_blocking=True)
         self.graph.replay()
         self.replays += 1
-        stream.synchronize()
+        return self.results() if wait else None
+
+    def results(self):
+        torch.cuda.current_stream().synchronize()
         return [h.numpy() for h in self.outs_host]
 
 

@@ -255,3 +255,27 @@ def test_joint_driver_in_flight_equals_the_trials_alone(tmp_path):
         B200GPFitter._fit_counter = 0
         alone = ocbo.run_single(meths, f_infos, options)
         assert _timeline(got[t]['joint-mts'], names) == _timeline(alone['joint-mts'], names), t
+
+
+@pytest.mark.gpu
+def test_pipelined_chunks_equal_the_single_pass(monkeypatch):
+    """A merged pass of >= 128 problems is split into chunks whose staging overlaps the device
+    (batched._chunks); every problem gets the bits of the unsplit pass."""
+    from ocbo_b200 import batched
+    from ocbo_b200.gp.gp_interface import make_gp
+    rs = np.random.RandomState(2)
+    gps, pts, n_old, Z = [], [], [], []
+    for k in range(150):
+        n = 4 + k % 9
+        X = rs.uniform(size=(n, 2))
+        y = np.sin(3 * X.sum(1))
+        gps.append(make_gp(X, y, 'se', 1.0, [0.3, 0.4], 1e-2, 0.1, build=False))
+        pts.append(np.vstack([X, rs.uniform(size=(20 + k % 5, 2))]))
+        n_old.append(n)
+        Z.append(rs.normal(size=(len(pts[-1]), 1)))
+    assert [len(c) for c in batched._chunks(list(range(150)))] == [75, 75]
+    got = batched.mts_step(gps, pts, n_old, Z)
+    again = batched.mts_step(gps, pts, n_old, Z)       # replayed plans
+    monkeypatch.setattr(batched, 'PIPELINE_MIN', 10 ** 9)
+    ref = batched.mts_step(gps, pts, n_old, Z)
+    assert got == ref and again == ref
