@@ -23,12 +23,13 @@ struct EiArgs {
   double* mean_out; int64_t sMeanOut;
 };
 
-// One CTA = 32 candidates x 8 row slices: warp w walks rows k = w, w+8, ... of V (each row
-// access is one 256-byte line per warp), 8 loads in flight per thread; the 8 partial sums are
+// One CTA = 32 candidates x 16 row slices: warp w walks rows k = w, w+16, ... of V (each row
+// access is one 256-byte line per warp), 8 loads in flight per thread; the 16 partial sums are
 // combined through shared memory in a fixed order, so results do not depend on scheduling.
 // (The first version used one thread per candidate and one CTA per 128 candidates: 64 CTAs
-// for the sweep's m = 8192 and 354 GB/s; this one keeps m/32 CTAs x 8 warps busy.)
-constexpr int EI_COLS = 32, EI_SLICES = 8;
+// for the sweep's m = 8192 and 354 GB/s.  8 slices: 2.65 TB/s with 256 CTAs of 8 warps on 148
+// SMs -- 16-32 KB in flight per SM, under Little's law for HBM3e; 16 slices double that.)
+constexpr int EI_COLS = 32, EI_SLICES = 16;
 
 __global__ void __launch_bounds__(EI_COLS * EI_SLICES) post_var_ei_kernel(EiArgs a) {
   __shared__ double ps[EI_SLICES][EI_COLS], pd[EI_SLICES][EI_COLS];

@@ -1,9 +1,10 @@
 """Continuous-context driver: ``python -m ocbo_b200.cts_ocbo --options <file>``.
 
-Host mirror of /root/reference/src/cts_ocbo.py:47-140 for CMTS / CMTS-PM; reads
-the reference's option files unchanged (src/options/conth42.txt ...).  Methods
-outside the MTS path (pei, revi, rand ...) are skipped unless
-``--strict_methods 1`` (then ``ValueError('Invalid method: ...')`` as at :139)."""
+Host mirror of /root/reference/src/cts_ocbo.py:47-140; reads the reference's option
+files unchanged (src/options/conth42.txt, conth22.txt, contbran.txt, *_sethps.txt ...).
+Every method of the reference's registry runs (cmts, cmts-pm, pei, revi, rand, ei, ts); a
+name outside it is skipped, or raises ``ValueError('Invalid method: ...')`` as at :139
+with ``--strict_methods 1``.  ``--trials_in_flight`` and rank sharding as in ocbo.py."""
 import os
 import pickle as pkl
 import sys

@@ -1,15 +1,18 @@
 """Discrete / joint driver: ``python -m ocbo_b200.ocbo --options <file>``.
 
-Host mirror of /root/reference/src/ocbo.py:67-144 for the MTS family: it reads
-the reference's option files UNCHANGED (src/options/set2d.txt, rand6d.txt,
-jointbran.txt ...), seeds numpy with the reference's seed (:74-75), builds the
-task functions, runs ``trials`` x methods and (optionally) pickles per-trial
-results under ``write_dir/run_id`` with the reference's file names (:95-107).
+Host mirror of /root/reference/src/ocbo.py:67-144: it reads the reference's option
+files UNCHANGED (src/options/set2d.txt, rand6d.txt, jointbran.txt, jointh*.txt ...),
+seeds numpy with the reference's seed (:74-75), builds the task functions, runs
+``trials`` x methods and (optionally) pickles per-trial results under
+``write_dir/run_id`` with the reference's file names (:95-107).  Every method of the
+reference's registry runs (MTS / EI families, REVI, the agnostic and random baselines);
+a name outside it is reported and skipped, or raises ``ValueError('Invalid method: ...')``
+like the reference (:187) with ``--strict_methods 1``.  Plotting is out of scope.
 
-Methods of the option file that are not on the accelerated MTS path (agn-*,
-mei, random, revi ...) are reported and skipped unless ``--strict_methods 1``,
-in which case they raise ``ValueError('Invalid method: ...')`` like the
-reference (:187).  Plotting is out of scope.
+Two additions over the reference's sequential loop, both off by default:
+``--trials_in_flight R`` advances R trials in lockstep and merges their device passes
+(ocbo_b200/inflight.py), and under a launcher (``torchrun -m ocbo_b200.ocbo ...``) the
+trials are sharded over the ranks, trial t on rank t mod W, with one gather of the results.
 """
 import os
 import pickle as pkl
