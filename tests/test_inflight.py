@@ -279,3 +279,70 @@ def test_pipelined_chunks_equal_the_single_pass(monkeypatch):
     monkeypatch.setattr(batched, 'PIPELINE_MIN', 10 ** 9)
     ref = batched.mts_step(gps, pts, n_old, Z)
     assert got == ref and again == ref
+
+
+def _merged(kind_fn, payloads):
+    """Run one merged pass the way the scheduler does (several requests at once)."""
+    return kind_fn(payloads)
+
+
+@pytest.mark.gpu
+def test_merged_joint_and_mean_passes_fall_back_per_request():
+    """joint_many / mean_many with several requests: a well-conditioned group equals the requests
+    run alone; a group holding a problem that needs the host-continued ladder (duplicated
+    candidates, vanishing noise) hands every request back to its own tuned path."""
+    from ocbo_b200 import batched
+    from ocbo_b200.gp.gp_interface import make_gp
+    rs = np.random.RandomState(6)
+    T, A = 3, 20
+
+    def request(noise, duplicate):
+        n = 12
+        X = np.hstack([np.repeat(np.linspace(0, 1, T), n // T)[:, None], rs.uniform(size=(n, 1))])
+        y = np.sin(4 * X.sum(1))
+        gp = make_gp(X, y, 'se', 1.0, [0.5, 0.5], noise, 0.0, build=False)
+        grid = np.hstack([np.repeat(np.linspace(0, 1, T), A)[:, None], rs.uniform(size=(T * A, 1))])
+        if duplicate:
+            grid[A:2 * A] = grid[:A]
+        rows = np.vstack([X, grid])
+        seg = np.concatenate([np.arange(0, n + 1, n // T), n + A * np.arange(1, T + 1)]).astype(np.int32)
+        return gp.gp_core, rows, seg, T, rs.normal(size=(len(rows), 1))
+
+    for dup in (False, True):
+        reqs = [request(1e-2, False), request(1e-12 if dup else 1e-2, dup), request(1e-2, False)]
+        alone = [c._sample_and_pick_alone(r, s, t, z) for c, r, s, t, z in reqs]
+        jit = [c.last_sample_jitter for c, _, _, _, _ in reqs]
+        for c, _, _, _, _ in reqs:
+            c._post = None
+        assert _merged(batched.joint_many, reqs) == alone
+        assert [c.last_sample_jitter for c, _, _, _, _ in reqs] == jit
+    cores = [r[0] for r in reqs]
+    pts = [rs.uniform(size=(30 + 5 * k, 2)) for k in range(3)]
+    means_alone = [c._mean_alone(p) for c, p in zip(cores, pts)]
+    merged = _merged(batched.mean_many, list(zip(cores, pts)))
+    assert all(np.array_equal(a, b) for a, b in zip(means_alone, merged))
+
+
+@pytest.mark.gpu
+def test_merged_lml_group_equals_single_passes(monkeypatch):
+    """_lml_many over three data sets of different sizes == three single passes, including a
+    candidate that needs the jitter ladder."""
+    from ocbo_b200 import engine
+    from ocbo_b200.gp import hp_search
+    rs = np.random.RandomState(8)
+    jobs = []
+    for n in (20, 57, 130):
+        X = rs.uniform(size=(n, 3))
+        if n == 57:
+            X[10:20] = X[:10]
+        y = np.sin(4 * X.sum(1))
+        th = hp_search.hp_candidates(X, y, 8, uniforms=rs.uniform(size=(7, 6)))
+        if n == 57:
+            th[3, 1] = 1e-18
+        jobs.append((X, y, 0, th))
+    single = [hp_search._lml_single(*j)[0] for j in jobs]
+    for graphs in (True, False):
+        monkeypatch.setattr(engine, 'graphs_enabled', lambda g=graphs: g)
+        merged = hp_search._lml_many(jobs)
+        for a, (b, _) in zip(single, merged):
+            assert np.array_equal(a, b)
