@@ -8,8 +8,6 @@ Only the set-evaluation form (:139-160) is offered: the thresholded variant (:16
 reached with ``--judge_ctx_thresh / --judge_act_thresh`` only, which no option file sets, and
 calls ``gp.eval(..., uncert_form=...)`` with a keyword the reference's own GP wrapper does not
 accept."""
-import numpy as np
-
 from .cts_opt import ContinuousOpt
 from .. import batched
 from ..options import get_option_specs

@@ -9,7 +9,6 @@ import os
 import pickle as pkl
 import sys
 import time
-from argparse import Namespace
 from copy import copy
 
 import numpy as np

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .. import _lib, engine, rng
-from ..engine import DevicePosterior, F64, TILE
+from ..engine import DevicePosterior, F64
 
 
 class _Kernel(object):

@@ -3,8 +3,6 @@
 368-385, random-search EI over max_opt_evals uniform points per task).  All tasks
 are evaluated in one batched device pass; EI comes from the fused mean + diagonal
 variance kernel, the m x m covariance the reference builds is never formed."""
-import numpy as np
-
 from .multi_opt import MultiOpt
 from .. import batched
 from ..util import uniform_draw
