@@ -18,3 +18,9 @@ $NCU -k regex:"post_var_ei|segment_argmax|philox_normal|joint_pick|solve_alpha" 
 $NCU -k regex:gemm_nn_kernel --launch-skip 15 --launch-count 1 -o gpurun_out/full_sample \
     python scripts/profile_step.py 1 > gpurun_out/ncu_f5.log 2>&1; echo "sample exit $?"
 ls -la gpurun_out/*.ncu-rep
+python -c "
+from tests.tools import bench_small
+print(bench_small.measure_revi(1))" > gpurun_out/plain_revi.log 2>&1 && \
+$NCU -k regex:kg_kernel --launch-count 1 -o gpurun_out/full_kg python -c "
+from tests.tools import bench_small
+print(bench_small.measure_revi(1))" > gpurun_out/ncu_kg.log 2>&1; echo "kg exit $?"
