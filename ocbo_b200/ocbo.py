@@ -87,7 +87,22 @@ def assemble(options):
     return f_infos
 
 
-def assemble_methods(f_infos, options):
+def get_function_gps(f_infos, options):
+    """src/ocbo.py:146-159 -- pre-tuned mode: with ``--pretune_for_joint`` ONE empty-data joint
+    GP carrying tuned hyper-parameters is shared by every task (and ``tune_every`` drops to 0);
+    with ``--tune_every 0`` every task gets its own tuned empty prior (100 d samples); else the
+    strategies fit as they go (None)."""
+    from .gp.gp_util import get_best_joint_prior, get_best_prior
+    if options.pretune_for_joint:
+        options.tune_every = 0
+        pre_gp = get_best_joint_prior(f_infos)
+        return [pre_gp for _ in f_infos]
+    if options.tune_every > 0:
+        return None
+    return [get_best_prior(w.function, w.domain, num_samples=len(w.domain) * 100) for w in f_infos]
+
+
+def assemble_methods(f_infos, options, gps=None):
     if options.methods is None:
         raise ValueError('Methods must be specified.')
     names = options.methods.split(',')
@@ -104,12 +119,15 @@ def assemble_methods(f_infos, options):
             continue
         if tunings is not None:
             options.tuning_methods = tunings[m_idx]
-        methods.append(impl[0](f_infos, options, pre_tuned_gps=None, rn_info=rn_info))
+        methods.append(impl[0](f_infos, options, pre_tuned_gps=gps, rn_info=rn_info))
         rn_info = (methods[-1].rn_grids, methods[-1].rn_bests)
     if skipped:
         sys.stderr.write('ocbo_b200: methods outside the MTS hot path skipped: %s\n' % ','.join(skipped))
     if not methods:
         raise ValueError('No runnable method in: %s' % options.methods)
+    if rn_info[1] is not None:  # the random risk-neutral grids give the tasks their maxima (:189-192)
+        for f_idx, max_val in enumerate(rn_info[1]):
+            f_infos[f_idx].max_val = max_val
     return methods
 
 
@@ -141,7 +159,7 @@ def run(argv=None):
     rank, world_size = _dist.init_from_env()
     rand_state = np.random.get_state()
     f_infos = assemble(options)
-    methods = assemble_methods(f_infos, options)
+    methods = assemble_methods(f_infos, options, get_function_gps(f_infos, options))
     created = None
     if options.write_dir is not None and rank == 0:
         created = os.path.join(options.write_dir, options.run_id)
@@ -162,6 +180,9 @@ def run(argv=None):
 
         def make_trial(t_id):
             own = [copy(m) for m in methods]  # set_clean() gives every copy its own run state
+            for m in own:  # (the reference's joint strategies SHARE their pre-tuned GP across
+                if m.pre_tuned_gps is not None:  # trials, src/strategies/joint_opt.py:52; in
+                    m.pre_tuned_gps = deepcopy(m.pre_tuned_gps)  # flight a trial owns its copy)
             return lambda: run_single(own, f_infos, options)
         mine = _dist.shard_trials(options.trials, rank, world_size)
         local, LAST_MERGE_STATS[0] = inflight.run_waves(

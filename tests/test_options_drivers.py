@@ -192,3 +192,40 @@ def test_vectorised_objective_is_bitwise_equal():
     from ocbo_b200 import synth
     X = np.random.RandomState(3).uniform(size=(5000, 6))
     assert np.array_equal(synth.hartmann6.batch(X), np.asarray([synth.hartmann6(x) for x in X]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['pretune_for_joint', 'tune_every_0'])
+def test_discrete_driver_pre_tuned_modes(tmp_path, mode):
+    """src/ocbo.py:146-159: ``--pretune_for_joint`` (one shared empty-data joint GP with tuned
+    hyper-parameters, tune_every forced to 0) and ``--tune_every 0`` (a tuned empty prior per
+    task): the GPs start without data and grow a point at a time, nothing is re-fitted."""
+    from ocbo_b200 import ocbo
+    from ocbo_b200.gp import hp_search
+    f = tmp_path / 'pre.txt'
+    if mode == 'pretune_for_joint':
+        f.write_text('--run_id pre\n--trials 2\n--max_capital 3\n--init_capital 3\n--pretune_for_joint 1\n'
+                     '--methods joint-mts,joint-mei\n--cts_f branin\n--num_chops 3\n--risk_neutral 1\n')
+        names = {'joint-mts', 'joint-mei'}
+    else:
+        f.write_text('--run_id pre\n--trials 2\n--max_capital 3\n--init_capital 3\n--tune_every 0\n'
+                     '--methods mts,mei\n--functions branin,parabaloid\n')
+        names = {'mts', 'mei'}
+    fits = []
+    real = hp_search.batched_lml
+
+    def counting(*a, **k):
+        fits.append(1)
+        return real(*a, **k)
+    hp_search.batched_lml = counting
+    try:
+        res = ocbo.run(argv=['--options', str(f)])
+        n_fits = len(fits)
+        res_fl = ocbo.run(argv=['--options', str(f), '--trials_in_flight', '2'])
+    finally:
+        hp_search.batched_lml = real
+    assert n_fits == (1 if mode == 'pretune_for_joint' else 2)  # the prior fits only, none per step
+    assert len(res) == 2 and set(res[0]) == names and set(res_fl[1]) == names
+    for r in res + res_fl:
+        for h in r.values():
+            assert len(h.choice_timeline) == 3 and np.all(np.isfinite(h.total_best))
