@@ -9,6 +9,7 @@ import os
 import pickle as pkl
 import sys
 import time
+from argparse import Namespace
 from copy import copy
 
 import numpy as np
@@ -114,8 +115,11 @@ def run(argv=None):
         if os.path.isdir(created):
             raise ValueError('Run ID already exists: %s' % options.run_id)
         os.makedirs(created)
+        pure_f_info = Namespace(**{k: v for k, v in vars(f_info).items() if k != 'function'})
+        pure_f_info.function = None  # (:70-72)
         for name, obj in (('run_info.pkl', options), ('rand_state.pkl', rand_state),
-                          ('eval_set.pkl', methods[0].get_eval_set())):
+                          ('eval_set.pkl', methods[0].get_eval_set()),
+                          ('function_info.pkl', pure_f_info)):
             with open(os.path.join(created, name), 'wb') as fh:
                 pkl.dump(obj, fh, protocol=2)
     width = max(1, int(options.trials_in_flight or 1))

@@ -126,9 +126,13 @@ def test_continuous_driver_runs_an_option_file(tmp_path):
     f = tmp_path / 'mini.txt'
     f.write_text('--run_id cmini\n--trials 1\n--max_capital 2\n--init_capital 40\n--methods cmts,cmts-pm,revi\n'
                  '--function hartmann6\n--act_dim 2\n--num_profiles 5\n--eval_ctx_fidel 4\n'
-                 '--eval_act_fidel 4\n--judge_ctx_size 5\n--judge_act_size 10\n--cand_size 20\n')
+                 '--eval_act_fidel 4\n--judge_ctx_size 5\n--judge_act_size 10\n--cand_size 20\n'
+                 '--write_dir %s\n' % tmp_path)
     res = cts_ocbo.run(argv=['--options', str(f)])
     assert set(res[0]) == {'cmts', 'cmts-pm', 'revi'}
+    # the reference's file set (src/cts_ocbo.py:63-78)
+    assert sorted(os.listdir(tmp_path / 'cmini')) == ['eval_set.pkl', 'function_info.pkl', 'rand_state.pkl',
+                                                      'run_info.pkl', 'trial_0.pkl']
     assert len(res[0]['cmts'].query_history) == 2 and len(res[0]['cmts'].score_history) == 2
 
 
