@@ -346,3 +346,33 @@ def test_merged_lml_group_equals_single_passes(monkeypatch):
         merged = hp_search._lml_many(jobs)
         for a, (b, _) in zip(single, merged):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_driver_processes_share_one_gpu(tmp_path):
+    """``torchrun --nproc-per-node 2`` on ONE GPU: both ranks use the device (time-sliced), the
+    trials are sharded over them and gathered through gloo; the pickles equal the single-process
+    run's (a trial's stream is keyed by its global id)."""
+    import pickle
+    import subprocess
+    import sys
+    import torch
+    from ocbo_b200 import ocbo
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    if torch.cuda.device_count() != 1:
+        pytest.skip('needs exactly one visible GPU')
+    f = tmp_path / 'pp.txt'
+    f.write_text('--run_id pp\n--trials 4\n--max_capital 4\n--tune_every 1\n--tuning_methods ml\n'
+                 '--methods mts\n--functions branin,parabaloid\n--trials_in_flight 2\n--write_dir %s\n' % tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                    '--master-addr', '127.0.0.1', '--master-port', '29533', '-m', 'ocbo_b200.ocbo',
+                    '--options', str(f)], check=True, env=env, cwd=root, timeout=240)
+    B200GPFitter._fit_counter = 0
+    ref = ocbo.run(argv=['--options', str(f), '--write_dir', str(tmp_path / 'one')])
+    for t in range(4):
+        with open(tmp_path / 'pp' / ('trial_%d.pkl' % t), 'rb') as fh:
+            got = pickle.load(fh)['mts']
+        assert got.choice_timeline == ref[t]['mts'].choice_timeline
+        assert got.total_best == ref[t]['mts'].total_best

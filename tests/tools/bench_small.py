@@ -191,7 +191,7 @@ def measure_revi(cpu_reps=1):
     return res
 
 
-def measure_bo_loop(capital=40, in_flight=(8, 32)):
+def measure_bo_loop(capital=40, in_flight=(8, 32), procs=8):
     """Whole BO iterations/s through the drivers that read the reference's option files
     (ocbo_b200.ocbo / cts_ocbo): hyper-parameter re-fit (64-candidate LML pass) + posterior draw
     + decision + objective evaluation + bookkeeping every iteration, one method, one trial -- and,
@@ -227,6 +227,15 @@ def measure_bo_loop(capital=40, in_flight=(8, 32)):
                 for R in in_flight:
                     dt = timed(['--trials', str(R), '--trials_in_flight', str(R)])
                     res[name]['b200_iterations_per_s_%d_in_flight' % R] = R * capital / dt
+    # ... and with several driver processes sharing this GPU (what ``torchrun --nproc-per-node P``
+    # on one GPU gives, ocbo_b200/dist.py:init_from_env): the per-trial Python runs in parallel
+    if procs:
+        from tests.tools import bench_procs
+        for name in ('set2d', 'rand6d', 'jointbran'):
+            try:
+                res[name]['processes_sharing_the_gpu'] = bench_procs.measure(name, procs, 8, capital)
+            except Exception as exc:  # a measurement, not a dependency of the bench line
+                res[name]['processes_sharing_the_gpu'] = {'error': repr(exc)}
     return res
 
 
