@@ -39,6 +39,8 @@ def measure(name, P, R=8, capital=40):
         ready, go = os.path.join(tmp, 'ready_'), os.path.join(tmp, 'go')
         code = CHILD % dict(root=ROOT, drv='ocbo' if kind == 'd' else 'cts_ocbo', argv=argv, ready=ready, go=go)
         env = dict(os.environ, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+        for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'LOCAL_WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):
+            env.pop(k, None)  # independent processes: no launcher, no process group
         procs = [subprocess.Popen([sys.executable, '-c', code], stdout=subprocess.PIPE, text=True, env=env)
                  for _ in range(P)]
         t_end = time.time() + 300
