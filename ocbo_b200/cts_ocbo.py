@@ -123,6 +123,7 @@ def run(argv=None):
             with open(os.path.join(created, name), 'wb') as fh:
                 pkl.dump(obj, fh, protocol=2)
     width = max(1, int(options.trials_in_flight or 1))
+    LAST_MERGE_STATS[0] = None
     if width > 1 or world_size > 1:
         # trials advance in lockstep and share their device passes (ocbo_b200/inflight.py);
         # their numpy streams are keyed by trial, so the shard a rank runs does not matter
