@@ -1,0 +1,1 @@
+"""Parity and host-logic tests (pytest -m gpu / -m "not gpu")."""
