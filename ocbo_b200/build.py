@@ -55,5 +55,28 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+HOSTPACK_SRC = os.path.join(CSRC, 'hostpack.c')
+
+
+def hostpack_path():
+    import sysconfig
+    return os.path.join(LIB_DIR, '_hostpack' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+
+
+def build_hostpack(force=False):
+    """gcc: the CPython staging helper (csrc/hostpack.c; host-side copies only, no CUDA)."""
+    import sysconfig
+    import numpy as np
+    out = hostpack_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(HOSTPACK_SRC):
+        return out
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [os.environ.get('CC', 'gcc'), '-O2', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'],
+           '-I', np.get_include(), HOSTPACK_SRC, '-o', out]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_hostpack(force='--force' in sys.argv))

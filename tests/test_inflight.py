@@ -161,8 +161,34 @@ def test_pack_rows_pads_ragged_inputs():
         assert np.array_equal(out[b, :len(a)], a) and not out[b, len(a):].any()
     out1, _, n1 = engine.pack_rows([np.zeros((0, 2))], 2)
     assert out1.shape == (1, 128, 2) and n1 == 128 and not out1.any()
-    out2 = engine.pack_rows([a[:, :1] for a in arrs], 1, 384)[0]
+    out2 = engine.pack_rows([a[:, :1] for a in arrs], 1, 384)[0]     # (non-contiguous inputs)
     assert out2.shape == (5, 384, 1) and np.array_equal(out2[2, :130, 0], arrs[2][:, 0])
+
+
+def test_pack_rows_c_helper_equals_the_numpy_loop(monkeypatch):
+    """csrc/hostpack.c (built by build()) and the fallback loop give the same block; inputs the
+    helper does not take (strided, integer) go through the loop."""
+    from ocbo_b200 import build, engine
+    build.build_hostpack()
+    helper = engine._load_hostpack()
+    assert helper is not None
+    rs = np.random.RandomState(1)
+    cases = [[rs.uniform(size=(n, 4)) for n in (3, 0, 129, 40)],
+             [rs.uniform(size=(7, 1)), rs.uniform(size=(2, 1))],
+             [rs.uniform(size=(6, 8))[:, ::2], np.arange(8).reshape(2, 4)]]
+    for arrs in cases:
+        width = arrs[0].shape[1]
+        monkeypatch.setattr(engine, '_HOSTPACK', helper)
+        fast = engine.pack_rows(arrs, width)
+        monkeypatch.setattr(engine, '_HOSTPACK', None)
+        slow = engine.pack_rows(arrs, width)
+        assert np.array_equal(fast[0], slow[0]) and fast[1:] == slow[1:]
+    out = np.empty((2, 128, 4))
+    assert helper.pack_rows(cases[0][:2], 4, 128, out) == [3, 0] and not out[0, 3:].any()
+    with pytest.raises(TypeError):
+        helper.pack_rows([np.arange(4)], 4, 128, np.empty((1, 128, 4)))
+    with pytest.raises(ValueError):
+        helper.pack_rows([np.zeros((200, 4))], 4, 128, np.empty((1, 128, 4)))
 
 
 def _timeline(hist, names):
