@@ -158,7 +158,7 @@ def _mts_launch(gps, samp_pts_list, n_old_list, Z_list, members, D, kind, chunk)
     Xs_ = [c.X_array() for c in cores]
     ys_ = [c.Y_array() for c in cores]
     thetas = _thetas(cores, D)
-    pts = [np.asarray(samp_pts_list[f], dtype=np.float64).reshape(-1, D) for f in members]
+    pts = [samp_pts_list[f] for f in members]
     segs = [[0, n_old_list[f], len(samp_pts_list[f])] for f in members]
     Zs = [Z_list[f] for f in members]
 

@@ -377,39 +377,48 @@ _HOSTPACK = _load_hostpack() if os.environ.get('OCBO_HOSTPACK', '1') != '0' else
 
 
 def pack_rows(arrs, width, n_pad=None, stage=False):
-    """Ragged list of (n_b, width) arrays -> zero-padded [B, n_pad, width], the lengths, n_pad.
-    With ``stage`` the block is written straight into the active staging arena and the DEVICE
-    view is returned in its place (no intermediate array: with R trials in flight a pass
-    stages hundreds of problems, several MB).  The copies run in C (csrc/hostpack.c: a memcpy
-    and a memset per problem) when the helper is built and the inputs are contiguous float64
-    arrays, else as a loop of slice assignments (~1 us each; a concatenate + fancy-index
-    scatter measured 2.7x slower than that loop)."""
+    """Ragged list of arrays holding n_b rows of ``width`` values -> zero-padded
+    [B, n_pad, width], the row counts, n_pad.  With ``stage`` the block is written straight into
+    the active staging arena and the DEVICE view is returned in its place (no intermediate
+    array: with R trials in flight a pass stages hundreds of problems, several MB).  The copies
+    run in C (csrc/hostpack.c: a memcpy and a memset per problem, no per-problem numpy call)
+    when the helper is built and the inputs are contiguous float64 arrays; anything else
+    (lists, strided or integer arrays) is converted and copied by a loop of slice assignments
+    (~1 us each; a concatenate + fancy-index scatter measured 2.7x slower than that loop)."""
     B = len(arrs)
     lens = [len(a) for a in arrs]
-    if n_pad is None:
-        n_pad = pad_to(max(lens + [1]))
-    region = _ACTIVE[-1].alloc((B, n_pad, width), F64) if stage and _ACTIVE else None
-    out = region[0] if region is not None else np.empty((B, n_pad, width))
+    pad = pad_to(max(lens + [1])) if n_pad is None else n_pad
+    arena = _ACTIVE[-1] if stage and _ACTIVE else None
+    mark = arena.used if arena is not None else 0
+    region = arena.alloc((B, pad, width), F64) if arena is not None else None
+    out = region[0] if region is not None else np.empty((B, pad, width))
     done = False
     if _HOSTPACK is not None and B:
         try:
-            done = _HOSTPACK.pack_rows(arrs, width, n_pad, out) == lens
+            done = _HOSTPACK.pack_rows(arrs, width, pad, out) == lens
         except (TypeError, ValueError):
             done = False
     if not done:
+        arrs = [np.asarray(a, dtype=np.float64).reshape(-1, width) for a in arrs]
+        lens = [len(a) for a in arrs]
+        if n_pad is None and pad_to(max(lens + [1])) != pad:  # (row counts only known now)
+            pad = pad_to(max(lens + [1]))
+            if arena is not None:
+                arena.used = mark
+                region = arena.alloc((B, pad, width), F64)
+            out = region[0] if region is not None else np.empty((B, pad, width))
         out[...] = 0.0
         for b, a in enumerate(arrs):
             if lens[b]:
                 out[b, :lens[b]] = a
     if stage:
-        return (region[1] if region is not None else _h2d(out)), lens, n_pad
-    return out, lens, n_pad
+        return (region[1] if region is not None else _h2d(out)), lens, pad
+    return out, lens, pad
 
 
 def upload_points(B, D, pts_list):
     """Candidate sets -> (Xs [B, m_pad, D], mv device, mv host, m_pad)."""
-    Xd, mv, m_pad = pack_rows([np.asarray(p, dtype=np.float64).reshape(-1, D) for p in pts_list], D,
-                              stage=True)
+    Xd, mv, m_pad = pack_rows(pts_list, D, stage=True)
     return Xd, _h2d(np.asarray(mv, dtype=np.int32), I32), mv, m_pad
 
 
@@ -427,10 +436,8 @@ class DevicePosterior(object):
         B, D = len(X_list), int(dim)
         if D < 1 or D > _lib.MAX_DIM:
             raise ValueError('input dimension must be in [1, %d]' % _lib.MAX_DIM)
-        Xd, nv_host, n_pad = pack_rows([np.asarray(x, dtype=np.float64).reshape(-1, D) for x in X_list],
-                                       D, stage=True)
-        yd = pack_rows([np.asarray(y, dtype=np.float64).reshape(-1, 1) for y in y_list], 1, n_pad,
-                       stage=True)[0].view(B, n_pad)
+        Xd, nv_host, n_pad = pack_rows(X_list, D, stage=True)
+        yd = pack_rows(y_list, 1, n_pad, stage=True)[0].view(B, n_pad)
         theta_host = np.asarray(thetas, dtype=np.float64).reshape(B, 3 + D)
         return (Xd, yd, _h2d(theta_host), _h2d(np.asarray(nv_host, dtype=np.int32), I32), nv_host)
 
@@ -748,9 +755,8 @@ def knowledge_gradients(judge_means, ld_means, inter, cand_var, noise, C, G, E):
 def pad_normals(Z_list, mv, m_pad, S):
     """Host normals [(m_b, S)] -> device [B, m_pad, S_pad] (zero padded)."""
     S_pad = S if S <= 8 else pad_to(S, 64)
-    Zs = [np.asarray(z, dtype=np.float64).reshape(-1, S) for z in Z_list]
     if S_pad == S:
-        return pack_rows(Zs, S, m_pad, stage=True)[0]
+        return pack_rows(Z_list, S, m_pad, stage=True)[0]
     Zp = np.zeros((len(Z_list), m_pad, S_pad))
-    Zp[:, :, :S] = pack_rows(Zs, S, m_pad)[0]
+    Zp[:, :, :S] = pack_rows(Z_list, S, m_pad)[0]
     return _h2d(Zp)
