@@ -109,13 +109,16 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     return inflight.merge('mts', (gps, samp_pts_list, n_old_list, Z_list), _many(_mts_flat))
 
 
-PIPELINE_MIN = 64  # problems per chunk: a larger pass is split so that staging overlaps the device
+import os as _os
+
+PIPELINE_MIN = int(_os.environ.get('OCBO_PIPELINE_MIN', '64'))  # problems per chunk of a split pass
+PIPELINE_MAX_CHUNKS = int(_os.environ.get('OCBO_PIPELINE_CHUNKS', '3'))
 
 
 def _chunks(members):
     """A merged pass of hundreds of problems is host-bound (staging ~6 us per problem, then the
     device runs while the host waits): split it, enqueue chunk k and stage chunk k + 1 meanwhile."""
-    n = min(3, len(members) // PIPELINE_MIN) if engine.graphs_enabled() else 1
+    n = min(PIPELINE_MAX_CHUNKS, len(members) // PIPELINE_MIN) if engine.graphs_enabled() else 1
     if n < 2:
         return [members]
     step = (len(members) + n - 1) // n
@@ -185,7 +188,8 @@ def _mts_launch(gps, samp_pts_list, n_old_list, Z_list, members, D, kind, chunk)
         _, mx_, ag_ = tail()
         return [mx_, ag_, post_.info, pend.info, pend.rung]
 
-    plan.run(st_now, [], body, wait=False)
+    # chunk k > 0 replays on its own stream: the chunks' device work overlaps too
+    plan.run(st_now, [], body, wait=False, stream=engine.chunk_stream(chunk) if chunk else None)
     return members, D, kind, stage, plan
 
 

@@ -233,11 +233,11 @@ class StepPlan(object):
     def staging(self):
         return _PlanStaging(self)
 
-    def run(self, staged, ext, body, wait=True):
+    def run(self, staged, ext, body, wait=True, stream=None):
         """body(staged, ext) -> list of device tensors; returns them as numpy arrays.  With
         ``wait=False`` the replay is only enqueued (the caller stages its next chunk while this
-        one runs) and ``results()`` synchronises later."""
-        stream = torch.cuda.current_stream()
+        one runs) and ``results()`` synchronises later; ``stream`` replays the graph on another
+        stream than the current one (chunks of one pass overlap on the device)."""
         if self.graph is None:
             self.staged, self.used0 = staged, self.used
             self.ext = [t.clone() for t in ext]
@@ -257,12 +257,19 @@ class StepPlan(object):
                 raise RuntimeError('StepPlan: staged layout changed under a fixed shape key')
             for own, t in zip(self.ext, ext):
                 own.copy_(t, non_blocking=True)
-        self.graph.replay()
+        self._stream = stream if stream is not None else torch.cuda.current_stream()
+        if stream is not None:
+            if ext:  # (the copies into the plan's own buffers were enqueued on the current stream)
+                stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                self.graph.replay()
+        else:
+            self.graph.replay()
         self.replays += 1
         return self.results() if wait else None
 
     def results(self):
-        torch.cuda.current_stream().synchronize()
+        self._stream.synchronize()
         return [h.numpy() for h in self.outs_host]
 
 
@@ -596,6 +603,16 @@ def ladder_rungs(A, A0, invd, info, rung, nv, exponents):
 
 
 _SIDE = {}
+_CHUNK_STREAMS = {}
+
+
+def chunk_stream(k):
+    """Persistent stream number k (per device) for the chunks of a split pass."""
+    key = (torch.cuda.current_device(), k)
+    s = _CHUNK_STREAMS.get(key)
+    if s is None:
+        s = _CHUNK_STREAMS[key] = torch.cuda.Stream()
+    return s
 
 
 def _side_stream():
