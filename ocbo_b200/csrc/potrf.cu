@@ -221,22 +221,66 @@ __global__ void __launch_bounds__(256) solve_alpha_lml_kernel(SolveArgs a) {
   for (int i = tid; i < n; i += 256) r[i] = (i < nv) ? y[i] - mu0 : 0.0;
   __syncthreads();
   // forward
+  // Each warp owns rows warp, warp + 8, ... of a block and walks RU of them at a time: the row
+  // dot products are independent, so their loads are in flight together (one row at a time was
+  // one exposed HBM latency per row and 8 warps x 256 B in flight per SM: 254 us for 64 problems
+  // of n = 768, 0.8 TB/s, "long scoreboard" 31 cycles per issue in ncu).  Measured for (rows at a
+  // time, k chunks per step): (16, 1) 127 us, (4, 4) 145, (16, 2) 181, (4, 2) 186, (2, 4) 192,
+  // (8, 2) 209, (8, 4) 314.  Every row keeps its own lane-strided accumulation order, so the
+  // values are those of the one-row loop bit for bit.
+#ifndef OCBO_SOLVE_RU
+#define OCBO_SOLVE_RU 16
+#endif
+  constexpr int RU = OCBO_SOLVE_RU;
+#ifndef OCBO_SOLVE_KQ
+#define OCBO_SOLVE_KQ 1
+#endif
+  constexpr int KQ = OCBO_SOLVE_KQ;  // k chunks of 32 per step (base is a multiple of 128)
   for (int I = 0; I < nblk; ++I) {
     const int base = I * NB;
-    for (int rr = warp; rr < NB; rr += 8) {
-      const double* Lrow = L + (size_t)(base + rr) * a.ldl;
-      double s = 0.0;
-      for (int k = lane; k < base; k += 32) s = fma(Lrow[k], r[k], s);
-      s = warp_sum(s);
-      if (lane == 0) tmp[rr] = r[base + rr] - s;
+    for (int rr0 = warp; rr0 < NB; rr0 += 8 * RU) {
+      double s[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) s[u] = 0.0;
+      const double* Lrow = L + (size_t)(base + rr0) * a.ldl;
+      // (all RU x KQ loads of a step are issued before the first use -- written out, the
+      // compiler otherwise keeps only two or three in flight)
+      for (int k = lane; k < base; k += 32 * KQ) {
+        double v[KQ][RU];
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+#pragma unroll
+          for (int u = 0; u < RU; ++u) v[q][u] = Lrow[(size_t)(8 * u) * a.ldl + k + 32 * q];
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) {
+          const double rk = r[k + 32 * q];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) s[u] = fma(v[q][u], rk, s[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const double t = warp_sum(s[u]);
+        if (lane == 0) tmp[rr0 + 8 * u] = r[base + rr0 + 8 * u] - t;
+      }
     }
     __syncthreads();
     const double* Ib = Inv + (size_t)I * NB * NB;
-    for (int rr = warp; rr < NB; rr += 8) {
-      double s = 0.0;
-      for (int k = lane; k <= rr; k += 32) s = fma(Ib[rr * NB + k], tmp[k], s);
-      s = warp_sum(s);
-      if (lane == 0) r[base + rr] = s;
+    for (int rr0 = warp; rr0 < NB; rr0 += 8 * RU) {
+      double s[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) s[u] = 0.0;
+      for (int k = lane; k <= rr0 + 8 * (RU - 1); k += 32) {
+        const double tk = tmp[k];
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+          if (k <= rr0 + 8 * u) s[u] = fma(Ib[(rr0 + 8 * u) * NB + k], tk, s[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const double t = warp_sum(s[u]);
+        if (lane == 0) r[base + rr0 + 8 * u] = t;
+      }
     }
     __syncthreads();
   }
