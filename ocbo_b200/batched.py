@@ -8,6 +8,7 @@ sequence of batched kernel launches.  Normals are passed in (drawn by the
 caller in the reference's order) so a seeded run consumes the global numpy
 stream exactly like the reference.
 """
+import os
 from collections import defaultdict
 
 import numpy as np
@@ -109,10 +110,8 @@ def mts_step(gps, samp_pts_list, n_old_list, Z_list):
     return inflight.merge('mts', (gps, samp_pts_list, n_old_list, Z_list), _many(_mts_flat))
 
 
-import os as _os
-
-PIPELINE_MIN = int(_os.environ.get('OCBO_PIPELINE_MIN', '64'))  # problems per chunk of a split pass
-PIPELINE_MAX_CHUNKS = int(_os.environ.get('OCBO_PIPELINE_CHUNKS', '3'))
+PIPELINE_MIN = int(os.environ.get('OCBO_PIPELINE_MIN', '64'))  # problems per chunk of a split pass
+PIPELINE_MAX_CHUNKS = int(os.environ.get('OCBO_PIPELINE_CHUNKS', '3'))
 
 
 def _chunks(members):
