@@ -231,7 +231,7 @@ def measure_bo_loop(capital=40, in_flight=(8, 32), procs=8):
     # on one GPU gives, ocbo_b200/dist.py:init_from_env): the per-trial Python runs in parallel
     if procs:
         from tests.tools import bench_procs
-        for name in ('set2d', 'rand6d', 'jointbran'):
+        for name in ('set2d', 'rand6d', 'jointbran', 'conth42'):
             try:
                 res[name]['processes_sharing_the_gpu'] = bench_procs.measure(name, procs, 8, capital)
             except Exception as exc:  # a measurement, not a dependency of the bench line
