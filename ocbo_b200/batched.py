@@ -323,23 +323,38 @@ class _PostView(object):
 def profile_step(gp, act_sets, Z_list):
     """Continuous MTS inner loop (src/cstrats/profile_cts.py:76-105) for all
     contexts at once.  Returns (sample_max, sample_argmax, mean_max, mean_argmax,
-    sample_at_mean_argmax) as arrays over contexts."""
+    sample_at_mean_argmax) as arrays over contexts.  With trials in flight the steps of the
+    trials are enqueued one after the other, each on its own stream, and collected afterwards:
+    trial k's device pass runs while trial k + 1 is staged and its posterior built."""
+    return inflight.merge('cts', (gp, act_sets, Z_list), _profile_many)
+
+
+def _profile_many(requests):
+    if len(requests) == 1 or not engine.graphs_enabled():
+        return [_profile_finish(_profile_launch(*r)) for r in requests]
+    launched = [_profile_launch(*r, slot=k) for k, r in enumerate(requests)]
+    return [_profile_finish(h) for h in launched]
+
+
+def _reduce_means(mean, Fm, seg):
+    mmx, mag = engine.segment_argmax(mean.unsqueeze(2), 1, seg)
+    s_at = Fm[:, :, 0].gather(1, mag[:, 0, :].long())[:, 0]
+    return mmx[:, 0, 0], mag[:, 0, 0], s_at
+
+
+def _profile_launch(gp, act_sets, Z_list, slot=None):
+    """Stage one trial's profile step and enqueue its plan (slot k: plan and stream number k;
+    None: the current stream).  Nothing is read back here."""
     core = gp.gp_core
     if core._post_raw is None:
         core.build_posterior()
-    base = core._post_raw  # possibly unverified: checked with the results, below
+    base = core._post_raw  # possibly unverified: checked with the results, in _profile_finish
     B, D = len(act_sets), base.D
     segs = [[0, len(a)] for a in act_sets]
-
-    def reduce_means(mean, Fm, seg):
-        mmx, mag = engine.segment_argmax(mean.unsqueeze(2), 1, seg)
-        s_at = Fm[:, :, 0].gather(1, mag[:, 0, :].long())[:, 0]
-        return mmx[:, 0, 0], mag[:, 0, 0], s_at
-
-    res = None
+    plan = None
     if engine.graphs_enabled():
         m_pad = engine.pad_to(max([len(a) for a in act_sets] + [1]))
-        plan = engine.StepPlan.get(('cts', base.kind, D, B, base.n_pad, m_pad),
+        plan = engine.StepPlan.get(('cts', base.kind, D, B, base.n_pad, m_pad, slot),
                                    _arena_bytes(B, 0, m_pad, D, 1, False))
         view = _PostView(base)
         with plan.staging():
@@ -349,25 +364,34 @@ def profile_step(gp, act_sets, Z_list):
             post = SharedPosterior(_PostView(base, ext), B)
             mean, pend, tail = _enqueue_tail(post, st, engine.GRAPH_SPEC_RUNGS)
             Fm, mx, ag = tail()
-            return [mx, ag] + list(reduce_means(mean, Fm, st[5])) + [pend.info, pend.rung]
+            return [mx, ag] + list(_reduce_means(mean, Fm, st[5])) + [pend.info, pend.rung]
 
-        mx, ag, mmx, mag, s_at, info_s, rung = plan.run(staged, view.tensors(), body)
+        plan.run(staged, view.tensors(), body, wait=False,
+                 stream=engine.chunk_stream(slot + 1) if slot is not None else None)
+    return gp, act_sets, Z_list, base, segs, plan
+
+
+def _profile_finish(handle):
+    gp, act_sets, Z_list, base, segs, plan = handle
+    core = gp.gp_core
+    B, D = len(act_sets), base.D
+    if plan is not None:
+        mx, ag, mmx, mag, s_at, info_s, rung = plan.results()
         if base.unchecked and not core._verify(base):
-            return profile_step(gp, act_sets, Z_list)  # K needed the ladder: redo on the rebuilt factor
+            # K needed the ladder: redo on the rebuilt factor
+            return _profile_finish(_profile_launch(gp, act_sets, Z_list))
         if not (info_s > 0).any():
-            res = tuple(np.array(v) for v in (mx[:, 0, 0], ag[:, 0, 0], mmx, mag, s_at))
             core.last_sample_jitter = _rungs(rung)
-    if res is None:
-        post = SharedPosterior(base, B)
-        with engine.staging():
-            staged = _stage_candidates(B, D, act_sets, Z_list, segs)
-        mx, ag, mean, Fm, mv, jit = _sample_reduce(post, staged)
-        if base.unchecked and not core._verify(base):
-            return profile_step(gp, act_sets, Z_list)
-        mmx, mag, s_at = [t.cpu().numpy() for t in reduce_means(mean, Fm, staged[5])]
-        core.last_sample_jitter = jit
-        res = (mx[:, 0], ag[:, 0], mmx, mag, s_at)
-    return res
+            return tuple(np.array(v) for v in (mx[:, 0, 0], ag[:, 0, 0], mmx, mag, s_at))
+    post = SharedPosterior(base, B)
+    with engine.staging():
+        staged = _stage_candidates(B, D, act_sets, Z_list, segs)
+    mx, ag, mean, Fm, mv, jit = _sample_reduce(post, staged)
+    if base.unchecked and not core._verify(base):
+        return _profile_finish(_profile_launch(gp, act_sets, Z_list))
+    mmx, mag, s_at = [t.cpu().numpy() for t in _reduce_means(mean, Fm, staged[5])]
+    core.last_sample_jitter = jit
+    return (mx[:, 0], ag[:, 0], mmx, mag, s_at)
 
 
 # ---------------------------------------------------------------------------

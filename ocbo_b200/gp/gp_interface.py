@@ -110,8 +110,12 @@ class B200GPFitter(GPFitterWrapper):
     _fit_counter = 0
 
     def _init_gpf(self):
-        if isinstance(self.x_data, np.ndarray) and self.x_data.ndim == 2 and len(self.x_data):
-            self._X = np.ascontiguousarray(self.x_data, dtype=np.float64)  # (n, D) array: as is
+        try:  # an (n, D) array or a list of n equal-length points: one conversion, not n
+            X2 = np.asarray(self.x_data, dtype=np.float64)
+        except (ValueError, TypeError):
+            X2 = None
+        if X2 is not None and X2.ndim == 2 and len(X2):
+            self._X = np.ascontiguousarray(X2)
             self.dim = self._X.shape[1]
         else:
             X = [np.asarray(x, dtype=np.float64).ravel() for x in self.x_data]

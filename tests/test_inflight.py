@@ -235,8 +235,9 @@ def test_discrete_driver_in_flight_equals_the_trials_alone(tmp_path, methods, tu
 
 @pytest.mark.gpu
 def test_continuous_driver_in_flight(tmp_path):
-    """cts_ocbo with two trials in flight: only the hyper-parameter fits merge (the profile step
-    shares ONE posterior over its 50 contexts and stays per trial); results equal the trials alone."""
+    """cts_ocbo with two trials in flight: the hyper-parameter fits and the policy-score evaluations
+    merge; the profile steps (ONE posterior shared by 50 contexts, per trial) are enqueued together
+    on their own streams; results equal the trials alone."""
     from ocbo_b200 import cts_ocbo
     from ocbo_b200.gp.gp_interface import B200GPFitter
     f = tmp_path / 'cfl.txt'
@@ -247,6 +248,7 @@ def test_continuous_driver_in_flight(tmp_path):
     B200GPFitter._fit_counter = 0
     got = cts_ocbo.run(argv=argv + ['--trials_in_flight', '2'])
     assert cts_ocbo.LAST_MERGE_STATS[0]['lml'][1] == 2 * cts_ocbo.LAST_MERGE_STATS[0]['lml'][0]
+    assert cts_ocbo.LAST_MERGE_STATS[0]['cts'] == (3, 6)  # the trials' profile steps are enqueued together
     B200GPFitter._fit_counter = 0
     alone0 = cts_ocbo.run(argv=argv + ['--trials', '1'])
     a = [np.ravel(q.pt).tolist() + [q.reward] for q in got[0]['cmts'].query_history]
