@@ -13,19 +13,21 @@ import numpy as np
 
 from .multi_opt import MultiOpt
 from .. import batched, rng
-from ..util import uniform_box
+from ..util import Box
 
 
 class MTS(MultiOpt):
 
     def decide_next_query(self):
         queries = self._get_queried_pts()
+        boxes = self.__dict__.get('_boxes')
+        if boxes is None:  # (the tasks' bounds as arrays, converted once per strategy object)
+            boxes = self._boxes = [Box(d) for d in self.domains]
         samp_pts, n_old, normals = [], [], []
         for f_idx, f_name in enumerate(self.f_names):
             f_qs = queries[f_name]
-            low, high = zip(*self.domains[f_idx])
-            rand_pts = uniform_box(low, high, self.options.max_opt_evals)
-            pts = np.concatenate([f_qs.reshape(-1, len(low)), rand_pts], axis=0)
+            rand_pts = boxes[f_idx].draw(self.options.max_opt_evals)
+            pts = np.concatenate([f_qs.reshape(-1, rand_pts.shape[1]), rand_pts], axis=0)
             samp_pts.append(pts)
             n_old.append(len(f_qs))
             normals.append(rng.normals((len(pts), 1)))
