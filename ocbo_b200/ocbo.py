@@ -16,6 +16,7 @@ trials are sharded over the ranks, trial t on rank t mod W, with one gather of t
 """
 import os
 import pickle as pkl
+from argparse import Namespace
 import sys
 from copy import copy, deepcopy
 
@@ -166,7 +167,9 @@ def run(argv=None):
         if os.path.isdir(created):
             raise ValueError('Run ID already exists: %s' % options.run_id)
         os.makedirs(created)
-        clones = [deepcopy({k: v for k, v in vars(f).items() if k != 'function'}) for f in f_infos]
+        # (:229-235) the task Namespaces with ``function = None``: callables do not pickle
+        clones = [Namespace(function=None, **deepcopy({k: v for k, v in vars(f).items() if k != 'function'}))
+                  for f in f_infos]
         for name, obj in (('run_info.pkl', options), ('rand_state.pkl', rand_state),
                           ('functions.pkl', clones)):
             with open(os.path.join(created, name), 'wb') as fh:

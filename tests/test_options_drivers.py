@@ -233,3 +233,40 @@ def test_discrete_driver_pre_tuned_modes(tmp_path, mode):
     for r in res + res_fl:
         for h in r.values():
             assert len(h.choice_timeline) == 3 and np.all(np.isfinite(h.total_best))
+
+
+@pytest.mark.refsrc
+def test_results_feed_the_reference_analysis_functions(tmp_path, monkeypatch):
+    """the per-trial results keep the reference's Namespace schema -- its own
+    analysis helpers (src/util/post_util.py:32-90, imported where they lie) assemble them.  The
+    run uses the numpy oracle engine behind the driver (host logic only, no GPU)."""
+    import importlib.util
+    import pickle
+    from ocbo_b200 import batched, ocbo
+    from ocbo_b200.strategies import joint_opt, multi_opt
+    from oracle import gp_numpy as o
+    from tests.test_host_strategies import _Fitter, _fake_mts_step
+    spec = importlib.util.spec_from_file_location('ref_post_util', '/root/reference/src/util/post_util.py')
+    post_util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(post_util)
+    fitter = lambda engine, x, y, opts: _Fitter(x, y, opts)
+    monkeypatch.setattr(multi_opt, 'get_gp_fitter', fitter)
+    monkeypatch.setattr(joint_opt, 'get_gp_fitter', fitter)
+    monkeypatch.setattr(batched, '_mts_flat', _fake_mts_step)
+    o.EuclideanGPFitter._fit_counter = 0
+    f = tmp_path / 'sch.txt'
+    f.write_text('--run_id sch\n--trials 3\n--max_capital 4\n--tune_every 1\n--tuning_methods ml\n'
+                 '--methods mts,random\n--functions branin,parabaloid\n--write_dir %s\n' % tmp_path)
+    ocbo.run(argv=['--options', str(f)])
+    data = []
+    for t in range(3):  # (post_util.load_results opens the pickles in text mode: a python-2 idiom)
+        with open(tmp_path / 'sch' / ('trial_%d.pkl' % t), 'rb') as fh:
+            data.append(pickle.load(fh))
+    with open(tmp_path / 'sch' / 'functions.pkl', 'rb') as fh:
+        f_infos = pickle.load(fh)
+    totals = post_util.get_total_best_mats(data)
+    assert set(totals) == {'mts', 'Random'} and totals['mts'].shape == (3, 4)
+    assert post_util.get_choice_timelines(data)['mts'].shape == (3, 4)
+    assert f_infos[0].function is None and f_infos[0].max_val is not None  # (src/ocbo.py:229-235)
+    name = f_infos[0].name
+    assert len(post_util.get_best_for_function(name, data)['mts']) == 3
