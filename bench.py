@@ -30,7 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_OBS, N_TASK, N_ACT, N_DRAW, DIM = 1024, 64, 128, 256, 6
+from ocbo_b200.workload import (DIM, N_ACT, N_DRAW, N_OBS, N_TASK, SEED,  # noqa: E402  (numpy only:
+                                make_trial_inputs, step_flops, workload_config)  # no torch, no .so)
+
 METRIC = 'GP joint Thompson samples/sec (m=8192 grid, fp64)'
 UNIT = 'samples/s'
 
@@ -46,13 +48,11 @@ def parse():
     ap.add_argument('--cpu-trials', type=int, default=2, help='trials timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-peaks', action='store_true')
+    ap.add_argument('--no-one-thread', action='store_true')
+    ap.add_argument('--sweep-trials', type=int, default=512,
+                    help='trials of the fixed-work (strong-scaling) leg; 0 skips it')
+    ap.add_argument('--no-parity', action='store_true')
     return ap.parse_args()
-
-
-def workload_name():
-    return ('sweep: n=%d obs, m=%d candidates (T=%d x A=%d), d=%d, S=%d draws/trial, SE-ARD '
-            'bw ctx 0.25 / act 0.05, scale 1, noise 1e-2, mu0 0'
-            % (N_OBS, N_TASK * N_ACT, N_TASK, N_ACT, DIM, N_DRAW))
 
 
 # --------------------------------------------------------------------------
@@ -146,21 +146,36 @@ def use_all_blas_threads():
         _BLAS_LIMIT.append(None)
 
 
-def cpu_step_seconds(trial):
-    """One full-size trial-step of the CPU restatement (numpy + LAPACK, all BLAS threads)."""
-    from oracle import sweep_step
-    from ocbo_b200.sweep import make_trial_inputs
-    use_all_blas_threads()
+def cpu_step(trial, threads=None, with_philox=False):
+    """One full-size trial-step of the CPU restatement (numpy + LAPACK).  Returns
+    (seconds, (task, action, gain, samples, mean)): the timing is the cpu_baseline figure,
+    the results are what the device's trial is checked against (``with_philox``: the
+    oracle is fed the device RNG's definition of the normals, generated outside the clock)."""
+    from oracle import philox, sweep_step
     X, y, Xs = make_trial_inputs(trial, N_OBS, N_TASK, N_ACT)
+    Z = philox.normals(SEED, trial, N_TASK * N_ACT, N_DRAW) if with_philox else None
     np.random.seed(trial)
-    t0 = time.perf_counter()
-    sweep_step.step(X, y, Xs, N_TASK, N_DRAW)
-    return time.perf_counter() - t0
+    use_all_blas_threads()
+    import contextlib
+    ctx = contextlib.nullcontext()
+    if threads is not None:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=threads, user_api='blas')
+    with ctx:
+        t0 = time.perf_counter()
+        out = sweep_step.step(X, y, Xs, N_TASK, N_DRAW, Z=Z, return_samples=True)
+        dt = time.perf_counter() - t0
+    return dt, out
+
+
+def cpu_step_seconds(trial):
+    return cpu_step(trial)[0]
 
 
 def run_reference(args):
     """Reference arm: the reference's own algorithm for this path on the host
-    cores (oracle port -- Dragonfly, which holds it, is not installable here)."""
+    cores (oracle port -- Dragonfly, which holds it, is not installable here).
+    Imports nothing of the product but its numpy-only workload generator."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -172,15 +187,23 @@ def run_reference(args):
     cores = cpu_threads()
     sample = '%d steps x 1 full-size trial (n=%d, m=%d, S=%d) per step' % (
         args.steps, N_OBS, N_TASK * N_ACT, N_DRAW)
+    one = None
+    if not args.no_one_thread:
+        try:
+            one = N_DRAW / cpu_step(args.warmup + args.steps, threads=1)[0]
+        except Exception:  # threadpoolctl missing: the all-cores figure stands alone
+            one = None
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': workload_name(), 'trials_per_step': 1,
-                   'note': 'numpy/LAPACK restatement of the Dragonfly path (oracle/), host cores only'},
+        'config': workload_config(),
+        'run': {'trials_per_step': 1,
+                'note': 'numpy/LAPACK restatement of the Dragonfly path (oracle/), host cores only'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': sample},
+                         'sample': sample, 'one_thread_value': one,
+                         'one_thread_sample': '1 full-size trial, BLAS limited to 1 thread'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -239,6 +262,45 @@ def measure_fp64_peaks(torch, lib_call, dev):
     return out
 
 
+def check_trial(torch, grp, trial, ref, acc):
+    """Headline-shape parity (outside every timed region): trial ``trial`` through the product's
+    host-buffer API against the oracle's results for the same inputs and the same normals.
+    Picks bit-exact for every draw; mean and samples to max(1e-8, 10 cond eps) relative
+    (cond(Sigma) ~ 4e5 at this shape); gains 1e-8."""
+    t_ref, a_ref, g_ref, F_ref, mu_ref, _ = ref
+    ids = [trial] * grp.B
+    inp = make_trial_inputs(trial, N_OBS, N_TASK, N_ACT)
+    task, act, gain = grp.step_host(ids, [inp] * grp.B)
+    torch.cuda.synchronize()
+    mean = grp.mean[0].cpu().numpy()
+    e_mean = float(np.max(np.abs(mean - mu_ref)) / np.max(np.abs(mu_ref)))
+    e_gain = float(np.max(np.abs(gain[0] - g_ref)) / np.max(np.abs(g_ref)))
+    e_samp = None
+    F = grp.samples_host(0) if hasattr(grp, 'samples_host') else None
+    if F is not None:
+        e_samp = float(np.max(np.abs(F - F_ref)) / np.max(np.abs(F_ref)))
+    tol = max(1e-8, 10 * 4.3e5 * 2.2e-16)
+    n_task = int(np.sum(task[0] != t_ref))
+    n_act = int(np.sum(act[0] != a_ref))
+    ok = (n_task == 0 and n_act == 0 and e_mean <= tol and e_gain <= tol
+          and (e_samp is None or e_samp <= tol))
+    acc = acc or {'ok': True, 'trials': [], 'draws_compared': 0, 'task_mismatches': 0,
+                  'action_mismatches': 0, 'max_rel_err_mean': 0.0, 'max_rel_err_gain': 0.0,
+                  'max_rel_err_samples': None, 'tolerance': tol,
+                  'against': 'oracle.sweep_step.step fed oracle.philox.normals, same trial inputs, '
+                             'n=%d m=%d S=%d' % (N_OBS, N_TASK * N_ACT, N_DRAW)}
+    acc['ok'] = bool(acc['ok'] and ok)
+    acc['trials'].append(trial)
+    acc['draws_compared'] += int(len(t_ref))
+    acc['task_mismatches'] += n_task
+    acc['action_mismatches'] += n_act
+    acc['max_rel_err_mean'] = max(acc['max_rel_err_mean'], e_mean)
+    acc['max_rel_err_gain'] = max(acc['max_rel_err_gain'], e_gain)
+    if e_samp is not None:
+        acc['max_rel_err_samples'] = max(acc['max_rel_err_samples'] or 0.0, e_samp)
+    return acc
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -275,7 +337,7 @@ def run_b200(args):
         for g in range(G):
             for b in range(B):
                 t = trial_id(step, g, b)
-                pool[t] = sweep.make_trial_inputs(t, N_OBS, N_TASK, N_ACT)
+                pool[t] = make_trial_inputs(t, N_OBS, N_TASK, N_ACT)
 
     def ids(step, g):
         return [trial_id(step, g, b) for b in range(B)]
@@ -350,11 +412,36 @@ def run_b200(args):
     value = samples_per_step * args.steps / (ms_resident * 1e-3)
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
 
-    # ---- single NCCL gather of the picks -----------------------------
-    if world > 1:
-        last = torch.from_numpy(np.stack([picks[-1][0], picks[-1][1]])).to(dev)
-        gathered = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
-        dist.gather(last, gathered, dst=0)
+    # ---- fixed work: the SAME --sweep-trials trials at every N (SURVEY 8e, configs[4]) -------
+    # trial r on rank r mod W through the host-buffer API, the one NCCL gather of the picks
+    # INSIDE the clock; the digest over all trials x draws must not depend on N.
+    sweep_fixed = None
+    if args.sweep_trials > 0:
+        from ocbo_b200 import dist as odist
+        ntr = args.sweep_trials
+        mine = {t: make_trial_inputs(t, N_OBS, N_TASK, N_ACT) for t in odist.shard_trials(ntr, rank, world)}
+        barrier()
+        t0 = time.perf_counter()
+        res = odist.run_sweep(ntr, None, mine.__getitem__, groups=groups)
+        barrier()
+        wall = time.perf_counter() - t0
+        wt = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            import hashlib
+            task_all, act_all, gain_all = res
+            h = hashlib.sha256()
+            h.update(np.ascontiguousarray(task_all).tobytes())
+            h.update(np.ascontiguousarray(act_all).tobytes())
+            sweep_fixed = {'trials': ntr, 'draws_per_trial': N_DRAW, 'wall_s': float(wt[0]),
+                           'samples_per_s': ntr * N_DRAW / float(wt[0]),
+                           'picks_sha256_16': h.hexdigest()[:16],
+                           'picks_sum': int(task_all.astype(np.int64).sum() + act_all.astype(np.int64).sum()),
+                           'scaling': 'strong (fixed %d trials, trial r on rank r mod W, gather inside '
+                                      'the clock); the digest is identical at every N' % ntr,
+                           'survey_target_s': {1: 5.9, 8: 0.85}.get(world)}
+        del mine
 
     # ---- the option-file shapes at N > 1: every rank runs its own independent decisions ------
     # (BO trials shard with no collective, SURVEY 8e: the aggregate is the sum of the ranks' rates)
@@ -412,7 +499,7 @@ def run_b200(args):
         trailing_tflops = alg_outer / (ms3[3] * 1e-3) / 1e12 if ms3[3] > 0 else all_updates_tflops
         peaks = {} if args.no_peaks else measure_fp64_peaks(torch, lib_call, dev)
         peak = peaks.get('cublas_dgemm_tflops')
-        step_tflops = sweep.step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
+        step_tflops = step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
             / (ms_resident * 1e-3) / 1e12
         roof = {
             'bound': 'tensor',
@@ -435,10 +522,17 @@ def run_b200(args):
             'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,
         }
-        cpu = None
+        cpu, parity = None, None
         if not args.no_cpu_baseline and world == 1:
             cpu_step_seconds(0)  # warm BLAS threads
-            ts = [cpu_step_seconds(1 + k) for k in range(args.cpu_trials)]
+            ts = []
+            for k in range(args.cpu_trials):
+                # the timed CPU trials double as the checker of the device's results on the
+                # SAME full-size trial (the oracle is fed the device RNG's normals)
+                dt, ref = cpu_step(1 + k, with_philox=not args.no_parity)
+                ts.append(dt)
+                if not args.no_parity:
+                    parity = check_trial(torch, groups[0], 1 + k, ref, parity)
             cpu = {'value': N_DRAW * len(ts) / float(np.sum(ts)), 'unit': UNIT,
                    'cores': cpu_threads(), 'kind': 'port',
                    'sample': '%d full-size trials (n=%d, m=%d, S=%d), numpy+LAPACK oracle, '
@@ -448,11 +542,10 @@ def run_b200(args):
             'warmup': args.warmup, 'ms_per_step': ms_resident / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': workload_name(), 'trials_per_step_per_gpu': trials_per_step,
-                       'streams': G, 'batch': B, 'parallelism': 'trials sharded r mod W, no collective '
-                       'inside the step, one gather of picks',
-                       'l2': 'working set per trial (Sigma 512 MiB) exceeds the 126 MB L2; no flush needed',
-                       'rng': 'device Philox4x32-10 keyed (seed, trial)'},
+            'config': workload_config(),
+            'run': {'trials_per_step_per_gpu': trials_per_step, 'streams': G, 'batch': B,
+                    'parallelism': 'trials sharded r mod W, no collective inside the step, one gather '
+                                   'of picks', 'rng': 'device Philox4x32-10 keyed (seed, trial)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': sum(g.h2d_bytes for g in groups),
@@ -461,6 +554,9 @@ def run_b200(args):
             'gpu_launches': launches,
             'roofline': roof,
             'cpu_baseline': cpu,
+            'parity_checked': bool(parity and parity['ok']),
+            'parity': parity,
+            'sweep_fixed_trials': sweep_fixed,
         }
         if not args.no_cpu_baseline and world == 1:
             # second half of BASELINE.json's metric: MTS BO decision steps/s at the option-file

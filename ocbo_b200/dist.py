@@ -100,12 +100,16 @@ def gather_picks(trial_ids, task, action, gain, num_trials, device=None):
     return out_t, out_a, out_g
 
 
-def run_sweep(num_trials, step_factory, make_inputs, streams=4, batch=1):
-    """Run ``num_trials`` independent trial-steps sharded over the ranks.
-    ``step_factory(stream)`` -> SweepStep; ``make_inputs(trial)`` -> (X, y, Xs).
+def run_sweep(num_trials, step_factory, make_inputs, streams=4, batch=1, groups=None):
+    """Run ``num_trials`` independent trial-steps sharded over the ranks (the reference's
+    trial loop, src/ocbo.py:104-107, with trial r on rank r mod W).
+    ``step_factory(stream)`` -> SweepStep, or ``groups`` = SweepStep objects already built (one
+    per stream, equal batch); ``make_inputs(trial)`` -> (X, y, Xs).
     Returns gather_picks(...) (rank 0) / None."""
     mine = shard_trials(num_trials)
-    groups = [step_factory(torch.cuda.Stream()) for _ in range(streams)]
+    if groups is None:
+        groups = [step_factory(torch.cuda.Stream()) for _ in range(streams)]
+    streams, batch = len(groups), groups[0].B
     ids, tasks, acts, gains = [], [], [], []
     pending = [None] * streams
     chunks = [mine[i:i + batch] for i in range(0, len(mine), batch)]

@@ -28,42 +28,8 @@ from . import _lib, engine
 from ._lib import TILE, call
 from .engine import F64, I32, _p
 
-SEED = 100826730  # the reference's global seed (src/ocbo.py:74-75)
-# SE-ARD bandwidths of the sweep: 0.25 on the 4 context dims, 0.05 on the 2 action dims.
-# (SURVEY 8d quotes an isotropic 0.25 "to keep cond(Sigma) <~ 1e6"; measured, that choice gives
-# cond ~ 1e16 and fires the jitter ladder, so the action bandwidth is set to meet the stated
-# conditioning goal instead: cond(Sigma) ~ 1e4-1e5.  DESIGN.md "sweep configuration".)
-SWEEP_BANDWIDTHS = (0.25, 0.25, 0.25, 0.25, 0.05, 0.05)
-
-# algorithmic FLOPs of one trial-step
-def step_flops(n, m, S):
-    return (n ** 3 / 3.0 + float(n) ** 2 * m + float(n) * m ** 2 + m ** 3 / 3.0
-            + float(m) ** 2 * S + 2.0 * m * n + 2.0 * n ** 2)
-
-
-def hartmann6(x):
-    A = np.asarray([[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14],
-                    [3, 3.5, 1.7, 10, 17, 8], [17, 8, 0.05, 10, 0.1, 14]])
-    P = 1e-4 * np.asarray([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
-                           [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]])
-    alpha = np.asarray([1.0, 1.2, 3.0, 3.2])
-    x = np.atleast_2d(x)
-    e = -np.einsum('ij,nij->ni', A, (x[:, None, :] - P[None]) ** 2)
-    return (alpha * np.exp(e)).sum(axis=1)
-
-
-def make_trial_inputs(trial, n=1024, T=64, A=128, ctx_dim=4, act_dim=2):
-    """Synthetic inputs of trial ``trial``: X ~ U[0,1]^(n x 6),
-    y = hartmann6(X) + N(0, 1e-4), candidates = task-major grid of T task
-    locations ~ U[0,1]^4 times A actions ~ U[0,1]^2 (misc_util.py:104-116)."""
-    g = np.random.default_rng(trial)
-    D = ctx_dim + act_dim
-    X = g.uniform(size=(n, D))
-    y = (hartmann6(X) if D == 6 else np.sin(3.0 * X.sum(axis=1))) + 1e-2 * g.standard_normal(n)
-    locs = g.uniform(size=(T, ctx_dim))
-    acts = g.uniform(size=(T * A, act_dim))
-    Xs = np.hstack([np.repeat(locs, A, axis=0), acts])
-    return X, y, Xs
+from .workload import (SEED, SWEEP_BANDWIDTHS, hartmann6, make_trial_inputs,  # noqa: F401
+                       step_flops)
 
 
 class SweepStep(object):
@@ -234,6 +200,12 @@ class SweepStep(object):
             call('ocbo_joint_pick', _p(self.seg_max[s]), _p(self.seg_arg[s]), T, 0, T, S,
                  _p(self.task[s]), _p(self.action[s]), _p(self.gain[s]), 1, st)
         self.jitter[b] = (jK[0], jS[0])
+
+    def samples_host(self, b):
+        """The (S, m) joint samples of trial slot ``b`` of the last step (diagnostics / parity
+        tests; the picks never need them on the host)."""
+        self.stream.synchronize()
+        return self.F[b].t().contiguous().cpu().numpy()
 
     def step_host(self, trial_ids, inputs):
         self.submit_host(trial_ids, inputs)

@@ -27,6 +27,27 @@ def test_sweep_step_matches_oracle_small():
         assert np.max(np.abs(gain[b] - g_ref)) <= 1e-8 * np.max(np.abs(g_ref))
 
 
+def test_sweep_step_matches_oracle_at_the_headline_shape():
+    """BASELINE.json configs[4] / bench.py's workload itself: n=1024, m=8192 (64 x 128), S=256.
+    Picks bit-exact for all 256 draws; mean, samples and gains to max(1e-8, 10 cond eps)
+    relative (cond(Sigma) = 4.3e5 at this shape)."""
+    from ocbo_b200 import sweep, workload
+    from oracle import philox, sweep_step
+    n, T, A, S = workload.N_OBS, workload.N_TASK, workload.N_ACT, workload.N_DRAW
+    tol = max(1e-8, 10 * 4.3e5 * np.finfo(np.float64).eps)
+    step = sweep.SweepStep(n, T, A, S, 6, batch=1)
+    for trial in (0, 7):
+        X, y, Xs = workload.make_trial_inputs(trial, n, T, A)
+        task, act, gain = step.step_host([trial], [(X, y, Xs)])
+        assert step.jitter[0] == (None, None)  # the headline configuration never walks the ladder
+        Z = philox.normals(sweep.SEED, trial, T * A, S)
+        t_ref, a_ref, g_ref, F_ref, mu, var = sweep_step.step(X, y, Xs, T, S, Z=Z, return_samples=True)
+        assert np.array_equal(task[0], t_ref) and np.array_equal(act[0], a_ref)
+        assert np.max(np.abs(step.mean[0].cpu().numpy() - mu)) <= tol * np.max(np.abs(mu))
+        assert np.max(np.abs(step.samples_host(0) - F_ref)) <= tol * np.max(np.abs(F_ref))
+        assert np.max(np.abs(gain[0] - g_ref)) <= tol * np.max(np.abs(g_ref))
+
+
 def test_sweep_results_do_not_depend_on_batching_or_stream():
     """Trial r gives the same picks whether it runs alone, in a batch, or on a
     side stream -- the property that makes 1/2/4/8-GPU runs agree."""
