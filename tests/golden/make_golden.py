@@ -20,6 +20,48 @@ from oracle import gp_numpy, refshim  # noqa: E402
 from tests import scenarios as sc  # noqa: E402
 
 
+def long_traces(classes, discrete_functions, hartmann6):
+    """tests/golden/mts_long_traces.json: the option files' real task counts and capitals,
+    free runs of the reference's own classes (tests/scenarios.py LONG_*)."""
+    import time
+    out = {}
+    for name, cfg in sc.LONG_DISCRETE.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        f_infos = discrete_functions(cfg)
+        gp_numpy.TRACE = []
+        t0 = time.time()
+        r = sc.run_discrete_long(cfg, classes[cfg['kind']], f_infos, sc.discrete_options(cfg, 'dragonfly'))
+        trace, gp_numpy.TRACE = gp_numpy.TRACE, None
+        per = 1 if cfg['kind'] == 'joint-mts' else len(f_infos)
+        r['margins'] = sc.discrete_margins(cfg, len(f_infos), r['choices'], trace)
+        r['rungs'] = [[d['jitter_p'] for d in trace[k * per:(k + 1) * per]] for k in range(cfg['capital'])]
+        out[name] = r
+        nr = sum(1 for st in r['rungs'] for p in st if p is not None)
+        print('%s: %d steps in %.1f s, %d of %d draws needed the ladder, %d picks lead by less than their '
+              'tolerance' % (name, cfg['capital'], time.time() - t0, nr, per * cfg['capital'],
+                             sum(1 for m, t in r['margins'] if m <= t)))
+    for name, cfg in sc.LONG_CONTINUOUS.items():
+        np.random.seed(sc.SEED)
+        gp_numpy.EuclideanGPFitter._fit_counter = 0
+        gp_numpy.TRACE, gp_numpy.TRACE_EVAL = [], []
+        t0 = time.time()
+        r = sc.run_continuous_long(cfg, classes[cfg['kind']], hartmann6, [[0, 1] for _ in range(6)],
+                                   sc.continuous_options(cfg, 'dragonfly'))
+        trace, gp_numpy.TRACE, gp_numpy.TRACE_EVAL = gp_numpy.TRACE, None, None
+        P = cfg['num_profiles']
+        r['margins'] = sc.continuous_margins(cfg, trace, r['y_init'], r['rewards'])
+        r['rungs'] = [[d['jitter_p'] for d in trace[k * P:(k + 1) * P]] for k in range(cfg['capital'])]
+        out[name] = r
+        nr = sum(1 for st in r['rungs'] for p in st if p is not None)
+        print('%s: %d steps in %.1f s, %d of %d draws needed the ladder, final regret %.4f' % (
+            name, cfg['capital'], time.time() - t0, nr, P * cfg['capital'], r['regret'][-1]))
+    path = os.path.join(ROOT, 'tests', 'golden', 'mts_long_traces.json')
+    with open(path, 'w') as fh:
+        json.dump(out, fh, separators=(',', ':'))
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
 def main():
     refshim.install()
     from strategies.mts import MTS
@@ -47,6 +89,21 @@ def main():
             return assemble_functions(cfg['functions'])
         return assemble_chopped_1d_functions(cfg['cts_f'], cfg['num_chops'])
 
+    def functions_of(cfg):
+        if 'functions' in cfg:
+            return assemble_functions(cfg['functions'])
+        if 'cts_f' in cfg:
+            return assemble_chopped_1d_functions(cfg['cts_f'], cfg['num_chops'])
+        easy, med, hard = cfg['masses']
+        domain = [[0, 1] for _ in range(cfg['massf_dim'])]
+        return get_hard_mass_functions(hard, domain, None) + \
+            get_med_mass_functions(med, domain, None) + get_easy_mass_functions(easy, domain, None)
+
+    if '--short-only' not in sys.argv:
+        long_traces({'mts': MTS, 'joint-mts': JointMTS, 'cmts': ContinuousMultiTaskTS, 'cmts-pm': CMTSPM},
+                    functions_of, hartmann6)
+    if '--long-only' in sys.argv:
+        return
     out = {}
     # baselines: picks only (no tie margins: the CPU host-logic test is their parity gate)
     base_cls = {'agn-thomp': AgnThompson, 'agn-ei': AgnEI, 'Random': RandomOpt, 'ja-thomp': JointAgnThompson,

@@ -248,3 +248,138 @@ def assert_same_up_to_ties(got_pts, ref, atol=1e-9):
     assert margin <= tol, ('selection differs at step %d but the reference pick led by %.3e '
                            '> tie tolerance %.3e' % (k, margin, tol))
     return k
+
+
+# ---------------------------------------------------------------------------
+# Option-file-length traces (src/options/{set2d,jointbran,rand6d,conth42}.txt at their real
+# task counts and capitals) with the comparison CONTINUING past an accepted tie.
+#
+# The golden side is the reference's own strategy class, run freely; per step it stores the
+# pick, the tie margin / tolerance, the jitter rung of every draw and a digest of every GP's
+# hyper-parameters at decision time.  The checked side runs the same loop "teacher forced":
+# its own decision is recorded and compared, then the REFERENCE's query is the one evaluated
+# and added, so both runs hold the same data (and the same position in the global numpy
+# stream) at every step -- one accepted tie no longer ends the comparison.
+# ---------------------------------------------------------------------------
+LONG_DISCRETE = {
+    # set2d.txt:3-8: T=5, capital 100
+    'set2d-full': dict(kind='mts', functions='branin,parabaloid,parabaloid,parabaloid,parabaloid',
+                       capital=100, init_capital=5, tuning_methods='ml', hp_samples=3,
+                       risk_neutral=False),
+    # jointbran.txt:3-12: T=10 chops of Branin, capital 110, risk-neutral bookkeeping
+    'jointbran-full': dict(kind='joint-mts', cts_f='branin', num_chops=10, capital=110, init_capital=5,
+                           tuning_methods='ml', hp_samples=3, risk_neutral=True),
+    # rand6d.txt:3-13: T=30 (15 easy / 10 medium / 5 hard), 6-D, ml-post_sampling, 5 HP draws;
+    # 300 of the file's 1500 steps
+    'rand6d-full': dict(kind='mts', masses=(15, 10, 5), massf_dim=6, capital=300, init_capital=5,
+                        tuning_methods='ml-post_sampling', hp_samples=5, risk_neutral=False),
+}
+LONG_CONTINUOUS = {
+    # conth42.txt:3-9: Hartmann-6 as 4 context + 2 action dims, 50 contexts x 100 actions per step
+    # (profile_cts.py:13-18); 200 of the file's 750 steps; the policy score on an 8 x 8 grid
+    'conth42-full-cmts': dict(kind='cmts', act_dim=2, capital=200, init_capital=5, num_profiles=50,
+                              profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+    'conth42-full-cmts-pm': dict(kind='cmts-pm', act_dim=2, capital=200, init_capital=5, num_profiles=50,
+                                 profile_evals=100, eval_ctx_fidel=8, eval_act_fidel=8),
+}
+
+
+def hp_digest(gp):
+    """One number per GP: log scale + sum log length-scales + log noise (GPWrapper interface,
+    src/gp/gp_interface.py:32-38) -- enough to see a hyper-parameter fit go a different way."""
+    hps = gp.get_kernel_hps()
+    ls = np.ravel(np.asarray(hps['lengthscale'], dtype=np.float64))
+    return float(np.log(float(hps['scale'])) + np.sum(np.log(ls)) + np.log(gp.get_estimated_noise()))
+
+
+def _discrete_gps(method):
+    gps = list(method.gps)
+    return gps[:1] if all(g is gps[0] for g in gps) else gps   # JointOpt aliases one GP T times
+
+
+class Recorder(object):
+    """Wraps a strategy object's decision method.  ``forced`` = the reference's per-step picks
+    (teacher forcing) or None (free run: golden generation).  ``rungs(method)`` returns the
+    jitter rungs of the step's draws if the engine exposes them (else None)."""
+
+    def __init__(self, method, attr, forced=None, rungs=None, gps=_discrete_gps):
+        self.method, self.attr, self.forced, self.rungs_fn, self.gps_fn = method, attr, forced, rungs, gps
+        self.picks, self.rungs, self.hps = [], [], []
+        self.inner = getattr(method, attr)
+        setattr(method, attr, self)
+
+    def __call__(self, *args, **kwargs):
+        self.hps.append([hp_digest(g) for g in self.gps_fn(self.method)])
+        out = self.inner(*args, **kwargs)
+        self.picks.append(out)
+        if self.rungs_fn is not None:
+            self.rungs.append(self.rungs_fn(self.method))
+        if self.forced is not None:
+            return self.forced[len(self.picks) - 1]
+        return out
+
+
+def run_discrete_long(cfg, strategy_cls, f_infos, options, ref=None, rungs=None):
+    """src/ocbo.py:128-144 for one method; with ``ref`` (a golden entry) the run is teacher
+    forced.  Returns the per-step record."""
+    method = strategy_cls(f_infos, options)
+    init_pts = []
+    for wrap in f_infos:
+        low, high = zip(*wrap.domain)
+        init_pts.append([np.random.uniform(low, high) for _ in range(cfg['init_capital'])])
+    method.set_clean()
+    forced = None
+    if ref is not None:
+        forced = [(int(c), np.asarray(p, dtype=np.float64)) for c, p in zip(ref['choices'], ref['points'])]
+    rec = Recorder(method, 'decide_next_query', forced, rungs)
+    h = method.optimize(cfg['capital'], init_pts=init_pts)
+    return dict(choices=[int(p[0]) for p in rec.picks],
+                points=[[float(v) for v in np.ravel(p[1])] for p in rec.picks],
+                hps=rec.hps, rungs=rec.rungs, total_best=[float(v) for v in h.total_best])
+
+
+def run_continuous_long(cfg, strategy_cls, function, domain, options, ref=None, rungs=None):
+    """src/cts_ocbo.py:95-110 for one method, optionally teacher forced."""
+    ctx_dim = len(domain) - cfg['act_dim']
+    method = strategy_cls(function, domain, ctx_dim, options)
+    init_pts = list(np.random.uniform(*zip(*domain), (cfg['init_capital'], len(domain))))
+    method.set_clean()
+    forced = [np.asarray(p, dtype=np.float64) for p in ref['points']] if ref is not None else None
+    rec = Recorder(method, '_determine_next_query', forced, rungs, gps=lambda m: [m.gp])
+    h = method.optimize(cfg['capital'], init_pts=init_pts)
+    return dict(points=[[float(v) for v in np.ravel(p)] for p in rec.picks], hps=rec.hps,
+                rungs=rec.rungs, rewards=[float(q.reward) for q in h.query_history],
+                y_init=[float(v) for v in h.y_init],
+                regret=[float(s.regret) for s in h.score_history])
+
+
+def compare_long(got, ref, atol=1e-9, hp_atol=1e-6):
+    """Per-step comparison of a teacher-forced run with its golden trace.  Every differing
+    pick must be a documented tie (margin <= tolerance).  Returns the statistics DESIGN.md
+    section 2 quotes."""
+    steps = len(ref['points'])
+    assert len(got['points']) == steps
+    diff_pick, diff_rung, rung_steps, hp_diff, worst, bad = [], 0, 0, 0, 0.0, []
+    for k in range(steps):
+        if np.max(np.abs(np.asarray(got['hps'][k]) - np.asarray(ref['hps'][k]))) > hp_atol:
+            hp_diff += 1
+        if got['rungs'] and ref.get('rungs'):
+            rung_steps += 1
+            if list(got['rungs'][k]) != list(ref['rungs'][k]):
+                diff_rung += 1
+        same = np.max(np.abs(np.asarray(got['points'][k]) - np.asarray(ref['points'][k]))) <= atol
+        if 'choices' in ref:
+            same = same and got['choices'][k] == ref['choices'][k]
+        if not same:
+            margin, tol = ref['margins'][k]
+            diff_pick.append(k)
+            ratio = margin / tol if tol > 0 else float('inf')
+            worst = max(worst, ratio)
+            if not margin <= tol:
+                bad.append((k, margin, tol))
+    stats = dict(steps_compared=steps, steps_with_a_different_pick=len(diff_pick),
+                 steps_with_a_different_rung=diff_rung, steps_with_rungs_compared=rung_steps,
+                 steps_with_different_hyper_parameters=hp_diff,
+                 worst_margin_over_tolerance_among_differing_picks=worst,
+                 differing_steps=diff_pick[:50], undocumented=bad[:10])
+    return stats

@@ -139,3 +139,88 @@ def test_sampling_free_continuous_methods_reproduce_reference_selections(golden,
     ref = golden[name]
     assert np.allclose(got['points'], ref['points'], rtol=0, atol=1e-12)
     assert np.allclose(got['regret'], ref['regret'], rtol=0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+# Option-file-length traces, teacher forced (tests/scenarios.py "LONG_*")
+# ---------------------------------------------------------------------------
+LONG_GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'mts_long_traces.json')
+STATS_OUT = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out', 'long_trace_stats.json')
+
+
+@pytest.fixture(scope='module')
+def long_golden():
+    with open(LONG_GOLDEN) as fh:
+        return json.load(fh)
+
+
+def _save_stats(name, stats):
+    try:
+        os.makedirs(os.path.dirname(STATS_OUT), exist_ok=True)
+        allstats = {}
+        if os.path.exists(STATS_OUT):
+            with open(STATS_OUT) as fh:
+                allstats = json.load(fh)
+        allstats[name] = stats
+        with open(STATS_OUT, 'w') as fh:
+            json.dump(allstats, fh, indent=1)
+    except OSError:
+        pass
+    print('\n[long trace] %s: %s' % (name, json.dumps(stats)))
+
+
+def _mts_rungs(method):
+    return [g.gp_core.last_sample_jitter for g in method.gps]
+
+
+def _joint_rungs(method):
+    return [method.gps[0].gp_core.last_sample_jitter]
+
+
+def _profile_rungs(method):
+    j = method.gp.gp_core.last_sample_jitter
+    return list(j) if isinstance(j, (list, tuple)) else [j]
+
+
+@pytest.mark.parametrize('name', sorted(sc.LONG_DISCRETE))
+def test_option_file_length_discrete_traces(long_golden, name):
+    """set2d (T=5, 100 steps), jointbran (T=10, 110 steps), rand6d (T=30, 300 steps): every
+    decision of the B200 strategies against the reference's own classes, continuing past
+    accepted ties; a differing pick must be a documented tie.  The statistics are written to
+    gpurun_out/long_trace_stats.json (DESIGN.md section 2 quotes them)."""
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    from ocbo_b200.strategies import strategies
+    cfg = sc.LONG_DISCRETE[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    f_infos = _functions(cfg)
+    cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
+    ref = long_golden[name]
+    got = sc.run_discrete_long(cfg, cls, f_infos, sc.discrete_options(cfg, 'b200'), ref=ref,
+                               rungs=_joint_rungs if cfg['kind'] == 'joint-mts' else _mts_rungs)
+    stats = sc.compare_long(got, ref)
+    _save_stats(name, stats)
+    assert not stats['undocumented'], stats
+    assert stats['steps_with_different_hyper_parameters'] == 0, stats
+    # teacher forced: both runs evaluated the same queries, so the bookkeeping agrees throughout
+    assert np.allclose(got['total_best'], ref['total_best'], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', sorted(sc.LONG_CONTINUOUS))
+def test_option_file_length_continuous_traces(long_golden, name):
+    """conth42 (50 contexts x 100 actions per step, 200 steps) for cmts and cmts-pm."""
+    from ocbo_b200 import synth
+    from ocbo_b200.cstrats import cstrats
+    from ocbo_b200.gp.gp_interface import B200GPFitter
+    cfg = sc.LONG_CONTINUOUS[name]
+    np.random.seed(sc.SEED)
+    B200GPFitter._fit_counter = 0
+    cls = [s.impl for s in cstrats if s.name == cfg['kind']][0]
+    ref = long_golden[name]
+    got = sc.run_continuous_long(cfg, cls, synth.hartmann6, [[0, 1] for _ in range(6)],
+                                 sc.continuous_options(cfg, 'b200'), ref=ref, rungs=_profile_rungs)
+    stats = sc.compare_long(got, ref)
+    _save_stats(name, stats)
+    assert not stats['undocumented'], stats
+    assert stats['steps_with_different_hyper_parameters'] == 0, stats
+    assert np.allclose(got['regret'], ref['regret'], rtol=0, atol=1e-8)

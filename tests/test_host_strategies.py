@@ -198,3 +198,43 @@ def test_unknown_engine_raises_value_error():
     from ocbo_b200.gp.gp_util import get_gp_fitter
     with pytest.raises(ValueError):
         get_gp_fitter('gpytorch', [[0.0]], [0.0], None)
+
+
+LONG_GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'mts_long_traces.json')
+
+
+@pytest.mark.parametrize('name,steps', [('set2d-full', 100), ('rand6d-full', 40), ('jointbran-full', 12)])
+def test_teacher_forced_long_traces_on_the_oracle_engine(oracle_engine, name, steps):
+    """The option-file-length traces (tests/scenarios.py LONG_*) with ocbo_b200's strategy classes on
+    the numpy engine, teacher forced: same engine as the golden run, so every decision, every
+    hyper-parameter digest and the bookkeeping must agree exactly -- no tie is needed."""
+    from ocbo_b200.strategies import strategies
+    with open(LONG_GOLDEN) as fh:
+        ref = json.load(fh)[name]
+    cfg = dict(sc.LONG_DISCRETE[name], capital=steps)
+    ref = {k: (v[:steps] if isinstance(v, list) and k != 'total_best' else v) for k, v in ref.items()}
+    np.random.seed(sc.SEED)
+    cls = [s.impl for s in strategies if s.name == cfg['kind']][0]
+    got = sc.run_discrete_long(cfg, cls, _functions(cfg), sc.discrete_options(cfg, 'b200'), ref=ref)
+    stats = sc.compare_long(got, ref, atol=1e-12, hp_atol=1e-12)
+    assert stats['steps_compared'] == steps
+    assert stats['steps_with_a_different_pick'] == 0, stats
+    assert stats['steps_with_different_hyper_parameters'] == 0, stats
+
+
+def test_teacher_forced_continuous_trace_on_the_oracle_engine(oracle_engine):
+    from ocbo_b200 import synth
+    from ocbo_b200.cstrats import cstrats
+    steps = 25
+    with open(LONG_GOLDEN) as fh:
+        ref = json.load(fh)['conth42-full-cmts']
+    cfg = dict(sc.LONG_CONTINUOUS['conth42-full-cmts'], capital=steps)
+    ref = {k: (v[:steps] if isinstance(v, list) and k != 'y_init' else v) for k, v in ref.items()}
+    np.random.seed(sc.SEED)
+    cls = [s.impl for s in cstrats if s.name == 'cmts'][0]
+    got = sc.run_continuous_long(cfg, cls, synth.hartmann6, [[0, 1] for _ in range(6)],
+                                 sc.continuous_options(cfg, 'b200'), ref=ref)
+    stats = sc.compare_long(got, ref, atol=1e-12, hp_atol=1e-12)
+    assert stats['steps_with_a_different_pick'] == 0, stats
+    assert stats['steps_with_different_hyper_parameters'] == 0, stats
+    assert np.allclose(got['regret'], ref['regret'][:steps], rtol=0, atol=1e-12)
