@@ -360,6 +360,7 @@ def compare_long(got, ref, atol=1e-9, hp_atol=1e-6):
     steps = len(ref['points'])
     assert len(got['points']) == steps
     diff_pick, diff_rung, rung_steps, hp_diff, worst, bad = [], 0, 0, 0, 0.0, []
+    draws, draw_diff, hist = 0, 0, {}
     for k in range(steps):
         if np.max(np.abs(np.asarray(got['hps'][k]) - np.asarray(ref['hps'][k]))) > hp_atol:
             hp_diff += 1
@@ -367,6 +368,11 @@ def compare_long(got, ref, atol=1e-9, hp_atol=1e-6):
             rung_steps += 1
             if list(got['rungs'][k]) != list(ref['rungs'][k]):
                 diff_rung += 1
+            for a, b in zip(got['rungs'][k], ref['rungs'][k]):
+                d = (P_NONE if a is None else a) - (P_NONE if b is None else b)
+                draws += 1
+                draw_diff += d != 0
+                hist[str(d)] = hist.get(str(d), 0) + 1
         same = np.max(np.abs(np.asarray(got['points'][k]) - np.asarray(ref['points'][k]))) <= atol
         if 'choices' in ref:
             same = same and got['choices'][k] == ref['choices'][k]
@@ -380,6 +386,8 @@ def compare_long(got, ref, atol=1e-9, hp_atol=1e-6):
     stats = dict(steps_compared=steps, steps_with_a_different_pick=len(diff_pick),
                  steps_with_a_different_rung=diff_rung, steps_with_rungs_compared=rung_steps,
                  steps_with_different_hyper_parameters=hp_diff,
+                 draws_compared=draws, draws_with_a_different_rung=draw_diff,
+                 rung_difference_histogram=hist,  # ours - reference's, "no jitter" counted as -12
                  worst_margin_over_tolerance_among_differing_picks=worst,
                  differing_steps=diff_pick[:50], undocumented=bad[:10])
     return stats
