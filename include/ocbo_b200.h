@@ -238,6 +238,20 @@ int ocbo_sample(const double* mean, int64_t s_mean,
                 double* F, int ldf, int64_t s_f,
                 const int32_t* info, int batch, ocbo_stream_t stream);
 
+/* Fused sampling tail: per 128-row tile t of F = mean + L Z and per sample column s,
+ *   tile_max[b][t][s] = max_i F[b][128 t + i][s],  tile_arg[b][t][s] = first arg-max i in [0,128)
+ * (np.max / np.argmax semantics, NaN included), WITHOUT writing F: the m x S sample matrix of
+ * joint_mts.py:42 never exists in memory.  With task segments of exactly 128 rows (the sweep:
+ * A = 128 actions per task) tile_max / tile_arg ARE the seg_max / seg_arg of ocbo_joint_pick.
+ * m a multiple of 128, S a multiple of 32; values bit-identical to ocbo_sample followed by
+ * ocbo_segment_argmax.  Replaces draw_sample + np.max/np.argmax (src/gp/gp_interface.py:76-79,
+ * src/strategies/joint_mts.py:42-53). */
+int ocbo_sample_tile_argmax(const double* mean, int64_t s_mean,
+                            const double* L, int m, int ldl, int64_t s_l,
+                            const double* Z, int S, int ldz, int64_t s_z,
+                            double* tile_max, int32_t* tile_arg,
+                            const int32_t* info, int batch, ocbo_stream_t stream);
+
 /* Segmented max / first-index argmax per sample column:
  * seg_ptr[b][0..nseg] row offsets; out_max/out_arg are [batch][nseg][S]
  * (arg relative to the segment start; empty segment -> -inf / -1).

@@ -576,6 +576,29 @@ int ocbo_sample(const double* mean, int64_t s_mean, const double* L, int m, int 
   return 0;
 }
 
+int ocbo_sample_tile_argmax(const double* mean, int64_t s_mean, const double* L, int m, int ldl,
+                            int64_t s_l, const double* Z, int S, int ldz, int64_t s_z,
+                            double* tile_max, int32_t* tile_arg, const int32_t* info, int batch,
+                            ocbo_stream_t stream) {
+  if (!mean) return fail_arg(1, "mean null");
+  if (!L) return fail_arg(3, "L null");
+  if (!tile_ok(m)) return fail_arg(4, "m must be a positive multiple of 128");
+  if (ldl < m || (ldl & 1)) return fail_arg(5, "ldl must be even and >= m");
+  if (!Z) return fail_arg(7, "Z null");
+  if (S <= 0 || S % 32) return fail_arg(8, "S must be a positive multiple of 32");
+  if (ldz < S || (ldz & 1)) return fail_arg(9, "ldz must be even and >= S");
+  if (!tile_max || !tile_arg) return fail_arg(11, "outputs null");
+  if (batch <= 0) return fail_arg(14, "batch");
+  NnParams p{};
+  p.P = L; p.ldp = ldl; p.sP = s_l;
+  p.R = Z; p.ldr = ldz; p.sR = s_z;
+  p.rowvec = mean; p.sRowvec = s_mean;
+  p.ktiles = m / BK; p.ntr = m / TILE; p.tri_k = 1; p.pair_rows = 1; p.mode = 2; p.info = info;
+  p.tile_max = tile_max; p.tile_arg = tile_arg; p.out_ld = S;
+  CK(launch_sample_argmax(p, S / 32, batch, (cudaStream_t)stream), "ocbo_sample_tile_argmax");
+  return 0;
+}
+
 int ocbo_segment_argmax(const double* F, int S, int ldf, int64_t s_f, const int32_t* seg_ptr,
                         int nseg, double* out_max, int32_t* out_arg, int batch,
                         ocbo_stream_t stream) {

@@ -102,6 +102,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// Fused sampling tail (north_star c, joint_mts.py:42-53): the tile of
+//   F = mean + L Z      (L lower triangular, k stops at the row tile's diagonal block)
+// is reduced in the epilogue to one (max, FIRST arg-max) per sample column over the tile's
+// 128 rows, so the m x S sample matrix never exists in HBM.  128 x 32 tiles: S = 256 gives
+// 8 column tiles x 32 row-tile pairs = 256 CTAs for ONE trial (the 128 x 64 product had 128
+// CTAs on 296 slots: 65 % of the DMMA peak at batch 1); the accumulation order of every
+// element is that of gemm_nn_kernel, so the reduced values are bit-identical to
+// ocbo_sample + ocbo_segment_argmax.  np.argmax / np.max semantics incl. NaN (first NaN wins).
+// ---------------------------------------------------------------------------
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams p) {
+  using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.z;
+  if (p.info && p.info[b] != 0) return;
+  const int tj = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
+    if (pass == 1 && ti <= (int)blockIdx.y) break;
+    const double* P = p.P + (size_t)b * p.sP + (size_t)ti * BM * p.ldp;
+    const double* R = p.R + (size_t)b * p.sR + (size_t)tj * BN;
+    const int ktiles = min(p.ktiles, (ti + 1) * (BM / BK));
+
+    typename G::Acc acc;
+    G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
+    G::zero(acc);
+    G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);  // ends with a barrier: the ring is free
+
+    const double* rv = p.rowvec + (size_t)b * p.sRowvec + (size_t)ti * BM;
+    double* red_v = smem;                                   // [WARPS_M][BN]
+    int* red_r = reinterpret_cast<int*>(smem + WARPS_M * BN);
+#pragma unroll
+    for (int ni = 0; ni < G::NI; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double bv = 0.0;
+        int br = -1;
+#pragma unroll
+        for (int mi = 0; mi < G::MI; ++mi) {  // rows ascending: a later equal value never wins
+          const int r = wm * G::WM + mi * 8 + g;
+          const double v = rv[r] + acc[mi][ni][e];
+          if (br < 0 || arg_better(v, r, bv, br)) {
+            bv = v;
+            br = r;
+          }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {  // across the 8 row groups g (lane bits 2..4)
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+          if (arg_better(ov, orr, bv, br)) {
+            bv = ov;
+            br = orr;
+          }
+        }
+        if (g == 0) {
+          const int c = wn * G::WN + ni * 8 + 2 * t + e;
+          red_v[wm * BN + c] = bv;
+          red_r[wm * BN + c] = br;
+        }
+      }
+    __syncthreads();
+    if (threadIdx.x < BN) {
+      double bv = red_v[threadIdx.x];
+      int br = red_r[threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < WARPS_M; ++w) {
+        const double ov = red_v[w * BN + threadIdx.x];
+        const int orr = red_r[w * BN + threadIdx.x];
+        if (arg_better(ov, orr, bv, br)) {
+          bv = ov;
+          br = orr;
+        }
+      }
+      const size_t o = ((size_t)b * p.ntr + ti) * p.out_ld + (size_t)tj * BN + threadIdx.x;
+      p.tile_max[o] = bv;
+      p.tile_arg[o] = br;
+    }
+    __syncthreads();  // the reduction scratch is the ring of the next pass
+  }
+}
+
+// ---------------------------------------------------------------------------
 // C_tile = K(Xa_i, Xb_j) - sum_k V1[k][i] V2[k][j]     (posterior covariance)
 //   V1: n x ma, V2: n x mb row-major (k rows).  sym: Xa == Xb, V1 == V2,
 //   padding diagonal = 1; tri: lower-triangular tiles only (2:1 mapping).
@@ -244,6 +330,16 @@ cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch,
   if (e != cudaSuccess) return e;
   if (grid_rows <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
   gemm_nn_kernel<TM, TN, 4, 2><<<dim3(ntc, grid_rows, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  return counted(cudaGetLastError());
+}
+
+cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStream_t st) {
+  using G = Gemm<TM, 32, true, false, 4, 2>;
+  static bool init = false;
+  cudaError_t e = ensure_smem(sample_argmax_kernel<TM, 32, 4, 2>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
+  if (ntc <= 0 || batch <= 0) return cudaSuccess;
+  sample_argmax_kernel<TM, 32, 4, 2><<<dim3(ntc, (p.ntr + 1) / 2, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
   return counted(cudaGetLastError());
 }
 

@@ -29,6 +29,8 @@ struct NnParams {  // C (=|-=|= rowvec +) P R
   int pair_rows;     // CTA y computes row tiles y and ntr-1-y (balanced triangular product)
   int mode;          // 0 set, 1 sub, 2 rowvec + acc
   const int32_t* info;
+  // fused sampling tail (sample_argmax_kernel): per (row tile, column) max / first arg-max
+  double* tile_max; int32_t* tile_arg; int out_ld;
 };
 
 struct CovParams {  // C = K(Xa, Xb) - V1^T V2
@@ -45,6 +47,7 @@ struct CovParams {  // C = K(Xa, Xb) - V1^T V2
 cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st, int panel = 0);
 cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch, cudaStream_t st);
 cudaError_t launch_postcov(const CovParams& p, int ntiles, int batch, cudaStream_t st);
+cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStream_t st);
 
 cudaError_t launch_gram(int kind, int dim, const double* X1, int n1, int64_t sX1, const int32_t* nv1,
                         const double* X2, int n2, int64_t sX2, const int32_t* nv2,

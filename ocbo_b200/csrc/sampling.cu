@@ -74,6 +74,7 @@ cudaError_t launch_sample_rowdot(const double* mean, int64_t sMean, const double
   return counted(cudaGetLastError());
 }
 
+// (np.max / np.argmax semantics incl. NaN: arg_better in common.cuh)
 // Per (problem, segment): max and FIRST argmax over rows [seg[j], seg[j+1]) of
 // every sample column.  256 threads = CS columns x (256/CS) row lanes.
 __global__ void __launch_bounds__(256)
@@ -101,14 +102,14 @@ segment_argmax_kernel(const double* F, int S, int ldf, int64_t sF, const int32_t
         for (int u = 0; u < 4; ++u) v[u] = Fb[(size_t)(i + u * RL) * ldf + s];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (v[u] > best || arg < 0) {
+          if (arg < 0 || arg_better(v[u], i + u * RL, best, arg)) {
             best = v[u];
             arg = i + u * RL;
           }
       }
       for (; i < r1; i += RL) {
         const double v = Fb[(size_t)i * ldf + s];
-        if (v > best || arg < 0) {
+        if (arg < 0 || arg_better(v, i, best, arg)) {
           best = v;
           arg = i;
         }
@@ -123,7 +124,7 @@ segment_argmax_kernel(const double* F, int S, int ldf, int64_t sF, const int32_t
         const int oi = si[threadIdx.x + h * CS];
         const double mv = sv[threadIdx.x];
         const int mi = si[threadIdx.x];
-        if (oi >= 0 && (mi < 0 || ov > mv || (ov == mv && oi < mi))) {
+        if (oi >= 0 && (mi < 0 || arg_better(ov, oi, mv, mi))) {
           sv[threadIdx.x] = ov;
           si[threadIdx.x] = oi;
         }
@@ -174,7 +175,7 @@ __global__ void joint_pick_kernel(const double* seg_max, const int32_t* seg_arg,
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      if (t0 + u < T && (gain[u] > best || bt < 0)) {
+      if (t0 + u < T && (bt < 0 || arg_better(gain[u], t0 + u, best, bt))) {
         best = gain[u];
         bt = t0 + u;
       }

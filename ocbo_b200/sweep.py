@@ -37,7 +37,7 @@ class SweepStep(object):
 
     def __init__(self, n=1024, T=64, A=128, S=256, dim=6, batch=1, kernel_type='se',
                  scale=1.0, bandwidths=SWEEP_BANDWIDTHS, noise_var=1e-2, mu0=0.0, seed=SEED,
-                 stream=None):
+                 stream=None, fused_tail=None, ladder_rungs=0):
         engine.require_cuda()
         if n % TILE or (T * A) % TILE:
             raise ValueError('n and T*A must be multiples of %d' % TILE)
@@ -59,7 +59,25 @@ class SweepStep(object):
         self.alpha, self.lml, self.mean = e(B, n), e(B), e(B, m)
         self.V = e(B, n, m)
         self.Sigma, self.invdS = e(B, m, m), e(B, m // TILE, TILE, TILE)
-        self.Z, self.F = e(B, m, S), e(B, m, S)
+        # Fused sampling tail (ocbo_sample_tile_argmax): with task segments of exactly one 128-row
+        # tile the per-task max / arg-max come out of the L Z kernel's epilogue and the m x S
+        # sample matrix F is never written; other layouts materialise F and reduce it.
+        can_fuse = A == TILE and S % 32 == 0
+        if fused_tail and not can_fuse:
+            raise ValueError('the fused sampling tail needs A == %d and S %% 32 == 0' % TILE)
+        self.fused_tail = can_fuse if fused_tail is None else bool(fused_tail)
+        self.Z = e(B, m, S)
+        # stable_cholesky's jitter ladder for Sigma walked on the device (engine.ladder_rungs):
+        # the plain attempt and the first ``ladder_rungs`` rungs (10^-11, 10^-10, ... x max diag)
+        # are enqueued without a host round trip; a trial that fails them all is redone from the
+        # host (_redo_with_ladder).  0 = plain attempt only (the headline configuration never fails).
+        self.ladder_rungs = int(ladder_rungs)
+        if self.ladder_rungs:
+            self.Sigma0 = e(B, m, m)
+            self.every = torch.ones((B,), dtype=I32, device=dev)
+        self.rung = torch.full((B,), engine.NO_RUNG, dtype=I32, device=dev)
+        self.hrung = torch.empty((B,), dtype=I32).pin_memory()
+        self._F = None if self.fused_tail else e(B, m, S)
         self.info = torch.zeros((2, B), dtype=I32, device=dev)
         seg = np.tile((A * np.arange(T + 1)).astype(np.int32), (B, 1))
         self.seg = torch.from_numpy(seg).to(dev)
@@ -76,7 +94,7 @@ class SweepStep(object):
         # kernels per run(): gram, potrf(n), solve, mean, gram, trsm, cov, potrf(m), philox,
         # sample, segment, pick
         self.launches_per_run = 1 + (3 * (n // TILE) - 2) + 1 + 1 + 1 + (2 * (n // TILE) - 1) + 1 \
-            + (3 * (self.m // TILE) - 2) + 1 + 1 + 1 + 1
+            + (3 * (self.m // TILE) - 2) + 1 + 1 + 1 + (0 if self.fused_tail else 1)
         self.h2d_bytes = B * (n * D + n + m * D) * 8 + B * 4
         self.d2h_bytes = B * S * (8 + 8) + 2 * B * 4
 
@@ -107,17 +125,54 @@ class SweepStep(object):
              None, 0, B, st)
         call('ocbo_post_cov', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
              self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B, st)
+        if self.ladder_rungs:
+            with torch.cuda.stream(self.stream):
+                self.rung.fill_(engine.NO_RUNG)
+                # keep Sigma's lower blocks: restore with an all-pass gate and zero jitter, Sigma0 <- Sigma
+                call('ocbo_ladder_restore', _p(self.Sigma0), _p(self.Sigma), m, m, self.Sigma0.stride(0),
+                     m, self.Sigma.stride(0), None, _p(self.every), 0.0, B, st)
         call('ocbo_potrf', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(infoS), B, st)
+        if self.ladder_rungs:
+            with torch.cuda.stream(self.stream):
+                engine.ladder_rungs(self.Sigma, self.Sigma0, self.invdS, infoS, self.rung, None,
+                                    engine.LADDER[:self.ladder_rungs])
         call('ocbo_philox_normal', _p(self.Z), m, S, S, self.Z.stride(0),
              ctypes.c_uint64(self.seed), _p(self.trial_ids), B, st)
-        call('ocbo_sample', _p(self.mean), self.mean.stride(0), _p(self.Sigma), m, m,
-             self.Sigma.stride(0), _p(self.Z), S, S, self.Z.stride(0), _p(self.F), S,
-             self.F.stride(0), _p(infoS), B, st)
-        call('ocbo_segment_argmax', _p(self.F), S, S, self.F.stride(0), _p(self.seg), T,
-             _p(self.seg_max), _p(self.seg_arg), B, st)
+        self._sample_and_reduce(slice(0, B), st)
         call('ocbo_joint_pick', _p(self.seg_max), _p(self.seg_arg), T, 0, T, S, _p(self.task),
              _p(self.action), _p(self.gain), B, st)
         engine._count(self.launches_per_run)
+
+    @property
+    def F(self):
+        """[B, m, S] joint samples mu + L Z (diagnostics / parity tests).  On the fused path they
+        are not part of a step: computed here on demand from the step's factor and normals."""
+        if self._F is None:
+            self._F = torch.empty((self.B, self.m, self.S), dtype=F64, device=self.Z.device)
+        if self.fused_tail:
+            m, S = self.m, self.S
+            with torch.cuda.stream(self.stream):
+                call('ocbo_sample', _p(self.mean), self.mean.stride(0), _p(self.Sigma), m, m,
+                     self.Sigma.stride(0), _p(self.Z), S, S, self.Z.stride(0), _p(self._F), S,
+                     self._F.stride(0), _p(self.info[1]), self.B, ctypes.c_void_p(self.stream.cuda_stream))
+            self.stream.synchronize()
+        return self._F
+
+    def _sample_and_reduce(self, s, st):
+        """mu + L Z -> per-task max / first arg-max of every draw, for the trial slots ``s``."""
+        m, S, T = self.m, self.S, self.T
+        nb = s.stop - s.start
+        sd = lambda t: 0 if nb == 1 else t.stride(0)
+        mean, Sig, Z, info = self.mean[s], self.Sigma[s], self.Z[s], self.info[1, s]
+        if self.fused_tail:
+            call('ocbo_sample_tile_argmax', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
+                 sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, st)
+            return
+        F = self._F[s]
+        call('ocbo_sample', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S, sd(Z), _p(F), S,
+             sd(F), _p(info), nb, st)
+        call('ocbo_segment_argmax', _p(F), S, S, sd(F), _p(self.seg[s]), T, _p(self.seg_max[s]),
+             _p(self.seg_arg[s]), nb, st)
 
     def set_inputs_device(self, trial_ids, inputs):
         """Load trial inputs once (device-resident timing)."""
@@ -141,6 +196,7 @@ class SweepStep(object):
             self.haction.copy_(self.action, non_blocking=True)
             self.hgain.copy_(self.gain, non_blocking=True)
             self.hinfo.copy_(self.info, non_blocking=True)
+            self.hrung.copy_(self.rung, non_blocking=True)
 
     # -- host-buffer API (what bench.py's e2e leg times) ------------------------
     def submit_host(self, trial_ids, inputs):
@@ -158,7 +214,7 @@ class SweepStep(object):
         """Synchronise the stream and return (task[B,S], action[B,S], gain[B,S])."""
         self.stream.synchronize()
         info = self.hinfo.numpy()
-        self.jitter = [(None, None)] * self.B
+        self.jitter = [(None, None if r == engine.NO_RUNG else int(r)) for r in self.hrung.numpy()]
         if info.any():
             # the fast path factors without the ladder; trials whose K or Sigma is not
             # numerically PD are redone alone through Dragonfly's stable_cholesky ladder
@@ -181,22 +237,20 @@ class SweepStep(object):
             asm_K(0, 1)
             jK = engine.chol_with_ladder(asm_K, self.LK[s], self.invdK[s], self.info[0, s], None, [n])
             st = ctypes.c_void_p(self.stream.cuda_stream)
-            call('ocbo_solve_alpha_lml', _p(self.LK[s]), n, n, 0, _p(self.invdK[s]), _p(self.y[s]), 0,
+            # same kernels and formulas as run(): w = L^-1 (y - mu0), mean = mu0 + V^T w
+            call('ocbo_solve_forward_lml', _p(self.LK[s]), n, n, 0, _p(self.invdK[s]), _p(self.y[s]), 0,
                  None, _p(th), 0, _p(self.alpha[s]), 0, _p(self.lml[s]), _p(self.info[0, s]), 1, st)
-            call('ocbo_post_mean', self.kind, D, _p(Xs), m, 0, None, _p(X), n, 0, None, _p(th), 0,
-                 _p(self.alpha[s]), 0, _p(self.mean[s]), 0, 1, st)
             engine.gram(self.kind, X, None, Xs, None, th, self.V[s], 0)
             engine.trsm_lower(self.LK[s], self.invdK[s], self.V[s], self.info[0, s])
+            call('ocbo_post_mean_var_from_v', _p(self.V[s]), n, m, 0, None, _p(self.alpha[s]), 0,
+                 _p(th), 0, m, None, _p(self.mean[s]), 0, None, 0, 1, st)
 
             def asm_S(b0, b1):
                 call('ocbo_post_cov', self.kind, D, _p(Xs), m, 0, None, _p(self.V[s]), n, m, 0,
                      _p(th), 0, _p(self.Sigma[s]), m, 0, 1, 1, st)
             asm_S(0, 1)
             jS = engine.chol_with_ladder(asm_S, self.Sigma[s], self.invdS[s], self.info[1, s], None, [m])
-            call('ocbo_sample', _p(self.mean[s]), 0, _p(self.Sigma[s]), m, m, 0, _p(self.Z[s]), S, S, 0,
-                 _p(self.F[s]), S, 0, _p(self.info[1, s]), 1, st)
-            call('ocbo_segment_argmax', _p(self.F[s]), S, S, 0, _p(self.seg[s]), T,
-                 _p(self.seg_max[s]), _p(self.seg_arg[s]), 1, st)
+            self._sample_and_reduce(s, st)
             call('ocbo_joint_pick', _p(self.seg_max[s]), _p(self.seg_arg[s]), T, 0, T, S,
                  _p(self.task[s]), _p(self.action[s]), _p(self.gain[s]), 1, st)
         self.jitter[b] = (jK[0], jS[0])

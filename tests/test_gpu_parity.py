@@ -456,6 +456,54 @@ def test_segment_argmax_and_joint_pick(mods):
             assert (t2[b, s], a2[b, s], g2[b, s]) == picks.grid_only_pick(Fh[b, n_old:, s], T)
 
 
+def test_fused_sampling_tail_equals_sample_then_argmax(mods):
+    """ocbo_sample_tile_argmax (F never written) against ocbo_sample + np.max / np.argmax on the
+    materialised F: bit-identical maxima, first-index arg-max on ties (duplicate rows inside a
+    tile, equal maxima of two draws), NaN propagated like numpy, a failed problem left untouched."""
+    import ctypes
+    torch, engine = mods['torch'], mods['engine']
+    from ocbo_b200._lib import call
+    from ocbo_b200.engine import _p
+    rs = np.random.RandomState(21)
+    B, m, S = 3, 512, 64
+    L = np.tril(rs.normal(size=(B, m, m))) / np.sqrt(m)
+    Z = rs.normal(size=(B, m, S))
+    mean = rs.normal(size=(B, m))
+    # ties: row 200 repeats row 137 of problem 0 (same tile 1: 128..255) -- zero tail beyond column 137
+    L[0, 200, :] = 0.0
+    L[0, 200, :138] = L[0, 137, :138]
+    mean[0, 200] = mean[0, 137] = 50.0       # and make the pair the tile's maximum in every draw
+    Z[1, :, 5] = 0.0                          # problem 1, draw 5: F = mean, with duplicated maxima
+    mean[1, 300] = mean[1, 260] = mean[1, 383] = 9.0
+    mean[1, 17] = np.nan                      # NaN in tile 0 of problem 1: first NaN wins
+    mean[1, 90] = np.nan
+    Ld, Zd, md = engine._h2d(L), engine._h2d(Z), engine._h2d(mean)
+    info = torch.zeros(B, dtype=torch.int32, device=Ld.device)
+    info[2] = 7                               # problem 2 "failed its factorisation": skipped
+    F = torch.zeros((B, m, S), dtype=torch.float64, device=Ld.device)
+    tmax = torch.full((B, m // 128, S), -1.0, dtype=torch.float64, device=Ld.device)
+    targ = torch.full((B, m // 128, S), -5, dtype=torch.int32, device=Ld.device)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call('ocbo_sample', _p(md), m, _p(Ld), m, m, m * m, _p(Zd), S, S, m * S, _p(F), S, m * S, _p(info), B, st)
+    call('ocbo_sample_tile_argmax', _p(md), m, _p(Ld), m, m, m * m, _p(Zd), S, S, m * S, _p(tmax),
+         _p(targ), _p(info), B, st)
+    Fh, tmax, targ = F.cpu().numpy(), tmax.cpu().numpy(), targ.cpu().numpy()
+    for b in range(2):
+        tiles = Fh[b].reshape(m // 128, 128, S)
+        ref_arg = np.argmax(tiles, axis=1)
+        ref_max = np.max(tiles, axis=1)
+        assert np.array_equal(targ[b], ref_arg)
+        assert np.array_equal(tmax[b], ref_max, equal_nan=True)
+    assert (targ[0, 1] == 137 - 128).all()    # the earlier of the two equal rows
+    assert targ[1, 2, 5] == 260 - 256 and np.isnan(tmax[1, 0]).all() and (targ[1, 0] == 17).all()
+    assert (tmax[2] == -1.0).all() and (targ[2] == -5).all()
+    # the unfused reduction gives the same answers (shared comparator)
+    seg = np.stack([(128 * np.arange(m // 128 + 1)).astype(np.int32)] * B)
+    mx, ag = engine.segment_argmax(F[:2].contiguous(), S, seg[:2])
+    assert np.array_equal(mx.cpu().numpy(), tmax[:2], equal_nan=True)
+    assert np.array_equal(ag.cpu().numpy(), targ[:2])
+
+
 def test_batched_lml_matches_oracle(mods):
     from ocbo_b200.gp import hp_search
     X, y, hp = problem(17, 90, 3)

@@ -100,3 +100,26 @@ def test_sweep_falls_back_to_the_jitter_ladder():
         X, y, Xs = inputs[b]
         _, _, _, _, mu, _ = sweep_step.step(X, y, Xs, T, 2, bandwidths=0.25, return_samples=True)
         assert np.max(np.abs(mean[b] - mu)) <= 1e-8 * np.max(np.abs(mu))
+
+
+def test_sweep_device_ladder_equals_the_host_walk():
+    """SURVEY 8d's literal isotropic-0.25 configuration: Sigma is numerically singular and
+    stable_cholesky's ladder is needed.  With ``ladder_rungs`` the rungs are walked on the device
+    inside the step (no host round trip); rung, picks and gains must equal the host-walked redo
+    (same kernels on the same data), and the oracle's ladder must land within a rung."""
+    from ocbo_b200 import sweep, workload
+    n, T, A, S = 256, 8, 128, 64
+    trials = [3, 4]
+    inputs = [workload.make_trial_inputs(t, n, T, A) for t in trials]
+    host = sweep.SweepStep(n, T, A, S, 6, batch=2, bandwidths=0.25)
+    t0, a0, g0 = host.step_host(trials, inputs)
+    dev = sweep.SweepStep(n, T, A, S, 6, batch=2, bandwidths=0.25, ladder_rungs=4)
+    t1, a1, g1 = dev.step_host(trials, inputs)
+    assert all(j[1] is not None for j in dev.jitter), dev.jitter
+    assert [j[1] for j in dev.jitter] == [j[1] for j in host.jitter]
+    assert np.array_equal(t0, t1) and np.array_equal(a0, a1) and np.array_equal(g0, g1)
+    # a step that needs more rungs than were enqueued falls back to the host walk
+    short = sweep.SweepStep(n, T, A, S, 6, batch=2, bandwidths=0.25, ladder_rungs=1)
+    t2, a2, g2 = short.step_host(trials, inputs)
+    assert np.array_equal(t0, t2) and np.array_equal(a0, a2) and np.array_equal(g0, g2)
+    assert [j[1] for j in short.jitter] == [j[1] for j in host.jitter]
