@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams
 template <int BM, int BN, int WARPS_M, int WARPS_N, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
   using G = Gemm<BM, BN, false, false, WARPS_M, WARPS_N>;
-  static_assert(G::SMEM_DOUBLES >= MAXD * (BM + BN), "ring too small for the point staging");
+  static_assert(G::SMEM_DOUBLES >= (MAXD + 1) * (BM + BN), "ring too small for the point staging");
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.z;
   int ti, tj;
@@ -233,6 +233,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
     xb[d * BN + r] = Xb[e] / th[TH_BW + d];
   }
   __syncthreads();
+  // squared norms of the scaled points in numpy's summation order (dist2_np, common.cuh)
+  double* na = smem + MAXD * (BM + BN);
+  double* nb = na + BM;
+  for (int r = threadIdx.x; r < BM + BN; r += GEMM_THREADS) {
+    const double* xs = r < BM ? xa + r : xb + (r - BM);
+    const int ld = r < BM ? BM : BN;
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s = sqnorm_np(s, xs[d * ld]);
+    na[r] = s;
+  }
+  __syncthreads();
   const int mav = p.mav ? p.mav[b] : p.ma;
   const int mbv = p.mbv ? p.mbv[b] : p.mb;
   const int row0 = ti * BM, col0 = tj * BN;
@@ -247,9 +258,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int g = lane >> 2, t = lane & 3;
-    constexpr int HM = G::MI / 2;
+    constexpr int NH = 4, HM = G::MI / NH;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NH; ++h) {
       double kv[HM][G::NI][2];
 #pragma unroll
       for (int mi = 0; mi < HM; ++mi)
@@ -262,13 +273,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
             if (d < D) {
               const double xr = xa[d * BM + r];
               const double2 xc = *reinterpret_cast<const double2*>(xb + d * BN + c);
-              const double e0 = xr - xc.x, e1 = xr - xc.y;
-              d0 = fma(e0, e0, d0);
-              d1 = fma(e1, e1, d1);
+              d0 = fma(xr, xc.x, d0);
+              d1 = fma(xr, xc.y, d1);
             }
           }
-          kv[mi][ni][0] = d0;
-          kv[mi][ni][1] = d1;
+          const double2 ncol = *reinterpret_cast<const double2*>(nb + c);
+          kv[mi][ni][0] = dist2_np(na[r], ncol.x, d0);
+          kv[mi][ni][1] = dist2_np(na[r], ncol.y, d1);
         }
 #pragma unroll
       for (int mi = 0; mi < HM; ++mi)

@@ -24,6 +24,8 @@ template <int KIND>
 __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
   __shared__ double x1s[MAXD][GT];
   __shared__ __align__(16) double x2s[MAXD][GT];
+  __shared__ double n1s[GT];
+  __shared__ __align__(16) double n2s[GT];
   const int b = blockIdx.z, tj = blockIdx.x, ti = blockIdx.y;
   const bool sym = a.flags & OCBO_GRAM_SYM;
   if (sym && (a.flags & OCBO_GRAM_LOWER)) {
@@ -45,7 +47,16 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
     x2s[d][r] = (col0 + r < nv2) ? X2[(size_t)(col0 + r) * D + d] / bw : 0.0;
   }
   __syncthreads();
+  if (threadIdx.x < 2 * GT) {  // squared norms of the scaled points, numpy's summation order
+    const int r = threadIdx.x % GT;
+    double (*xs)[GT] = threadIdx.x < GT ? x1s : x2s;
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s = sqnorm_np(s, xs[d][r]);
+    (threadIdx.x < GT ? n1s : n2s)[r] = s;
+  }
+  __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const double2 nc = *reinterpret_cast<const double2*>(&n2s[2 * tx]);
   double xc0[MAXD], xc1[MAXD];
 #pragma unroll
   for (int d = 0; d < MAXD; ++d) {
@@ -67,13 +78,12 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
     for (int d = 0; d < MAXD; ++d) {
       if (d < D) {
         const double xr = x1s[d][r];
-        const double e0 = xr - xc0[d], e1 = xr - xc1[d];
-        d0 = fma(e0, e0, d0);
-        d1 = fma(e1, e1, d1);
+        d0 = fma(xr, xc0[d], d0);
+        d1 = fma(xr, xc1[d], d1);
       }
     }
-    kv[k][0] = d0;
-    kv[k][1] = d1;
+    kv[k][0] = dist2_np(n1s[r], nc.x, d0);
+    kv[k][1] = dist2_np(n1s[r], nc.y, d1);
   }
 #pragma unroll
   for (int k = 0; k < GT / 8; ++k) {
@@ -180,6 +190,7 @@ struct MeanArgs {
 template <int KIND>
 __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
   __shared__ double xs[MAXD][128];
+  __shared__ double ns[128];
   __shared__ double al[128];
   const int b = blockIdx.y;
   const int i = blockIdx.x * 128 + threadIdx.x;
@@ -192,6 +203,10 @@ __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
 #pragma unroll
   for (int d = 0; d < MAXD; ++d)
     if (d < D) xi[d] = (i < mv) ? a.Xs[(size_t)b * a.sXs + (size_t)i * D + d] / th[TH_BW + d] : 0.0;
+  double ni = 0.0;
+#pragma unroll
+  for (int d = 0; d < MAXD; ++d)
+    if (d < D) ni = sqnorm_np(ni, xi[d]);
   const double* X = a.X + (size_t)b * a.sX;
   const double* alpha = a.alpha + (size_t)b * a.sAlpha;
   double acc = 0.0;
@@ -203,6 +218,12 @@ __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
     }
     al[threadIdx.x] = (j0 + threadIdx.x < nv) ? alpha[j0 + threadIdx.x] : 0.0;
     __syncthreads();
+    {
+      double s = 0.0;
+      for (int d = 0; d < D; ++d) s = sqnorm_np(s, xs[d][threadIdx.x]);
+      ns[threadIdx.x] = s;
+    }
+    __syncthreads();
     // padded training points carry alpha = 0, so whole groups of 4 are evaluated: four
     // independent exp() chains per step instead of one (the sum order is unchanged)
     const int lim = (min(128, nv - j0) + 3) & ~3;
@@ -210,14 +231,11 @@ __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
       double kv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        double d2 = 0.0;
+        double dot = 0.0;
 #pragma unroll
         for (int d = 0; d < MAXD; ++d)
-          if (d < D) {
-            const double e = xi[d] - xs[d][j + u];
-            d2 = fma(e, e, d2);
-          }
-        kv[u] = kern_eval(KIND, scale, d2);
+          if (d < D) dot = fma(xi[d], xs[d][j + u], dot);
+        kv[u] = kern_eval(KIND, scale, dist2_np(ni, ns[j + u], dot));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc = fma(kv[u], al[j + u], acc);
