@@ -3,8 +3,8 @@
 Host mirror of /root/reference/src/cts_ocbo.py:47-140; reads the reference's option
 files unchanged (src/options/conth42.txt, conth22.txt, contbran.txt, *_sethps.txt ...).
 Every method of the reference's registry runs (cmts, cmts-pm, pei, revi, rand, ei, ts); a
-name outside it is skipped, or raises ``ValueError('Invalid method: ...')`` as at :139
-with ``--strict_methods 1``.  ``--trials_in_flight`` and rank sharding as in ocbo.py."""
+name outside it raises ``ValueError('Invalid method: ...')`` as at :139 (``--strict_methods 0``
+skips it instead).  ``--trials_in_flight`` and rank sharding as in ocbo.py."""
 import os
 import pickle as pkl
 import sys
@@ -42,7 +42,7 @@ ocbo_args = [
     get_option_specs('write_fig', False, False, 'Ignored (no plotting).'),
     get_option_specs('description', False, None, 'Free-text description.'),
     get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
-    get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
+    get_option_specs('strict_methods', False, True, 'Unknown methods raise ValueError like the reference (0: skip them).'),
 ]
 SEED = 100826730
 LAST_MERGE_STATS = [None]  # per kind (merged device passes, requests served) of the last in-flight run
@@ -75,7 +75,7 @@ def assemble_methods(f_info, options):
                                ctx_constraints=slices))
         eval_set = methods[-1].get_eval_set()
     if skipped:
-        sys.stderr.write('ocbo_b200: methods outside the MTS hot path skipped: %s\n' % ','.join(skipped))
+        sys.stderr.write('ocbo_b200: unknown method names skipped (--strict_methods 0): %s\n' % ','.join(skipped))
     if not methods:
         raise ValueError('No runnable method in: %s' % options.methods)
     return methods
@@ -103,9 +103,11 @@ def run(argv=None):
         raise ValueError('run_id not specified.')
     # One process per GPU under a launcher (torchrun): trial t runs on rank t mod W, no collective
     # inside a trial, ONE gather of the per-trial results; rank 0 writes the pickles.  Every rank
-    # assembles the same functions and methods from the same seed (``set_seed``).
+    # assembles the same functions and methods from the same stream (the seed, or rank 0's state).
     from . import dist as _dist
     rank, world_size = _dist.init_from_env()
+    if not options.set_seed:
+        _dist.share_numpy_stream()  # unseeded: every rank assembles from rank 0's stream
     rand_state = np.random.get_state()
     f_info = find_function(options.function)
     methods = assemble_methods(f_info, options)

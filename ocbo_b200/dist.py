@@ -37,6 +37,22 @@ def init_from_env():
     return world()
 
 
+def share_numpy_stream():
+    """Give every rank rank 0's global numpy stream.  The drivers build their task functions,
+    risk-neutral grids and evaluation sets from that stream before the trials are sharded; with
+    ``--set_seed 0`` the ranks' streams start from different entropy, and each rank would optimise
+    different random functions while rank 0 writes its own functions.pkl next to everybody's
+    trials.  One broadcast of the generator state makes the assembly identical everywhere."""
+    import numpy as _np
+    rank, W = world()
+    if W == 1:
+        return
+    box = [_np.random.get_state() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        _np.random.set_state(box[0])
+
+
 def gather_trials(local, trial_ids, num_trials):
     """Per-trial result objects of every rank -> list indexed by global trial id on rank 0
     (None elsewhere).  The one collective of a sharded driver run."""

@@ -187,6 +187,10 @@ def _lml_single(X, Y, kind, thetas):
 
 def select(lmls, criterion, num_samples):
     finite = np.where(np.isfinite(lmls), lmls, -np.inf)
+    if not np.isfinite(finite).any():
+        # every candidate's Gram matrix failed to factor / gave a non-finite likelihood: the
+        # arg-max (or NaN importance weights) would silently hand back candidate 0
+        raise ValueError('hyper-parameter search: no candidate has a finite log marginal likelihood')
     if criterion == 'ml' or not num_samples or num_samples < 1:
         return [int(np.argmax(finite))]
     if criterion in ('post_sampling', 'post_mean'):

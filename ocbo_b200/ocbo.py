@@ -6,8 +6,8 @@ seeds numpy with the reference's seed (:74-75), builds the task functions, runs
 ``trials`` x methods and (optionally) pickles per-trial results under
 ``write_dir/run_id`` with the reference's file names (:95-107).  Every method of the
 reference's registry runs (MTS / EI families, REVI, the agnostic and random baselines);
-a name outside it is reported and skipped, or raises ``ValueError('Invalid method: ...')``
-like the reference (:187) with ``--strict_methods 1``.  Plotting is out of scope.
+a name outside it raises ``ValueError('Invalid method: ...')`` like the reference (:187);
+``--strict_methods 0`` reports and skips it instead.  Plotting is out of scope.
 
 Two additions over the reference's sequential loop, both off by default:
 ``--trials_in_flight R`` advances R trials in lockstep and merges their device passes
@@ -50,7 +50,7 @@ docbo_args = [
     get_option_specs('max_opt_evals', False, 100, 'Candidate actions per task and step.'),
     get_option_specs('set_seed', False, True, 'Fix the global numpy seed.'),
     get_option_specs('run_ei_after', False, None, 'REVI: switch to round-robin EI after this many steps.'),
-    get_option_specs('strict_methods', False, False, 'Unknown methods raise instead of being skipped.'),
+    get_option_specs('strict_methods', False, True, 'Unknown methods raise ValueError like the reference (0: skip them).'),
     get_option_specs('chop_h4_2', False, False, 'Hartmann 4 contexts / 2 actions task set.'),
     get_option_specs('chop_h2_2', False, False, 'Hartmann 2 contexts / 2 actions task set.'),
     get_option_specs('chop_h3_1', False, False, 'Hartmann 3 contexts / 1 action task set.'),
@@ -123,7 +123,7 @@ def assemble_methods(f_infos, options, gps=None):
         methods.append(impl[0](f_infos, options, pre_tuned_gps=gps, rn_info=rn_info))
         rn_info = (methods[-1].rn_grids, methods[-1].rn_bests)
     if skipped:
-        sys.stderr.write('ocbo_b200: methods outside the MTS hot path skipped: %s\n' % ','.join(skipped))
+        sys.stderr.write('ocbo_b200: unknown method names skipped (--strict_methods 0): %s\n' % ','.join(skipped))
     if not methods:
         raise ValueError('No runnable method in: %s' % options.methods)
     if rn_info[1] is not None:  # the random risk-neutral grids give the tasks their maxima (:189-192)
@@ -155,9 +155,11 @@ def run(argv=None):
         raise ValueError('run_id not specified.')
     # One process per GPU under a launcher (torchrun): trial t runs on rank t mod W, no collective
     # inside a trial, ONE gather of the per-trial results; rank 0 writes the pickles.  Every rank
-    # assembles the same functions and methods from the same seed (``set_seed``).
+    # assembles the same functions and methods from the same stream (the seed, or rank 0's state).
     from . import dist as _dist
     rank, world_size = _dist.init_from_env()
+    if not options.set_seed:
+        _dist.share_numpy_stream()  # unseeded: every rank assembles from rank 0's stream
     rand_state = np.random.get_state()
     f_infos = assemble(options)
     methods = assemble_methods(f_infos, options, get_function_gps(f_infos, options))

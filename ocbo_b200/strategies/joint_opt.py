@@ -67,6 +67,12 @@ class JointOpt(MultiOpt):
     def _update_models(self):
         self._refit(0)  # one joint fit, not one per task
 
+    def _update_model(self, idx):
+        # the reference's JointOpt routes the per-task hook through the plural one
+        # (src/strategies/joint_opt.py:123-124), so a subclass that overrides ``_update_models``
+        # (joint-rand: no model at all unless risk-neutral) changes both
+        self._update_models()
+
     def _next_gps(self):
         shared = self.gp_fitters[0].get_next_gp()
         if 'post_sampling' in self.gp_options.hp_tune_criterion and self.tune_every > 1:
