@@ -17,6 +17,7 @@
 // (ncu: 0 shared-memory bank conflicts).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ocbo {
 
@@ -117,6 +118,77 @@ struct Gemm {
       }
     }
     cp_async_wait<0>();
+    __syncthreads();  // every warp is done with the ring: smem may be reused
+  }
+
+  // ---- TMA-fed operand stream (tma.cuh): same ring, same fragment addressing -----------------
+  // A tile origin (a_in, a_row) and B tile origin (b_in, b_row) in their tensor maps' frames
+  // (inner = contiguous coordinate); the k coordinate advances along the inner axis of a k-major
+  // operand and along the row axis otherwise.  ``it`` numbers the k-tiles a CTA has consumed since
+  // the barriers were initialised (stage = it % STAGES, phase parity = (it / STAGES) & 1), so a CTA
+  // that computes several tiles keeps one running count.
+  static constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+  struct TmaTile {
+    const CUtensorMap* mA; int a_in, a_row, a_b;
+    const CUtensorMap* mB; int b_in, b_row, b_b;
+  };
+  __device__ __forceinline__ static uint64_t* tma_barriers(double* smem) {
+    return reinterpret_cast<uint64_t*>(smem + SMEM_DOUBLES);
+  }
+  static constexpr int TMA_SMEM_BYTES = SMEM_BYTES + 64;
+  __device__ __forceinline__ static void tma_init(double* smem) {
+    if (threadIdx.x == 0) {
+      uint64_t* full = tma_barriers(smem);
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+      mbar_init_fence();
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ static void tma_issue(const TmaTile& t, int kt, int it, double* smem) {
+    double* st = smem + (it % STAGES) * STAGE_DOUBLES;
+    uint64_t* bar = tma_barriers(smem) + (it % STAGES);
+    mbar_expect_tx(bar, STAGE_BYTES);
+    if (A_KMAJ) tma_load_3d(st, t.mA, bar, t.a_in + kt * BK, t.a_row, t.a_b);
+    else tma_load_3d(st, t.mA, bar, t.a_in, t.a_row + kt * BK, t.a_b);
+    if (B_KMAJ) tma_load_3d(st + TA::SIZE, t.mB, bar, t.b_in + kt * BK, t.b_row, t.b_b);
+    else tma_load_3d(st + TA::SIZE, t.mB, bar, t.b_in, t.b_row + kt * BK, t.b_b);
+  }
+  __device__ __forceinline__ static void tma_prologue(const TmaTile& t, int ktiles, int it0, double* smem) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES - 1; ++s)
+        if (s < ktiles) tma_issue(t, s, it0 + s, smem);
+    }
+  }
+  // acc += A B over ``ktiles`` k-tiles; tma_prologue(t, ktiles, it0) must have been called.
+  __device__ __forceinline__ static void tma_mainloop(const TmaTile& t, int ktiles, int it0, double* smem,
+                                                      Acc& acc) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int g = lane >> 2, tt = lane & 3;
+    uint64_t* full = tma_barriers(smem);
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int it = it0 + kt;
+      mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
+      __syncthreads();  // every warp is past k-tile kt-1: its stage may be refilled
+      if (tid == 0 && kt + STAGES - 1 < ktiles) tma_issue(t, kt + STAGES - 1, it + STAGES - 1, smem);
+      const double* sa = smem + (it % STAGES) * STAGE_DOUBLES;
+      const double* sb = sa + TA::SIZE;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MI], b[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) a[mi] = TA::frag(sa, wm * WM + mi * 8 + g, kk * 4 + tt);
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) b[ni] = TB::frag(sb, wn * WN + ni * 8 + g, kk * 4 + tt);
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    }
     __syncthreads();  // every warp is done with the ring: smem may be reused
   }
 

@@ -1,5 +1,8 @@
 // DMMA tile kernels: C (-)= P Q^T, C (-)= P R, Sigma = K(Xa,Xb) - V1^T V2.
 // 128 x 64 tiles, 256 threads, two CTAs per SM (see gemm_core.cuh).
+#include <cstdlib>
+#include <cstring>
+
 #include "gemm_core.cuh"
 #include "kernels.h"
 
@@ -15,10 +18,11 @@ constexpr int TRI_BAND = 8;  // row tiles per band of the triangular tile order 
 //           mode 0): the CTA owns complete rows of the 128-wide panel, so reading
 //           P over the whole k range and then overwriting it is race free.
 // ---------------------------------------------------------------------------
-template <int BM, int BN, int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(NtParams p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TMA>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ, NtParams p) {
   using G = Gemm<BM, BN, true, true, WARPS_M, WARPS_N>;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
   if (p.info && p.info[b] != 0) return;
   int ti, tj;
@@ -35,16 +39,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(NtParams p) {
   const int ldc = p.ldc;
 
   typename G::Acc acc;
-  G::prologue(P, p.ldp, Q, p.ldq, p.ktiles, smem);
+  // operand tiles by TMA (one thread, mbarrier transaction counts) or by cp.async (all threads)
+  typename G::TmaTile tile{&mapP, 0, ti * BM, p.sP ? b : 0, &mapQ, 0, tj * BN, p.sQ ? b : 0};
+  if (TMA) {
+    G::tma_init(smem);
+    G::tma_prologue(tile, p.ktiles, 0, smem);
+  } else {
+    G::prologue(P, p.ldp, Q, p.ldq, p.ktiles, smem);
+  }
+  if (p.mode == 0) G::zero(acc);
+  else G::load_negated(acc, C, ldc);
+  if (TMA) G::tma_mainloop(tile, p.ktiles, 0, smem, acc);
+  else G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
   if (p.mode == 0) {
-    G::zero(acc);
-    G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
       *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(v0, v1);
     });
   } else {
-    G::load_negated(acc, C, ldc);
-    G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
       *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(-v0, -v1);
     });
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(NtParams p) {
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
   using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
   if (p.info && p.info[b] != 0) return;
   const int tj = blockIdx.x;
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams p) {
   using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
   if (p.info && p.info[b] != 0) return;
   const int tj = blockIdx.x;
@@ -194,11 +205,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams
 // The Gram term is evaluated in the epilogue from points staged (pre-scaled by
 // 1/bandwidth) in the drained cp.async ring, so K(Xs,Xs) never exists in HBM.
 // ---------------------------------------------------------------------------
-template <int BM, int BN, int WARPS_M, int WARPS_N, int KIND>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, int KIND, bool TMA>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+postcov_kernel(const __grid_constant__ CUtensorMap mapV1, const __grid_constant__ CUtensorMap mapV2, CovParams p) {
   using G = Gemm<BM, BN, false, false, WARPS_M, WARPS_N>;
   static_assert(G::SMEM_DOUBLES >= (MAXD + 1) * (BM + BN), "ring too small for the point staging");
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
   int ti, tj;
   if (p.tri) {
@@ -213,8 +225,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) postcov_kernel(CovParams p) {
 
   typename G::Acc acc;
   G::zero(acc);
-  G::prologue(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem);
-  G::mainloop(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem, acc);
+  if (TMA) {
+    typename G::TmaTile tile{&mapV1, ti * BM, 0, p.sV1 ? b : 0, &mapV2, tj * BN, 0, p.sV2 ? b : 0};
+    G::tma_init(smem);
+    G::tma_prologue(tile, p.ktiles, 0, smem);
+    G::tma_mainloop(tile, p.ktiles, 0, smem, acc);
+  } else {
+    G::prologue(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem);
+    G::mainloop(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem, acc);
+  }
 
   // stage scaled points: xa[d][BM], xb[d][BN]
   const int D = p.dim;
@@ -316,21 +335,46 @@ static cudaError_t ensure_smem(K kernel, int bytes, bool& done) {
   return e;
 }
 
+// OCBO_TMA=0 keeps every operand load on cp.async (the round-1 path), for A/B measurements
+static bool use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCBO_TMA");
+    v = (e ? atoi(e) != 0 : 1) && tma_encoder() != nullptr;
+  }
+  return v != 0;
+}
+
 cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st, int panel) {
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
+  CUtensorMap mP, mQ;
+  memset(&mP, 0, sizeof(mP));
+  memset(&mQ, 0, sizeof(mQ));
   if (panel) {
     using G = Gemm<TM / 2, TILE, true, true, 2, 4>;
     static bool init = false;
-    cudaError_t e = ensure_smem(gemm_nt_kernel<TM / 2, TILE, 2, 4>, G::SMEM_BYTES, init);
+    cudaError_t e = ensure_smem(gemm_nt_kernel<TM / 2, TILE, 2, 4, false>, G::SMEM_BYTES, init);
     if (e != cudaSuccess) return e;
-    gemm_nt_kernel<TM / 2, TILE, 2, 4><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
-  } else {
-    using G = Gemm<TM, TN, true, true, 4, 2>;
-    static bool init = false;
-    cudaError_t e = ensure_smem(gemm_nt_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
-    if (e != cudaSuccess) return e;
-    gemm_nt_kernel<TM, TN, 4, 2><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+    gemm_nt_kernel<TM / 2, TILE, 2, 4, false><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(mP, mQ, p);
+    return counted(cudaGetLastError());
   }
+  using G = Gemm<TM, TN, true, true, 4, 2>;
+  // region extents in rows: lower-triangular launches enumerate R x 2R tiles of a square region
+  const int64_t rowsP = p.tri ? (int64_t)(p.ntc / (TILE / TN)) * TILE : (int64_t)(ntiles / p.ntc) * TM;
+  const int64_t rowsQ = (int64_t)p.ntc * TN;
+  const uint64_t kext = (uint64_t)p.ktiles * BK;
+  if (use_tma() && tma_make_map(&mP, p.P, kext, rowsP, p.ldp, p.sP, batch, BK + 4, TM) &&
+      tma_make_map(&mQ, p.Q, kext, rowsQ, p.ldq, p.sQ, batch, BK + 4, TN)) {
+    static bool init = false;
+    cudaError_t e = ensure_smem(gemm_nt_kernel<TM, TN, 4, 2, true>, G::TMA_SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    gemm_nt_kernel<TM, TN, 4, 2, true><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::TMA_SMEM_BYTES, st>>>(mP, mQ, p);
+    return counted(cudaGetLastError());
+  }
+  static bool init = false;
+  cudaError_t e = ensure_smem(gemm_nt_kernel<TM, TN, 4, 2, false>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
+  gemm_nt_kernel<TM, TN, 4, 2, false><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(mP, mQ, p);
   return counted(cudaGetLastError());
 }
 
@@ -357,10 +401,22 @@ cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStre
 template <int KIND>
 static cudaError_t launch_postcov_kind(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
   using G = Gemm<TM, TN, false, false, 4, 2>;
+  CUtensorMap m1, m2;
+  memset(&m1, 0, sizeof(m1));
+  memset(&m2, 0, sizeof(m2));
+  const uint64_t kext = (uint64_t)p.ktiles * BK;
+  if (kext > 0 && use_tma() && tma_make_map(&m1, p.V1, p.ma, kext, p.ldv1, p.sV1, batch, TM + 4, BK) &&
+      tma_make_map(&m2, p.V2, p.mb, kext, p.ldv2, p.sV2, batch, TN + 4, BK)) {
+    static bool init = false;
+    cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2, KIND, true>, G::TMA_SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    postcov_kernel<TM, TN, 4, 2, KIND, true><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::TMA_SMEM_BYTES, st>>>(m1, m2, p);
+    return counted(cudaGetLastError());
+  }
   static bool init = false;
-  cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2, KIND>, G::SMEM_BYTES, init);
+  cudaError_t e = ensure_smem(postcov_kernel<TM, TN, 4, 2, KIND, false>, G::SMEM_BYTES, init);
   if (e != cudaSuccess) return e;
-  postcov_kernel<TM, TN, 4, 2, KIND><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  postcov_kernel<TM, TN, 4, 2, KIND, false><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(m1, m2, p);
   return counted(cudaGetLastError());
 }
 
