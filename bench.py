@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--sweep-trials', type=int, default=512,
                     help='trials of the fixed-work (strong-scaling) leg; 0 skips it')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-ladder-variant', action='store_true')
     return ap.parse_args()
 
 
@@ -301,6 +302,50 @@ def check_trial(torch, grp, trial, ref, acc):
     return acc
 
 
+def run_ladder_variant(torch, sweep, streams, B, args, steps=3, rungs=3):
+    """SURVEY 8d's LITERAL configuration -- isotropic bandwidth 0.25 -- beside the headline: Sigma is
+    numerically singular (cond ~ 1e16), so every trial walks stable_cholesky's jitter ladder.  The
+    rungs are enqueued on the device inside the step (SweepStep(ladder_rungs=...)): same host-buffer
+    API, H2D / D2H in the clock, no host round trip per rung."""
+    from ocbo_b200.workload import ISOTROPIC_BANDWIDTHS
+    try:
+        groups = [sweep.SweepStep(N_OBS, N_TASK, N_ACT, N_DRAW, DIM, batch=B, stream=s,
+                                  bandwidths=ISOTROPIC_BANDWIDTHS, ladder_rungs=rungs) for s in streams]
+        G = len(groups)
+        ids = lambda step, g: [10000 + (step * G + g) * B + b for b in range(B)]
+        pool = {t: make_trial_inputs(t, N_OBS, N_TASK, N_ACT)
+                for step in range(steps + 1) for g in range(G) for t in ids(step, g)}
+        hist, redone = {}, 0
+
+        def one(step):
+            nonlocal redone
+            for g, grp in enumerate(groups):
+                grp.submit_host(ids(step, g), [pool[t] for t in ids(step, g)])
+            for grp in groups:
+                grp.result_host()
+                for _, r in grp.jitter:
+                    hist[str(r)] = hist.get(str(r), 0) + 1
+                redone += int(np.count_nonzero(grp.hinfo.numpy().any(axis=0)))
+        one(0)
+        hist.clear()
+        redone = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one(1 + k)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        del groups
+        torch.cuda.empty_cache()
+        return {'workload': 'as config.workload but SE-ARD bandwidth 0.25 on all 6 dims (SURVEY 8d literal)',
+                'value': G * B * N_DRAW * steps / wall, 'unit': UNIT, 'ms_per_step': 1e3 * wall / steps,
+                'trials_per_step': G * B, 'steps': steps, 'device_ladder_rungs_enqueued': rungs,
+                'jitter_rung_histogram': hist, 'trials_redone_from_the_host': redone,
+                'timing': 'wall clock around submit_host/result_host (host buffers, copies inside)'}
+    except Exception as exc:  # secondary figure: never lose the headline line
+        return {'error': repr(exc)}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -501,27 +546,66 @@ def run_b200(args):
         peak = peaks.get('cublas_dgemm_tflops')
         step_tflops = step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
             / (ms_resident * 1e-3) / 1e12
+        # ---- the other DMMA launch classes of the step, CUDA events on the group's own stream ----
+        def timed(fn, reps=3):
+            best = 1e9
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(grp.stream)
+                fn()
+                e1.record(grp.stream)
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            return best
+
+        def postcov():
+            lib_call('ocbo_post_cov', grp.kind, DIM, ctypes.c_void_p(grp.Xs.data_ptr()), m,
+                     grp.Xs.stride(0), None, ctypes.c_void_p(grp.V.data_ptr()), N_OBS, m, grp.V.stride(0),
+                     ctypes.c_void_p(grp.theta.data_ptr()), grp.theta.stride(0),
+                     ctypes.c_void_p(grp.Sigma.data_ptr()), m, grp.Sigma.stride(0), 1, B, st)
+        ms_cov = timed(postcov)
+        grp.run()                       # leaves a valid factor in Sigma for the sampling product
+        torch.cuda.synchronize()
+        ms_lz = timed(lambda: grp._sample_and_reduce(slice(0, B), st))
+        tf = lambda flops, ms: flops * B / (ms * 1e-3) / 1e12
+        frac = lambda v: (v / peak) if (peak and v) else None
+        cov_tf, lz_tf = tf(float(N_OBS) * m * m, ms_cov), tf(float(m) * m * N_DRAW, ms_lz)
+        step_per_gpu = step_tflops / world
         roof = {
             'bound': 'tensor',
-            'kernel': 'gemm_nt_kernel<128,64> in its rank-%d trailing updates of chol(Sigma) '
-                      '(DMMA.8x8x4 fp64; %.0f%% of the factorisation update flops)' % (
-                          ot * 128, 100.0 * alg_outer / max(alg, 1.0)),
-            'achieved': trailing_tflops, 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': (trailing_tflops / peak) if (peak and trailing_tflops) else None,
+            # the step-level figure leads: every kernel of the path, 16 trials in flight, algorithmic
+            # (triangular-aware) flops of BASELINE.md section 4 over the timed region
+            'scope': 'whole step, all kernels (algorithmic 278.12 GFLOP per trial-step)',
+            'achieved': step_per_gpu, 'peak': peak, 'unit': 'TFLOP/s', 'frac': frac(step_per_gpu),
+            'step_tflops_per_gpu': step_per_gpu, 'step_frac_of_peak': frac(step_per_gpu),
             'traffic': load_traffic(B),
             'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
                            'MEASURED_PEAKS.json has no FP64 row',
+            'dominant_kernel': 'gemm_nt_kernel<128,64> (DMMA.8x8x4 fp64): Cholesky rank-k updates, '
+                               '~55 % of the device time of a step',
+            # launches of ONE group (batch trials) serialised on an otherwise idle GPU: short-k / small-grid
+            # classes cannot fill 148 SMs alone -- in the timed region the other 7 streams do
+            'by_launch_class': {
+                'chol_rank%d_trailing_updates' % (ot * 128): {
+                    'tflops': trailing_tflops, 'frac': frac(trailing_tflops),
+                    'share_of_update_flops': alg_outer / max(alg, 1.0), 'ms': ms3[3]},
+                'chol_all_update_launches': {'tflops': all_updates_tflops, 'frac': frac(all_updates_tflops),
+                                             'ms': ms_upd},
+                'posterior_covariance_k%d' % N_OBS: {'tflops': cov_tf, 'frac': frac(cov_tf), 'ms': ms_cov},
+                'sample_LZ_fused_argmax': {'tflops': lz_tf, 'frac': frac(lz_tf), 'ms': ms_lz,
+                                           'fused_tail': bool(grp.fused_tail)},
+            },
             'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],
                          'outer_update': ms3[3], 'batch': B,
                          'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 2048)),
-                         'inner': os.environ.get('OCBO_POTRF_INNER', 'left'),
-                         'note': 'serialised launches of ONE group (batch trials) on an otherwise idle '
-                                 'GPU; in the timed region 16 trials overlap'},
+                         'inner': os.environ.get('OCBO_POTRF_INNER', 'left')},
+            'operand_loads': 'cp.async' if os.environ.get('OCBO_TMA', '1') == '0' else 'TMA (cp.async.bulk.tensor)',
             'all_update_launches_tflops': all_updates_tflops,
-            'step_tflops_per_gpu': step_tflops / world,
-            'step_frac_of_peak': (step_tflops / world / peak) if peak else None,
             'fp64_probes_tflops': peaks,
         }
+        ladder_variant = None
+        if world == 1 and not args.no_ladder_variant:
+            ladder_variant = run_ladder_variant(torch, sweep, streams, B, args)
         cpu, parity = None, None
         if not args.no_cpu_baseline and world == 1:
             cpu_step_seconds(0)  # warm BLAS threads
@@ -557,6 +641,7 @@ def run_b200(args):
             'parity_checked': bool(parity and parity['ok']),
             'parity': parity,
             'sweep_fixed_trials': sweep_fixed,
+            'ladder_variant': ladder_variant,
         }
         if not args.no_cpu_baseline and world == 1:
             # second half of BASELINE.json's metric: MTS BO decision steps/s at the option-file

@@ -118,14 +118,6 @@ int ocbo_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t s_a,
                       int32_t* info, const int32_t* info1, int32_t* rung, int p, int batch,
                       ocbo_stream_t stream);
 
-/* ocbo_potrf with CUDA events around every launch, summed per kernel class into
- * ms_host[4] = { diagonal-block, panel-solve, in-panel rank-128 update,
- * outer rank-k trailing update } milliseconds.
- * Synchronises the stream; used by bench.py's roofline leg only. */
-int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a,
-                       double* invdiag, int32_t* info, int batch, ocbo_stream_t stream,
-                       float* ms_host);
-
 /* B <- L^{-1} B  (left, lower, non-transposed), B is n x nrhs row-major.
  * Replaces solve_lower_triangular(L, K(X*, X)^T)  (src/gp/gp_interface.py:116,118;
  * Dragonfly eval 'covar'). */
@@ -282,6 +274,21 @@ int ocbo_kg(const double* judge_means, int ld_means, const double* inter, int64_
             const double* cand_var, double noise, int C, int G, int E, double* kg,
             ocbo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * OCBO_BENCH section -- measurement helpers for bench.py, NOT part of the drop-in path and
+ * exempt from the "never synchronise, never allocate" contract above: they create CUDA events
+ * and wait for the stream.  No product code calls them.
+ * ------------------------------------------------------------------------------------------ */
+#ifndef OCBO_NO_BENCH
+
+/* ocbo_potrf with CUDA events around every launch, summed per kernel class into
+ * ms_host[4] = { diagonal-block, panel-solve, in-panel rank-128 update,
+ * outer rank-k trailing update } milliseconds.
+ * SYNCHRONISES the stream and creates / destroys CUDA events. */
+int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a,
+                       double* invdiag, int32_t* info, int batch, ocbo_stream_t stream,
+                       float* ms_host);
+
 /* FP64 throughput probes used by bench.py to measure the DMMA / DFMA rate the
  * roofline is quoted against (MEASURED_PEAKS.json has no FP64 row).
  * Each thread block runs `iters` dependent-free DMMA.8x8x4 / DFMA chains. */
@@ -291,6 +298,8 @@ int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream);
  * DMMA tile core -- the GEMM-shaped roofline reference for the core itself. */
 int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n,
                         ocbo_stream_t stream);
+
+#endif /* OCBO_NO_BENCH */
 
 #ifdef __cplusplus
 }

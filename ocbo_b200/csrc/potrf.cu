@@ -9,180 +9,22 @@
 namespace ocbo {
 
 constexpr int NB = TILE;        // 128
-constexpr int LDS_ = NB + 1;    // padded smem leading dimension
-constexpr int PD_THREADS = 4 * NB;
-constexpr int MB = 16;          // micro-block of the blocked triangular inverse
 
-// Factor the NB x NB diagonal block at (j0, j0): A = L L^T (lower referenced).
-// Output: L in place (strictly upper part of the block zeroed) and inv(L) to
-// invdiag (full NB x NB, upper part zero).
-// Shared-memory layout: one (NB x NB+1) array; the lower triangle holds L, the
-// strictly upper triangle holds inv(L)^T, diag of inv(L) in dinv[].
-// Failure (pivot <= 0 or NaN, LAPACK dpotrf convention) -> info[b] = column+1.
-//
-// Phase 1 (factor): right-looking, one column per step, two barriers per step;
-//   the rank-1 update keeps l_i / l_j in registers and only walks the rows and
-//   column passes that are still inside the trailing triangle (warp-uniform
-//   bounds), so the work shrinks with the triangle.
-// Phase 2 (inverse): 16 x 16 diagonal micro-blocks are inverted by forward
-//   substitution in registers (8 blocks in parallel), then block row I of
-//   X = L^{-1} is  X_I,: = -inv(L_II) * (L_I,<I * X_<I,:)  -- two short dot
-//   products per element, 7 sequential block rows instead of 127 scalar rows.
-__global__ void __launch_bounds__(PD_THREADS, 1)
-potrf_diag_kernel(double* A, int lda, int64_t sA, int j0, double* invdiag, int64_t sInv,
-                  int32_t* info) {
-  extern __shared__ double sm[];
-  double* As = sm;                  // NB * LDS_
-  double* col = sm + NB * LDS_;     // NB
-  double* dinv = col + NB;          // NB
-  double* Tm = dinv + NB;           // MB * LDS_  (temporary of the blocked inverse)
-  const int b = blockIdx.x;
-  if (info[b] != 0) return;
-  const int tid = threadIdx.x;
-  double* Ab = A + (size_t)b * sA + (size_t)j0 * lda + j0;
-
-  for (int e = tid; e < NB * NB; e += PD_THREADS) {
-    const int r = e / NB, c = e % NB;
-    As[r * LDS_ + c] = (c <= r) ? Ab[(size_t)r * lda + c] : 0.0;
-  }
-  const int tx = tid & 31, ty = tid >> 5;  // 32 lanes x 16 warps
-  int fail = 0;
-  for (int k = 0; k < NB; ++k) {
-    __syncthreads();
-    const double akk = As[k * LDS_ + k];
-    if (!(akk > 0.0)) {  // also catches NaN
-      fail = k + 1;
-      break;  // uniform: every thread read the same value
-    }
-    const double rinv = rsqrt(akk);
-    if (tid > k && tid < NB) {
-      const double l = As[tid * LDS_ + k] * rinv;
-      col[tid] = l;
-      As[tid * LDS_ + k] = l;
-    }
-    if (tid == k) As[k * LDS_ + k] = akk * rinv;
-    __syncthreads();
-    const int base = k + 1;
-    const int rem = NB - base;                       // trailing rows / cols
-    const int na = (rem > ty) ? (rem - ty + 15) >> 4 : 0;  // rows of this warp
-    const int nbp = (rem + 31) >> 5;                 // 32-wide column passes
-    double lj[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = base + tx + 32 * q;
-      lj[q] = (q < nbp && j < NB) ? col[j] : 0.0;
-    }
-    for (int a = 0; a < na; ++a) {
-      const int i = base + ty + 16 * a;
-      const double li = col[i];
-      double* row = As + i * LDS_;
-      double v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = base + tx + 32 * q;
-        v[q] = (q < nbp && j <= i) ? row[j] : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = base + tx + 32 * q;
-        if (q < nbp && j <= i) row[j] = fma(-li, lj[q], v[q]);
-      }
-    }
-  }
-  if (fail) {
-    if (tid == 0) info[b] = j0 + fail;
-    return;
-  }
-  __syncthreads();
-  // L back to global, strictly upper part of the block zeroed
-  for (int e = tid; e < NB * NB; e += PD_THREADS) {
-    const int r = e / NB, c = e % NB;
-    Ab[(size_t)r * lda + c] = (c <= r) ? As[r * LDS_ + c] : 0.0;
-  }
-  // ---- phase 2a: invert the 16 x 16 diagonal micro-blocks (thread = column) ----
-  if (tid < NB) {
-    const int c = tid, blk = c / MB, cl = c % MB, r0 = blk * MB;
-    double x[MB];
-#pragma unroll
-    for (int i = 0; i < MB; ++i) {
-      double s = (i == cl) ? 1.0 : 0.0;
-#pragma unroll
-      for (int kk = 0; kk < MB; ++kk)
-        if (kk < i) s = fma(-As[(r0 + i) * LDS_ + r0 + kk], (kk >= cl) ? x[kk] : 0.0, s);
-      x[i] = (i >= cl) ? s / As[(r0 + i) * LDS_ + r0 + i] : 0.0;
-    }
-    // every thread must finish READING the lower micro-block before the upper
-    // part is written: the upper storage of this block is disjoint from the
-    // lower triangle, so plain stores are safe.
-#pragma unroll
-    for (int i = 0; i < MB; ++i) {
-      if (i == cl) dinv[c] = x[i];
-      else if (i > cl) As[c * LDS_ + r0 + i] = x[i];
-    }
-  }
-  __syncthreads();
-  // ---- phase 2b: block rows I = 1 .. 7 ------------------------------------------
-  for (int I = 1; I < NB / MB; ++I) {
-    const int r0 = I * MB;         // first row of block row I; columns c < r0
-    // T[il][c] = sum_{k=c}^{r0-1} L[r0+il][k] * X[k][c]
-    for (int e = tid; e < MB * r0; e += PD_THREADS) {
-      const int il = e / r0, c = e % r0;
-      const double* Li = As + (r0 + il) * LDS_;
-      const double* Xc = As + c * LDS_;   // X[k][c] at Xc[k], k > c
-      double s0 = Li[c] * dinv[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = c + 1;
-      for (; k + 3 < r0; k += 4) {
-        s0 = fma(Li[k], Xc[k], s0);
-        s1 = fma(Li[k + 1], Xc[k + 1], s1);
-        s2 = fma(Li[k + 2], Xc[k + 2], s2);
-        s3 = fma(Li[k + 3], Xc[k + 3], s3);
-      }
-      for (; k < r0; ++k) s0 = fma(Li[k], Xc[k], s0);
-      Tm[il * LDS_ + c] = (s0 + s1) + (s2 + s3);
-    }
-    __syncthreads();
-    // X[r0+il][c] = - sum_{i2 <= il} invLII[il][i2] * T[i2][c]
-    for (int e = tid; e < MB * r0; e += PD_THREADS) {
-      const int il = e / r0, c = e % r0;
-      double s = dinv[r0 + il] * Tm[il * LDS_ + c];
-      for (int i2 = 0; i2 < il; ++i2) s = fma(As[(r0 + i2) * LDS_ + r0 + il], Tm[i2 * LDS_ + c], s);
-      As[c * LDS_ + r0 + il] = -s;
-    }
-    __syncthreads();
-  }
-  double* Inv = invdiag + (size_t)b * sInv + (size_t)(j0 / NB) * NB * NB;
-  for (int e = tid; e < NB * NB; e += PD_THREADS) {
-    const int r = e / NB, c = e % NB;
-    double v = 0.0;
-    if (c == r) v = dinv[r];
-    else if (c < r) v = As[c * LDS_ + r];
-    Inv[e] = v;
-  }
-}
-
+// The NB x NB diagonal block at (j0, j0): A = L L^T (lower referenced), L in place and inv(L)
+// to invdiag.  Failure (pivot <= 0 or NaN, LAPACK dpotrf convention) -> info[b] = column + 1.
+// Two register-resident kernels implement it: the blocked one (potrf_diag_blk.cu, default) and
+// the column-per-barrier one it is bit-identical to (potrf_diag_reg.cu, OCBO_DIAG_KERNEL=reg,
+// kept for that test).  The first shared-memory version (140 us per block) is gone.
 cudaError_t launch_potrf_diag(double* A, int lda, int64_t sA, int j0, double* invdiag,
                               int64_t sInv, int32_t* info, int batch, cudaStream_t st,
                               const int32_t* nv) {
-  // default: blocked register-resident kernel (potrf_diag_blk.cu); OCBO_DIAG_KERNEL=reg keeps
-  // the column-per-barrier register kernel and =smem the shared-memory version selectable
-  // for A/B measurements (blk and reg are bit-identical)
   static int which = -1;
   if (which < 0) {
     const char* e = getenv("OCBO_DIAG_KERNEL");
-    which = !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'r' ? 1 : 2));
+    which = (e && e[0] == 'r') ? 1 : 2;
   }
-  if (which == 2) return launch_potrf_diag_blk(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
   if (which == 1) return launch_potrf_diag_reg(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
-  constexpr int SMEM = (NB * LDS_ + 2 * NB + MB * LDS_) * 8;
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
-  potrf_diag_kernel<<<batch, PD_THREADS, SMEM, st>>>(A, lda, sA, j0, invdiag, sInv, info);
-  return counted(cudaGetLastError());
+  return launch_potrf_diag_blk(A, lda, sA, j0, invdiag, sInv, info, batch, st, nv);
 }
 
 // ---------------------------------------------------------------------------

@@ -203,6 +203,7 @@ class StepPlan(object):
     MAX_PLANS = 24
     _plans = {}
     _order = []
+    last_run = None  # the plan replayed most recently (measurement hooks: device_ms_per_replay)
 
     @classmethod
     def get(cls, key, capacity):
@@ -246,12 +247,14 @@ class StepPlan(object):
             torch.cuda.synchronize()
             self.outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
             g = torch.cuda.CUDAGraph()
+            launches0 = int(_lib.LIB.ocbo_launch_count())
             with torch.cuda.graph(g):
                 self.dev[:self.used].copy_(self.host[:self.used], non_blocking=True)
                 outs = body(self.staged, self.ext)
                 for h, o in zip(self.outs_host, outs):
                     h.copy_(o, non_blocking=True)
             self.graph = g
+            self.kernels = int(_lib.LIB.ocbo_launch_count()) - launches0  # library kernels in the graph
         else:
             if self.used != self.used0:
                 raise RuntimeError('StepPlan: staged layout changed under a fixed shape key')
@@ -266,7 +269,24 @@ class StepPlan(object):
         else:
             self.graph.replay()
         self.replays += 1
+        StepPlan.last_run = self
         return self.results() if wait else None
+
+    def device_ms_per_replay(self, reps=20):
+        """Device time of one replay of this plan's graph (H2D of the arena, every kernel, D2H of
+        the results), replays back to back with CUDA events around them -- no host work between."""
+        if self.graph is None:
+            return None
+        st = torch.cuda.current_stream()
+        self.graph.replay()
+        st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            self.graph.replay()
+        e1.record(st)
+        st.synchronize()
+        return e0.elapsed_time(e1) / reps
 
     def results(self):
         self._stream.synchronize()

@@ -42,6 +42,6 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'child':
         child()
     else:
-        for variant in ('smem', 'reg', 'blk'):
+        for variant in ('reg', 'blk'):
             subprocess.run([sys.executable, os.path.abspath(__file__), 'child'],
                            env=dict(os.environ, OCBO_DIAG_KERNEL=variant), check=False)

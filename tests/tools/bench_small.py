@@ -46,6 +46,49 @@ def _hp(X, y):
     return dict(scale=v, bw=0.3 * (X.max(0) - X.min(0) + 1e-3), noise=0.01 * v, mu0=float(np.median(y)))
 
 
+FP64_CORE_TFLOPS = 33.5   # DFMA issue rate measured on this pool's B200 (bench.py ocbo_probe_dfma)
+HBM_GBS = 6551.0          # MEASURED_PEAKS.json
+
+
+def _step_work(name):
+    """Algorithmic flops and minimum HBM bytes of ONE decision at the bench shapes (symmetric /
+    triangular aware, as BASELINE.md section 4): chol(K) n^3/3, V = L^-1 K n^2 m, Sigma n m^2,
+    chol(Sigma) m^3/3, sample m^2 -- per problem."""
+    per = lambda n, m: n ** 3 / 3.0 + float(n) ** 2 * m + float(n) * m ** 2 + m ** 3 / 3.0 + float(m) ** 2
+    byts = lambda n, m: 8.0 * (n * n / 2.0 + n * m + m * m / 2.0) * 2  # factor + V + Sigma written and read once
+    if name == 'set2d':
+        return 5 * per(50, 150), 5 * byts(50, 150)
+    if name == 'rand6d':
+        return 30 * per(55, 155), 30 * byts(55, 155)
+    if name == 'jointbran':
+        return per(160, 1160), byts(160, 1160)
+    n = 755  # conth42: one posterior, 50 contexts x 100 actions
+    return n ** 3 / 3.0 + 50 * (float(n) ** 2 * 100 + n * 100.0 ** 2 + 100 ** 3 / 3.0 + 100.0 ** 2), \
+        8.0 * (n * n + 50 * (n * 100 + 100 * 100)) * 2
+
+
+def _limiter(name, wall_ms):
+    """What bounds a decision at this shape: device time of the step's CUDA graph replayed back to
+    back (no host work between), the host share of the wall time, kernels per step, and the device
+    time against the FP64 CUDA-core and HBM rooflines.  These steps are chains of 25-60 dependent
+    kernels on matrices of 128-1280 rows: the bound that binds is launch / dependency LATENCY
+    (device_ms / kernels = a few us per kernel), not a throughput roofline."""
+    from ocbo_b200 import engine
+    plan = engine.StepPlan.last_run
+    if plan is None or plan.graph is None:
+        return {}
+    dev_ms = plan.device_ms_per_replay()
+    flops, byts = _step_work(name)
+    t_flop, t_hbm = flops / (FP64_CORE_TFLOPS * 1e12) * 1e3, byts / (HBM_GBS * 1e9) * 1e3
+    return {'wall_ms': wall_ms, 'device_ms': dev_ms, 'host_ms': max(wall_ms - dev_ms, 0.0),
+            'kernels_per_step': plan.kernels, 'us_per_kernel': 1e3 * dev_ms / max(plan.kernels, 1),
+            'algorithmic_gflop': flops / 1e9,
+            'fp64_core_bound_ms': t_flop, 'hbm_bound_ms': t_hbm,
+            'device_frac_of_fp64_core_roofline': t_flop / dev_ms, 'device_frac_of_hbm_roofline': t_hbm / dev_ms,
+            'limiter': 'latency: %d dependent kernels at %.1f us each; host staging + launch is %.0f %% of the wall time'
+                       % (plan.kernels, 1e3 * dev_ms / max(plan.kernels, 1), 100.0 * max(wall_ms - dev_ms, 0.0) / wall_ms)}
+
+
 def measure(gpu_reps=20, cpu_reps=3, cpu=True):
     import torch
     from ocbo_b200 import batched, synth
@@ -133,7 +176,12 @@ def measure(gpu_reps=20, cpu_reps=3, cpu=True):
     # device passes first, then the host loops: BLAS worker threads keep spinning after a LAPACK
     # call and would steal the core that launches the next device step
     for name, gpu_f, _, shape in jobs:
-        out[name] = {'b200_steps_per_s': 1 / _timeit(gpu_f, gpu_reps, sync), 'shape': shape}
+        dt = _timeit(gpu_f, gpu_reps, sync)
+        out[name] = {'b200_steps_per_s': 1 / dt, 'shape': shape}
+        try:
+            out[name]['limiter'] = _limiter(name, 1e3 * dt)
+        except Exception as exc:  # a diagnostic, never the reason to lose the figure
+            out[name]['limiter'] = {'error': repr(exc)}
     # the same decisions with R independent trials in flight: the R x T problems share ONE device
     # pass (ocbo_b200/inflight.py; aggregate decisions/s over the R trials)
     from tests.tools import bench_inflight
