@@ -107,8 +107,9 @@ class ContinuousOpt(object):
                          ('act_dim', self.act_dim), ('use_additive_gp', options.use_additive_gp),
                          ('add_max_group_size', options.add_max_group_size)):
             setattr(gp_opts, key, val)
-        if hasattr(options, 'hp_search_candidates'):
-            gp_opts.hp_search_candidates = options.hp_search_candidates
+        for key in ('hp_search_candidates', 'hp_search_rounds'):
+            if hasattr(options, key):
+                setattr(gp_opts, key, getattr(options, key))
         self.gp_options = gp_opts
         self.eval_options = deepcopy(gp_opts)
         self.eval_options.hp_tune_criterion = 'ml'  # the scoring GP is always ML-tuned (:99-100)

@@ -138,9 +138,9 @@ class B200GPFitter(GPFitterWrapper):
     def fit_gp(self):
         """:123-125.  One batched device pass evaluates every candidate's LML."""
         num_cand = int(getattr(self.options, 'hp_search_candidates', 64))
+        rounds = int(getattr(self.options, 'hp_search_rounds', 1) or 1)
         crit = self._criterion()
-        cands = hp_search.hp_candidates(self._X, self._Y, num_cand)
-        lmls, _ = hp_search.batched_lml(self._X, self._Y, self.kind, cands)
+        cands, lmls = hp_search.search(self._X, self._Y, self.kind, num_cand, rounds, crit)
         self.last_lmls, self.last_candidates = lmls, cands
         idx = hp_search.select(lmls, crit, getattr(self.options, 'hp_samples', 0))
         self.hp_list = [cands[i] for i in idx]

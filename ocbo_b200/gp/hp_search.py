@@ -67,6 +67,57 @@ def hp_candidates(X, Y, num, uniforms=None):
     return theta
 
 
+def _to_theta(t):
+    theta = np.array(t, dtype=np.float64, copy=True)
+    P = theta.shape[1]
+    for col in [0, 1] + list(range(3, P)):
+        theta[:, col] = np.exp(theta[:, col])
+    return theta
+
+
+def _to_box(theta):
+    t = np.array(theta, dtype=np.float64, copy=True).reshape(1, -1)
+    for col in [0, 1] + list(range(3, t.shape[1])):
+        t[:, col] = np.log(t[:, col])
+    return t[0]
+
+
+def refine_candidates(X, Y, num, rnd, crit, best_theta, uniforms=None):
+    """Candidates of search round ``rnd`` >= 1 (``hp_search_rounds`` > 1: the device is idle during
+    a 64-candidate fit -- 466 k LML evaluations/s at n = 55 -- so a fit can afford more of them).
+      'ml'            zoom: ``num - 1`` uniform draws in a box of half-width (hi - lo) / 2^(rnd+1)
+                      around the best candidate so far (transformed coordinates, clipped to the
+                      search box);
+      otherwise       ``num - 1`` more uniform draws in the whole box (importance resampling needs
+                      draws from the prior box, not from a zoomed proposal).
+    Consumes one ``np.random.uniform(size=(num-1, P))`` from the global stream."""
+    lo, hi = hp_bounds(X, Y)
+    P = len(lo)
+    if uniforms is None:
+        uniforms = np.random.uniform(size=(max(num - 1, 0), P))
+    u = np.asarray(uniforms, dtype=np.float64).reshape(-1, P)
+    if crit == 'ml':
+        centre = _to_box(best_theta)
+        half = (hi - lo) * 0.5 ** (rnd + 1)
+        blo, bhi = np.maximum(lo, centre - half), np.minimum(hi, centre + half)
+    else:
+        blo, bhi = lo, hi
+    return _to_theta(blo + u * (bhi - blo))
+
+
+def search(X, Y, kind, num, rounds, crit, lml_fn=None):
+    """All rounds of one fit.  Returns (candidates [rounds*num - (rounds-1), P], lmls)."""
+    lml_fn = lml_fn or (lambda th: batched_lml(X, Y, kind, th)[0])
+    cands = hp_candidates(X, Y, num)
+    lmls = np.asarray(lml_fn(cands), dtype=np.float64)
+    for rnd in range(1, max(int(rounds), 1)):
+        finite = np.where(np.isfinite(lmls), lmls, -np.inf)
+        more = refine_candidates(X, Y, num, rnd, crit, cands[int(np.argmax(finite))])
+        cands = np.concatenate([cands, more], axis=0)
+        lmls = np.concatenate([lmls, np.asarray(lml_fn(more), dtype=np.float64)])
+    return cands, lmls
+
+
 def batched_lml(X, Y, kind, thetas):
     """LML of every theta row in one device batch.  Returns (lml ndarray, post or None).  The
     data set is uploaded once and shared by all candidates (batch stride 0); a candidate whose

@@ -72,7 +72,8 @@ euclidean_gp_args = [
     get_option_specs('kernel_type', False, 'se', 'Kernel: se or matern.'),
     get_option_specs('hp_tune_criterion', False, 'ml', 'ml, post_sampling or hyphenated mix.'),
     get_option_specs('hp_samples', False, 0, 'Hyper-parameter samples per fit.'),
-    get_option_specs('hp_search_candidates', False, 64, 'Candidates per batched LML search.'),
+    get_option_specs('hp_search_candidates', False, 64, 'Candidates per batched LML search round.'),
+    get_option_specs('hp_search_rounds', False, 1, 'Search rounds per fit (ml: zoom on the best; else more draws).'),
     get_option_specs('matern_nu', False, 2.5, 'Matern smoothness (0.5, 1.5, 2.5).'),
     get_option_specs('use_additive_gp', False, False, 'Additive GP (unsupported).'),
     get_option_specs('add_max_group_size', False, 6, 'Unused (additive GP).'),

@@ -70,8 +70,9 @@ class MultiOpt(object):
         gp_opts.kernel_type = options.kernel_type
         gp_opts.hp_tune_criterion = str(options.tuning_methods).replace(',', '-')
         gp_opts.hp_samples = options.hp_samples
-        if hasattr(options, 'hp_search_candidates'):
-            gp_opts.hp_search_candidates = options.hp_search_candidates
+        for key in ('hp_search_candidates', 'hp_search_rounds'):
+            if hasattr(options, key):
+                setattr(gp_opts, key, getattr(options, key))
         self.gp_options = gp_opts
         self.t = 0
         self.set_clean()

@@ -313,6 +313,33 @@ def hp_candidates(X, Y, num, uniforms=None):
     return theta
 
 
+def _to_theta(t):
+    theta = np.array(t, dtype=np.float64, copy=True)
+    theta[:, 0] = np.exp(theta[:, 0])
+    theta[:, 1] = np.exp(theta[:, 1])
+    theta[:, 3:] = np.exp(theta[:, 3:])
+    return theta
+
+
+def refine_candidates(X, Y, num, rnd, crit, best_theta, uniforms=None):
+    """Round ``rnd`` >= 1 of a multi-round search (``hp_search_rounds``): 'ml' zooms on the best
+    candidate so far (box half-width (hi - lo) / 2^(rnd+1), clipped), other criteria draw ``num-1``
+    more uniform candidates.  Same definition as ocbo_b200.gp.hp_search.refine_candidates."""
+    lo, hi = hp_bounds(X, Y)
+    P = len(lo)
+    if uniforms is None:
+        uniforms = np.random.uniform(size=(max(num - 1, 0), P))
+    u = np.asarray(uniforms, dtype=np.float64).reshape(-1, P)
+    if crit == 'ml':
+        centre = np.array(best_theta, dtype=np.float64, copy=True)
+        centre[0], centre[1], centre[3:] = np.log(centre[0]), np.log(centre[1]), np.log(centre[3:])
+        half = (hi - lo) * 0.5 ** (rnd + 1)
+        blo, bhi = np.maximum(lo, centre - half), np.minimum(hi, centre + half)
+    else:
+        blo, bhi = lo, hi
+    return _to_theta(blo + u * (bhi - blo))
+
+
 euclidean_gp_args = None  # filled in by oracle.dragonfly_stub (option specs)
 
 
@@ -362,11 +389,18 @@ class EuclideanGPFitter(object):
     def fit_gp_for_gp_bandit(self, num_samples=1):
         num_cand = int(getattr(self.options, 'hp_search_candidates', 64))
         Xm = _as2d(np.asarray(self.X), self.dim)
+        rounds = int(getattr(self.options, 'hp_search_rounds', 1) or 1)
         crit = self._criterion()
+        lml_of = lambda ths: np.asarray([log_marginal_likelihood(Xm, self.Y, self.options.kernel_type, th,
+                                                                 getattr(self.options, 'matern_nu', 2.5))
+                                         for th in ths])
         cands = hp_candidates(Xm, self.Y, num_cand)
-        lmls = np.asarray([log_marginal_likelihood(Xm, self.Y, self.options.kernel_type, th,
-                                                   getattr(self.options, 'matern_nu', 2.5))
-                           for th in cands])
+        lmls = lml_of(cands)
+        for rnd in range(1, max(rounds, 1)):
+            fin = np.where(np.isfinite(lmls), lmls, -np.inf)
+            more = refine_candidates(Xm, self.Y, num_cand, rnd, crit, cands[int(np.argmax(fin))])
+            cands = np.concatenate([cands, more], axis=0)
+            lmls = np.concatenate([lmls, lml_of(more)])
         self.last_lmls, self.last_candidates = lmls, cands
         finite = np.where(np.isfinite(lmls), lmls, -np.inf)
         if crit == 'ml' or not num_samples or num_samples < 1:

@@ -45,7 +45,8 @@ EUCLIDEAN_GP_ARGS = [
     get_option_specs('kernel_type', False, 'se', 'Kernel type.'),
     get_option_specs('hp_tune_criterion', False, 'ml', 'ml / post_sampling / a-b.'),
     get_option_specs('hp_samples', False, 0, 'Number of HP samples.'),
-    get_option_specs('hp_search_candidates', False, 64, 'Candidates per HP fit.'),
+    get_option_specs('hp_search_candidates', False, 64, 'Candidates per HP fit round.'),
+    get_option_specs('hp_search_rounds', False, 1, 'Search rounds per fit.'),
     get_option_specs('matern_nu', False, 2.5, 'Matern smoothness.'),
     get_option_specs('use_additive_gp', False, False, 'Additive GP (unsupported).'),
     get_option_specs('add_max_group_size', False, 6, 'Unused.'),

@@ -159,6 +159,41 @@ def test_hp_candidates_and_fitter_criteria():
     assert gp.gp_core.alpha is not None
 
 
+def test_multi_round_hp_search_is_defined_alike_in_product_and_oracle():
+    """``hp_search_rounds`` > 1: 'ml' zooms on the best candidate, other criteria draw more
+    uniform candidates.  The product's host logic (ocbo_b200.gp.hp_search.search, LML injected
+    from the oracle so that no GPU is needed) and the oracle's fitter must consume the numpy
+    stream alike and arrive at the same candidates and the same choice."""
+    from argparse import Namespace
+    from ocbo_b200.gp import hp_search
+    X, y, hp = problem(13, 30, 3)
+    lml_of = lambda ths: np.asarray([o.log_marginal_likelihood(X, y, 'se', th) for th in ths])
+    for crit, nsel in (('ml', 1), ('post_sampling', 3)):
+        opts = Namespace(kernel_type='se', hp_tune_criterion=crit, hp_samples=3,
+                         hp_search_candidates=16, hp_search_rounds=3, use_additive_gp=False)
+        o.EuclideanGPFitter._fit_counter = 0
+        np.random.seed(7)
+        f = o.OracleGPFitter(list(X), list(y), opts)
+        f.fit_gp()
+        np.random.seed(7)
+        cands, lmls = hp_search.search(X, y, 0, 16, 3, crit, lml_fn=lml_of)
+        idx = hp_search.select(lmls, crit, 3)
+        assert cands.shape == (16 + 2 * 15, 6)
+        assert np.array_equal(cands, f.gpf_core.last_candidates)
+        assert np.array_equal(lmls, f.gpf_core.last_lmls)
+        assert len(idx) == nsel == len(f.gpf_core.hp_list)
+        for i, th in zip(idx, f.gpf_core.hp_list):
+            assert np.array_equal(cands[i], th)
+        lo, hi = o.hp_bounds(X, y)
+        box = np.log(np.delete(cands, 2, axis=1))
+        assert (box >= np.delete(lo, 2) - 1e-12).all() and (box <= np.delete(hi, 2) + 1e-12).all()
+        if crit == 'ml':  # a zoom never loses the incumbent, and the later rounds stay near it
+            assert lmls.max() >= lmls[:16].max()
+            best_t = np.log(np.delete(cands[int(np.argmax(lmls[:16]))], 2))
+            r1 = np.log(np.delete(cands[16:31], 2, axis=1))
+            assert (np.abs(r1 - best_t) <= 0.25 * (np.delete(hi, 2) - np.delete(lo, 2)) + 1e-12).all()
+
+
 def test_knowledge_gradient_restatement_is_pinned_by_the_reference_function():
     """oracle.kg.knowledge_gradient == the reference's util.misc_util.knowledge_gradient, bit for
     bit, on the committed vectors (tests/golden/make_kg_golden.py ran the reference's function)."""
