@@ -71,8 +71,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
 // pair_rows: the CTA computes row tile y and row tile ntr-1-y, so every CTA
 // of the triangular product carries the same amount of work.
 // ---------------------------------------------------------------------------
-template <int BM, int BN, int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TMA>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_nn_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR, NnParams p) {
   using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
   extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
   const int tj = blockIdx.x;
   const int ldc = p.ldc;
   const int npass = p.pair_rows ? 2 : 1;
+  if (TMA) G::tma_init(smem);
+  int it0 = 0;  // k-tiles consumed so far (mbarrier phase bookkeeping across the two passes)
   for (int pass = 0; pass < npass; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
     if (pass == 1 && ti <= (int)blockIdx.y) break;
@@ -90,10 +93,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
     if (p.tri_k) ktiles = min(ktiles, (ti + 1) * (BM / BK));
 
     typename G::Acc acc;
-    G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
+    typename G::TmaTile tile{&mapP, 0, ti * BM, p.sP ? b : 0, &mapR, tj * BN, 0, p.sR ? b : 0};
+    if (TMA) G::tma_prologue(tile, ktiles, it0, smem);
+    else G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
     if (p.mode == 1) G::load_negated(acc, C, ldc);
     else G::zero(acc);
-    G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
+    if (TMA) G::tma_mainloop(tile, ktiles, it0, smem, acc);
+    else G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
+    it0 += ktiles;
     if (p.mode == 0) {
       G::foreach(acc, [&](int r, int c, double v0, double v1) {
         *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = make_double2(v0, v1);
@@ -122,8 +129,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nn_kernel(NnParams p) {
 // element is that of gemm_nn_kernel, so the reduced values are bit-identical to
 // ocbo_sample + ocbo_segment_argmax.  np.argmax / np.max semantics incl. NaN (first NaN wins).
 // ---------------------------------------------------------------------------
-template <int BM, int BN, int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TMA>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+sample_argmax_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR,
+                     NnParams p) {
   using G = Gemm<BM, BN, true, false, WARPS_M, WARPS_N>;
   extern __shared__ __align__(128) double smem[];
   const int b = blockIdx.z;
@@ -132,6 +141,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
+  if (TMA) G::tma_init(smem);
+  int it0 = 0;
   for (int pass = 0; pass < 2; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
     if (pass == 1 && ti <= (int)blockIdx.y) break;
@@ -140,9 +151,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sample_argmax_kernel(NnParams
     const int ktiles = min(p.ktiles, (ti + 1) * (BM / BK));
 
     typename G::Acc acc;
-    G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
+    typename G::TmaTile tile{&mapP, 0, ti * BM, p.sP ? b : 0, &mapR, tj * BN, 0, p.sR ? b : 0};
     G::zero(acc);
-    G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);  // ends with a barrier: the ring is free
+    if (TMA) {
+      G::tma_prologue(tile, ktiles, it0, smem);
+      G::tma_mainloop(tile, ktiles, it0, smem, acc);  // ends with a barrier: the ring is free
+    } else {
+      G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
+      G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
+    }
+    it0 += ktiles;
 
     const double* rv = p.rowvec + (size_t)b * p.sRowvec + (size_t)ti * BM;
     double* red_v = smem;                                   // [WARPS_M][BN]
@@ -352,6 +370,15 @@ cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_
   memset(&mQ, 0, sizeof(mQ));
   if (panel) {
     using G = Gemm<TM / 2, TILE, true, true, 2, 4>;
+    const uint64_t kext = (uint64_t)p.ktiles * BK;
+    if (use_tma() && tma_make_map(&mP, p.P, kext, (int64_t)ntiles * (TM / 2), p.ldp, p.sP, batch, BK + 4, TM / 2) &&
+        tma_make_map(&mQ, p.Q, kext, (int64_t)p.ntc * TILE, p.ldq, p.sQ, batch, BK + 4, TILE)) {
+      static bool init = false;
+      cudaError_t e = ensure_smem(gemm_nt_kernel<TM / 2, TILE, 2, 4, true>, G::TMA_SMEM_BYTES, init);
+      if (e != cudaSuccess) return e;
+      gemm_nt_kernel<TM / 2, TILE, 2, 4, true><<<dim3(ntiles, 1, batch), GEMM_THREADS, G::TMA_SMEM_BYTES, st>>>(mP, mQ, p);
+      return counted(cudaGetLastError());
+    }
     static bool init = false;
     cudaError_t e = ensure_smem(gemm_nt_kernel<TM / 2, TILE, 2, 4, false>, G::SMEM_BYTES, init);
     if (e != cudaSuccess) return e;
@@ -378,23 +405,51 @@ cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_
   return counted(cudaGetLastError());
 }
 
+// tensor maps of a C (op)= P R launch: P k-major (rows x k), R k rows x columns
+template <int BN>
+static bool nn_maps(const NnParams& p, int rows, int ntc, int batch, CUtensorMap* mP, CUtensorMap* mR) {
+  memset(mP, 0, sizeof(*mP));
+  memset(mR, 0, sizeof(*mR));
+  const uint64_t kext = (uint64_t)p.ktiles * BK;
+  return use_tma() && kext > 0 && tma_make_map(mP, p.P, kext, rows, p.ldp, p.sP, batch, BK + 4, TM) &&
+         tma_make_map(mR, p.R, (uint64_t)ntc * BN, kext, p.ldr, p.sR, batch, BN + 4, BK);
+}
+
 cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch, cudaStream_t st) {
   using G = Gemm<TM, TN, true, false, 4, 2>;
-  static bool init = false;
-  cudaError_t e = ensure_smem(gemm_nn_kernel<TM, TN, 4, 2>, G::SMEM_BYTES, init);
-  if (e != cudaSuccess) return e;
   if (grid_rows <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
-  gemm_nn_kernel<TM, TN, 4, 2><<<dim3(ntc, grid_rows, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  CUtensorMap mP, mR;
+  const int rows = (p.pair_rows ? p.ntr : grid_rows) * TM;
+  if (nn_maps<TN>(p, rows, ntc, batch, &mP, &mR)) {
+    static bool init = false;
+    cudaError_t e = ensure_smem(gemm_nn_kernel<TM, TN, 4, 2, true>, G::TMA_SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    gemm_nn_kernel<TM, TN, 4, 2, true><<<dim3(ntc, grid_rows, batch), GEMM_THREADS, G::TMA_SMEM_BYTES, st>>>(mP, mR, p);
+    return counted(cudaGetLastError());
+  }
+  static bool init = false;
+  cudaError_t e = ensure_smem(gemm_nn_kernel<TM, TN, 4, 2, false>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
+  gemm_nn_kernel<TM, TN, 4, 2, false><<<dim3(ntc, grid_rows, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(mP, mR, p);
   return counted(cudaGetLastError());
 }
 
 cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStream_t st) {
   using G = Gemm<TM, 32, true, false, 4, 2>;
-  static bool init = false;
-  cudaError_t e = ensure_smem(sample_argmax_kernel<TM, 32, 4, 2>, G::SMEM_BYTES, init);
-  if (e != cudaSuccess) return e;
   if (ntc <= 0 || batch <= 0) return cudaSuccess;
-  sample_argmax_kernel<TM, 32, 4, 2><<<dim3(ntc, (p.ntr + 1) / 2, batch), GEMM_THREADS, G::SMEM_BYTES, st>>>(p);
+  CUtensorMap mP, mR;
+  const dim3 grid(ntc, (p.ntr + 1) / 2, batch);
+  if (nn_maps<32>(p, p.ntr * TM, ntc, batch, &mP, &mR)) {
+    static bool init = false;
+    cudaError_t e = ensure_smem(sample_argmax_kernel<TM, 32, 4, 2, true>, G::TMA_SMEM_BYTES, init);
+    if (e != cudaSuccess) return e;
+    sample_argmax_kernel<TM, 32, 4, 2, true><<<grid, GEMM_THREADS, G::TMA_SMEM_BYTES, st>>>(mP, mR, p);
+    return counted(cudaGetLastError());
+  }
+  static bool init = false;
+  cudaError_t e = ensure_smem(sample_argmax_kernel<TM, 32, 4, 2, false>, G::SMEM_BYTES, init);
+  if (e != cudaSuccess) return e;
+  sample_argmax_kernel<TM, 32, 4, 2, false><<<grid, GEMM_THREADS, G::SMEM_BYTES, st>>>(mP, mR, p);
   return counted(cudaGetLastError());
 }
 
