@@ -136,11 +136,15 @@ struct Gemm {
     return reinterpret_cast<uint64_t*>(smem + SMEM_DOUBLES);
   }
   static constexpr int TMA_SMEM_BYTES = SMEM_BYTES + 64;
-  __device__ __forceinline__ static void tma_init(double* smem) {
+  __device__ __forceinline__ static void tma_init(double* smem, int mode = 1) {
     if (threadIdx.x == 0) {
       uint64_t* full = tma_barriers(smem);
 #pragma unroll
-      for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full + s, 1);                         // "stage filled": one expect_tx arrival
+        // "stage drained": one arrival per warp (mode 3, experiment: one per thread)
+        mbar_init(full + STAGES + s, mode == 3 ? GEMM_THREADS : GEMM_THREADS / 32);
+      }
       mbar_init_fence();
     }
     __syncthreads();
@@ -162,8 +166,12 @@ struct Gemm {
     }
   }
   // acc += A B over ``ktiles`` k-tiles; tma_prologue(t, ktiles, it0) must have been called.
+  // ``free_run``: no CTA-wide barrier per k-tile -- every warp signals "stage drained" on the
+  // stage's second mbarrier and only the producing thread waits for it before refilling, so the
+  // warps drift up to STAGES-1 k-tiles apart and the DMMA pipe is not emptied at every k-tile.
   __device__ __forceinline__ static void tma_mainloop(const TmaTile& t, int ktiles, int it0, double* smem,
-                                                      Acc& acc) {
+                                                      Acc& acc, int mode = 1) {
+    const bool free_run = mode != 0;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
@@ -172,8 +180,12 @@ struct Gemm {
     for (int kt = 0; kt < ktiles; ++kt) {
       const int it = it0 + kt;
       mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
-      __syncthreads();  // every warp is past k-tile kt-1: its stage may be refilled
-      if (tid == 0 && kt + STAGES - 1 < ktiles) tma_issue(t, kt + STAGES - 1, it + STAGES - 1, smem);
+      if (!free_run) __syncthreads();  // every warp is past k-tile kt-1: its stage may be refilled
+      if (tid == 0 && kt + STAGES - 1 < ktiles) {
+        if (free_run && it >= 1)  // the stage of k-tile it-1 has been drained by all warps
+          mbar_wait(full + STAGES + ((it - 1) % STAGES), (uint32_t)(((it - 1) / STAGES) & 1));
+        tma_issue(t, kt + STAGES - 1, it + STAGES - 1, smem);
+      }
       const double* sa = smem + (it % STAGES) * STAGE_DOUBLES;
       const double* sb = sa + TA::SIZE;
 #pragma unroll
@@ -187,6 +199,15 @@ struct Gemm {
         for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
           for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+      // (arrivals are made in both modes so that the phases of the "drained" barriers always
+      // count k-tiles)
+      if (mode == 3) {
+        mbar_arrive(full + STAGES + (it % STAGES));
+      } else {
+        if (mode == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + STAGES + (it % STAGES));
       }
     }
     __syncthreads();  // every warp is done with the ring: smem may be reused

@@ -42,14 +42,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
   // operand tiles by TMA (one thread, mbarrier transaction counts) or by cp.async (all threads)
   typename G::TmaTile tile{&mapP, 0, ti * BM, p.sP ? b : 0, &mapQ, 0, tj * BN, p.sQ ? b : 0};
   if (TMA) {
-    G::tma_init(smem);
+    G::tma_init(smem, p.tma_free);
     G::tma_prologue(tile, p.ktiles, 0, smem);
   } else {
     G::prologue(P, p.ldp, Q, p.ldq, p.ktiles, smem);
   }
   if (p.mode == 0) G::zero(acc);
   else G::load_negated(acc, C, ldc);
-  if (TMA) G::tma_mainloop(tile, p.ktiles, 0, smem, acc);
+  if (TMA) G::tma_mainloop(tile, p.ktiles, 0, smem, acc, p.tma_free);
   else G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
   if (p.mode == 0) {
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
@@ -81,7 +81,7 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
   const int tj = blockIdx.x;
   const int ldc = p.ldc;
   const int npass = p.pair_rows ? 2 : 1;
-  if (TMA) G::tma_init(smem);
+  if (TMA) G::tma_init(smem, p.tma_free);
   int it0 = 0;  // k-tiles consumed so far (mbarrier phase bookkeeping across the two passes)
   for (int pass = 0; pass < npass; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
@@ -98,7 +98,7 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
     else G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
     if (p.mode == 1) G::load_negated(acc, C, ldc);
     else G::zero(acc);
-    if (TMA) G::tma_mainloop(tile, ktiles, it0, smem, acc);
+    if (TMA) G::tma_mainloop(tile, ktiles, it0, smem, acc, p.tma_free);
     else G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
     it0 += ktiles;
     if (p.mode == 0) {
@@ -141,7 +141,7 @@ sample_argmax_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
-  if (TMA) G::tma_init(smem);
+  if (TMA) G::tma_init(smem, p.tma_free);
   int it0 = 0;
   for (int pass = 0; pass < 2; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
@@ -155,7 +155,7 @@ sample_argmax_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
     G::zero(acc);
     if (TMA) {
       G::tma_prologue(tile, ktiles, it0, smem);
-      G::tma_mainloop(tile, ktiles, it0, smem, acc);  // ends with a barrier: the ring is free
+      G::tma_mainloop(tile, ktiles, it0, smem, acc, p.tma_free);  // ends with a barrier: the ring is free
     } else {
       G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
       G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
@@ -245,9 +245,9 @@ postcov_kernel(const __grid_constant__ CUtensorMap mapV1, const __grid_constant_
   G::zero(acc);
   if (TMA) {
     typename G::TmaTile tile{&mapV1, ti * BM, 0, p.sV1 ? b : 0, &mapV2, tj * BN, 0, p.sV2 ? b : 0};
-    G::tma_init(smem);
+    G::tma_init(smem, p.tma_free);
     G::tma_prologue(tile, p.ktiles, 0, smem);
-    G::tma_mainloop(tile, p.ktiles, 0, smem, acc);
+    G::tma_mainloop(tile, p.ktiles, 0, smem, acc, p.tma_free);
   } else {
     G::prologue(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem);
     G::mainloop(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem, acc);
@@ -363,8 +363,20 @@ static bool use_tma() {
   return v != 0;
 }
 
-cudaError_t launch_gemm_nt(const NtParams& p, int ntiles, int batch, cudaStream_t st, int panel) {
+// OCBO_TMA_FREE=0 keeps a CTA-wide barrier per k-tile in the TMA main loop (A/B measurements)
+static int tma_free_run() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCBO_TMA_FREE");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+cudaError_t launch_gemm_nt(const NtParams& p0, int ntiles, int batch, cudaStream_t st, int panel) {
   if (ntiles <= 0 || batch <= 0) return cudaSuccess;
+  NtParams p = p0;
+  p.tma_free = tma_free_run();
   CUtensorMap mP, mQ;
   memset(&mP, 0, sizeof(mP));
   memset(&mQ, 0, sizeof(mQ));
@@ -415,9 +427,11 @@ static bool nn_maps(const NnParams& p, int rows, int ntc, int batch, CUtensorMap
          tma_make_map(mR, p.R, (uint64_t)ntc * BN, kext, p.ldr, p.sR, batch, BN + 4, BK);
 }
 
-cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch, cudaStream_t st) {
+cudaError_t launch_gemm_nn(const NnParams& p0, int grid_rows, int ntc, int batch, cudaStream_t st) {
   using G = Gemm<TM, TN, true, false, 4, 2>;
   if (grid_rows <= 0 || ntc <= 0 || batch <= 0) return cudaSuccess;
+  NnParams p = p0;
+  p.tma_free = tma_free_run();
   CUtensorMap mP, mR;
   const int rows = (p.pair_rows ? p.ntr : grid_rows) * TM;
   if (nn_maps<TN>(p, rows, ntc, batch, &mP, &mR)) {
@@ -434,9 +448,11 @@ cudaError_t launch_gemm_nn(const NnParams& p, int grid_rows, int ntc, int batch,
   return counted(cudaGetLastError());
 }
 
-cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStream_t st) {
+cudaError_t launch_sample_argmax(const NnParams& p0, int ntc, int batch, cudaStream_t st) {
   using G = Gemm<TM, 32, true, false, 4, 2>;
   if (ntc <= 0 || batch <= 0) return cudaSuccess;
+  NnParams p = p0;
+  p.tma_free = tma_free_run();
   CUtensorMap mP, mR;
   const dim3 grid(ntc, (p.ntr + 1) / 2, batch);
   if (nn_maps<32>(p, p.ntr * TM, ntc, batch, &mP, &mR)) {
@@ -454,8 +470,10 @@ cudaError_t launch_sample_argmax(const NnParams& p, int ntc, int batch, cudaStre
 }
 
 template <int KIND>
-static cudaError_t launch_postcov_kind(const CovParams& p, int ntiles, int batch, cudaStream_t st) {
+static cudaError_t launch_postcov_kind(const CovParams& p0, int ntiles, int batch, cudaStream_t st) {
   using G = Gemm<TM, TN, false, false, 4, 2>;
+  CovParams p = p0;
+  p.tma_free = tma_free_run();
   CUtensorMap m1, m2;
   memset(&m1, 0, sizeof(m1));
   memset(&m2, 0, sizeof(m2));

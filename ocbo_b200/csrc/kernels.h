@@ -16,6 +16,7 @@ struct NtParams {  // C (=|-=) P Q^T ; all pointers pre-offset to the region ori
   int lower_skip;  // rectangular region: skip tiles entirely above the diagonal
   int mode;        // 0: C = acc, 1: C -= acc
   const int32_t* info;
+  int tma_free;    // TMA main loop without the per-k-tile CTA barrier (set by the launcher)
 };
 
 struct NnParams {  // C (=|-=|= rowvec +) P R
@@ -31,6 +32,7 @@ struct NnParams {  // C (=|-=|= rowvec +) P R
   const int32_t* info;
   // fused sampling tail (sample_argmax_kernel): per (row tile, column) max / first arg-max
   double* tile_max; int32_t* tile_arg; int out_ld;
+  int tma_free;
 };
 
 struct CovParams {  // C = K(Xa, Xb) - V1^T V2
@@ -41,6 +43,7 @@ struct CovParams {  // C = K(Xa, Xb) - V1^T V2
   const double* theta; int64_t sTheta;
   double* C; int ldc; int64_t sC;
   int ntc, ktiles, dim, kind, sym, tri;
+  int tma_free;
 };
 
 // panel = 0: 128 x 64 tiles (updates); panel = 1: 64 x 128 tiles (in-place panel solve)
