@@ -102,13 +102,12 @@ struct PotrfTimer {
   }
 };
 
-// Look-ahead at the launch level (OCBO_POTRF_LOOKAHEAD, default on; needs more than one outer
-// panel): the rank-`outer` update of panel i is split into (a) the columns of the NEXT outer panel,
+// Look-ahead at the launch level (OCBO_POTRF_LOOKAHEAD; needs more than two outer panels): the rank-`outer` update of panel i is split into (a) the columns of the NEXT outer panel,
 // (its first middle panel), on the caller's stream, and (b) everything to the right of it, on a
 // helper stream.  The
 // latency-bound chain of panel i+1 (diagonal blocks, panel solves, in-panel updates: a few CTAs
-// at a time) then runs beside (b), which fills the SMs: one m = 8192 factorisation alone
-// 11.2 -> ~9 ms.  Per caller stream the library keeps ONE helper stream and two events, created
+// at a time) then runs beside (b), which fills the SMs: one sweep trial alone 14.7 -> 14.1 ms
+// (the 64 diagonal blocks and panel solves, 3.7 ms, stay a serial chain).  Per caller stream the library keeps ONE helper stream and two events, created
 // on first use (the only state besides the per-kernel attributes).
 struct Lookahead {
   cudaStream_t side = nullptr;
@@ -130,13 +129,17 @@ static Lookahead* lookahead_for(cudaStream_t st) {
   table[st] = la;
   return la;
 }
-static bool lookahead_enabled() {
+// default: only for a single problem per launch (batch 1), where the chain's latency is the cost;
+// with several trials per launch / in flight the other trials already fill the chain's gaps and
+// the split update only adds launches (measured at 16 in flight: 30.1 k vs 30.5 k samples/s).
+// OCBO_POTRF_LOOKAHEAD=1 forces it on, =0 off.
+static bool lookahead_enabled(int batch) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OCBO_POTRF_LOOKAHEAD");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 2;
   }
-  return v != 0;
+  return v == 2 ? batch == 1 : v == 1;
 }
 
 static int potrf_outer_tiles(int nt) {
@@ -178,7 +181,7 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
     mid_env = (e ? atoi(e) : 1024) / TILE;
   }
   const int NBM = (mid_env > 0 && mid_env < NBO) ? mid_env : NBO;
-  Lookahead* la = (!tm && nt > 2 * NBO && lookahead_enabled()) ? lookahead_for(st) : nullptr;
+  Lookahead* la = (!tm && nt > 2 * NBO && lookahead_enabled(batch)) ? lookahead_for(st) : nullptr;
   bool side_busy = false;  // a (b) update is in flight on the helper stream
   for (int J0 = 0; J0 < nt; J0 += NBO) {
     const int J1 = (J0 + NBO < nt) ? J0 + NBO : nt;
