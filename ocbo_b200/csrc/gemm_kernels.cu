@@ -42,14 +42,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
   // operand tiles by TMA (one thread, mbarrier transaction counts) or by cp.async (all threads)
   typename G::TmaTile tile{&mapP, 0, ti * BM, p.sP ? b : 0, &mapQ, 0, tj * BN, p.sQ ? b : 0};
   if (TMA) {
-    G::tma_init(smem, p.tma_free);
+    G::tma_init(smem);
     G::tma_prologue(tile, p.ktiles, 0, smem);
   } else {
     G::prologue(P, p.ldp, Q, p.ldq, p.ktiles, smem);
   }
   if (p.mode == 0) G::zero(acc);
   else G::load_negated(acc, C, ldc);
-  if (TMA) G::tma_mainloop(tile, p.ktiles, 0, smem, acc, p.tma_free);
+  if (TMA) { if (p.tma_free) G::tma_mainloop(tile, p.ktiles, 0, smem, acc, 1); else G::tma_mainloop(tile, p.ktiles, 0, smem, acc, 0); }
   else G::mainloop(P, p.ldp, Q, p.ldq, p.ktiles, smem, acc);
   if (p.mode == 0) {
     G::foreach(acc, [&](int r, int c, double v0, double v1) {
@@ -81,7 +81,7 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
   const int tj = blockIdx.x;
   const int ldc = p.ldc;
   const int npass = p.pair_rows ? 2 : 1;
-  if (TMA) G::tma_init(smem, p.tma_free);
+  if (TMA) G::tma_init(smem);
   int it0 = 0;  // k-tiles consumed so far (mbarrier phase bookkeeping across the two passes)
   for (int pass = 0; pass < npass; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
@@ -98,7 +98,7 @@ gemm_nn_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
     else G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
     if (p.mode == 1) G::load_negated(acc, C, ldc);
     else G::zero(acc);
-    if (TMA) G::tma_mainloop(tile, ktiles, it0, smem, acc, p.tma_free);
+    if (TMA) { if (p.tma_free) G::tma_mainloop(tile, ktiles, it0, smem, acc, 1); else G::tma_mainloop(tile, ktiles, it0, smem, acc, 0); }
     else G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
     it0 += ktiles;
     if (p.mode == 0) {
@@ -141,7 +141,7 @@ sample_argmax_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
-  if (TMA) G::tma_init(smem, p.tma_free);
+  if (TMA) G::tma_init(smem);
   int it0 = 0;
   for (int pass = 0; pass < 2; ++pass) {
     const int ti = (pass == 0) ? (int)blockIdx.y : p.ntr - 1 - (int)blockIdx.y;
@@ -155,7 +155,7 @@ sample_argmax_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
     G::zero(acc);
     if (TMA) {
       G::tma_prologue(tile, ktiles, it0, smem);
-      G::tma_mainloop(tile, ktiles, it0, smem, acc, p.tma_free);  // ends with a barrier: the ring is free
+      { if (p.tma_free) G::tma_mainloop(tile, ktiles, it0, smem, acc, 1); else G::tma_mainloop(tile, ktiles, it0, smem, acc, 0); }  // ends with a barrier: the ring is free
     } else {
       G::prologue(P, p.ldp, R, p.ldr, ktiles, smem);
       G::mainloop(P, p.ldp, R, p.ldr, ktiles, smem, acc);
@@ -245,9 +245,9 @@ postcov_kernel(const __grid_constant__ CUtensorMap mapV1, const __grid_constant_
   G::zero(acc);
   if (TMA) {
     typename G::TmaTile tile{&mapV1, ti * BM, 0, p.sV1 ? b : 0, &mapV2, tj * BN, 0, p.sV2 ? b : 0};
-    G::tma_init(smem, p.tma_free);
+    G::tma_init(smem);
     G::tma_prologue(tile, p.ktiles, 0, smem);
-    G::tma_mainloop(tile, p.ktiles, 0, smem, acc, p.tma_free);
+    { if (p.tma_free) G::tma_mainloop(tile, p.ktiles, 0, smem, acc, 1); else G::tma_mainloop(tile, p.ktiles, 0, smem, acc, 0); }
   } else {
     G::prologue(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem);
     G::mainloop(V1, p.ldv1, V2, p.ldv2, p.ktiles, smem, acc);
