@@ -165,10 +165,21 @@ struct Gemm {
     }
   }
   // acc += A B over ``ktiles`` k-tiles; tma_prologue(t, ktiles, it0) must have been called.
-  // ``mode`` 1 (default, "free run"): no CTA-wide barrier per k-tile -- every warp signals "stage drained" on the
-  // stage's second mbarrier and only the producing thread waits for it before refilling, so the
-  // warps drift up to STAGES-1 k-tiles apart and the DMMA pipe is not emptied at every k-tile
-  // (measured on the sweep: 29.3 k -> 30.4 k samples/s).  ``mode`` 0 (OCBO_TMA_FREE=0) keeps the barrier.
+  // ``mode`` 1 (default, "free run"): no CTA-wide barrier per k-tile -- every warp signals "stage
+  // drained" on the stage's second mbarrier and only the producing thread waits for it before
+  // refilling, so the warps drift up to STAGES-1 k-tiles apart and the DMMA pipe is not emptied at
+  // every k-tile (measured on the sweep: 29.3 k -> 30.4 k samples/s).  ``mode`` 0 (OCBO_TMA_FREE=0)
+  // keeps the barrier.
+  //
+  // WHERE the "drained" arrival sits matters.  Placed right after the k-tile's DMMAs in the source,
+  // ptxas hoists it above them, directly behind the ISSUE of the last fragment loads and with no
+  // scoreboard wait on them (SASS: SYNCS.ARRIVE two slots after the last LDS.64) -- and the refill
+  // by the TMA engine then races with loads still in flight: wrong factors in some builds, right
+  // ones in others (the parity check in bench.py and three GPU tests caught it).  The arrival for
+  // k-tile it-1 is therefore the FIRST instruction of k-tile it, across the loop's back edge, where
+  // no scheduler moves it: every DMMA of k-tile it-1 has ISSUED by then (in-order issue), hence
+  // every fragment load it consumed has returned.  The last k-tile's arrival follows the closing
+  // CTA barrier.
   __device__ __forceinline__ static void tma_mainloop(const TmaTile& t, int ktiles, int it0, double* smem,
                                                       Acc& acc, int mode = 1) {
     const bool free_run = mode != 0;
@@ -179,6 +190,10 @@ struct Gemm {
     uint64_t* full = tma_barriers(smem);
     for (int kt = 0; kt < ktiles; ++kt) {
       const int it = it0 + kt;
+      if (kt > 0) {  // this warp is done with k-tile it-1 (first thing after the loop's back edge)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + STAGES + ((it - 1) % STAGES));
+      }
       mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
       if (!free_run) __syncthreads();  // every warp is past k-tile kt-1: its stage may be refilled
       if (tid == 0 && kt + STAGES - 1 < ktiles) {
@@ -200,12 +215,11 @@ struct Gemm {
 #pragma unroll
           for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
-      // (arrivals are made in both modes so that the phases of the "drained" barriers always
-      // count k-tiles)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full + STAGES + (it % STAGES));
     }
     __syncthreads();  // every warp is done with the ring: smem may be reused
+    // (the drained barriers count k-tiles in both modes: their phases stay in step over the passes
+    // of a kernel that computes several tiles)
+    if (ktiles > 0 && lane == 0) mbar_arrive(full + STAGES + ((it0 + ktiles - 1) % STAGES));
   }
 
   __device__ __forceinline__ static void zero(Acc& acc) {

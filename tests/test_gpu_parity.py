@@ -456,6 +456,28 @@ def test_segment_argmax_and_joint_pick(mods):
             assert (t2[b, s], a2[b, s], g2[b, s]) == picks.grid_only_pick(Fh[b, n_old:, s], T)
 
 
+@pytest.mark.parametrize('n', [256, 1024, 3072])
+def test_tile_core_dgemm_matches_cublas(mods, n):
+    """The DMMA tile core with its TMA-fed, free-running operand pipeline (gemm_core.cuh) on a plain
+    C = A B^T against cuBLAS: many CTAs per SM slot, many k-tiles per CTA -- a refill that raced with
+    the fragment loads of a stage (tma_mainloop's "drained" barrier) shows up here at once."""
+    import ctypes
+    torch = mods['torch']
+    from ocbo_b200._lib import call
+    g = torch.Generator(device='cuda').manual_seed(n)
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda', generator=g)
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda', generator=g)
+    c = torch.zeros(n, n, dtype=torch.float64, device='cuda')
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref = a @ b.t()
+    for _ in range(3):
+        c.zero_()
+        call('ocbo_probe_dgemm_nt', ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+             ctypes.c_void_p(c.data_ptr()), n, st)
+        torch.cuda.synchronize()
+        assert float((c - ref).abs().max() / ref.abs().max()) <= 1e-13
+
+
 def test_fused_sampling_tail_equals_sample_then_argmax(mods):
     """ocbo_sample_tile_argmax (F never written) against ocbo_sample + np.max / np.argmax on the
     materialised F: bit-identical maxima, first-index arg-max on ties (duplicate rows inside a
