@@ -638,7 +638,9 @@ def run_b200(args):
             'gpu_launches': launches,
             'roofline': roof,
             'cpu_baseline': cpu,
-            'parity_checked': bool(parity and parity['ok']),
+            # (the CPU checker runs on rank 0 at N = 1 only; at N > 1 the fixed-trials digest below, equal
+            # to N = 1's, ties the picks to the checked ones)
+            'parity_checked': bool(parity and parity['ok']) if world == 1 and parity is not None else None,
             'parity': parity,
             'sweep_fixed_trials': sweep_fixed,
             'ladder_variant': ladder_variant,

@@ -62,7 +62,8 @@ class OcboError(RuntimeError):
 
 
 def _load():
-    path = _build.LIB_PATH
+    # OCBO_B200_LIB: an experimental build of the same library (tests/tools/arrive_placement.py)
+    path = os.environ.get('OCBO_B200_LIB') or _build.LIB_PATH
     if not os.path.exists(path):
         try:
             _build.build()

@@ -31,16 +31,19 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source of the package into ``lib/libocbo_b200.so``."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out_dir=None):
+    """Compile every CUDA source of the package into ``lib/libocbo_b200.so`` (``defines`` /
+    ``out_dir``: an experimental variant of the library elsewhere, tests/tools only)."""
+    lib_dir = out_dir or LIB_DIR
+    lib_path = os.path.join(lib_dir, 'libocbo_b200.so')
+    if out_dir is None and not force and not _stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(lib_dir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace('.cu', '.o'))
-        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+        obj = os.path.join(lib_dir, src.replace('.cu', '.o'))
+        cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + \
               ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
@@ -50,9 +53,9 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s' % src)
-    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [_nvcc(), '-shared', '-o', lib_path] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return lib_path
 
 
 HOSTPACK_SRC = os.path.join(CSRC, 'hostpack.c')

@@ -190,10 +190,12 @@ struct Gemm {
     uint64_t* full = tma_barriers(smem);
     for (int kt = 0; kt < ktiles; ++kt) {
       const int it = it0 + kt;
+#ifndef OCBO_ARRIVE_AT_END
       if (kt > 0) {  // this warp is done with k-tile it-1 (first thing after the loop's back edge)
         __syncwarp();
         if (lane == 0) mbar_arrive(full + STAGES + ((it - 1) % STAGES));
       }
+#endif
       mbar_wait(full + (it % STAGES), (uint32_t)((it / STAGES) & 1));
       if (!free_run) __syncthreads();  // every warp is past k-tile kt-1: its stage may be refilled
       if (tid == 0 && kt + STAGES - 1 < ktiles) {
@@ -215,11 +217,19 @@ struct Gemm {
 #pragma unroll
           for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
+#ifdef OCBO_ARRIVE_AT_END
+      // the placement that FAILS (tests/tools/arrive_placement.py builds this variant to show it):
+      // straight-line behind the DMMAs, ptxas schedules the arrival above them
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + STAGES + (it % STAGES));
+#endif
     }
     __syncthreads();  // every warp is done with the ring: smem may be reused
     // (the drained barriers count k-tiles in both modes: their phases stay in step over the passes
     // of a kernel that computes several tiles)
+#ifndef OCBO_ARRIVE_AT_END
     if (ktiles > 0 && lane == 0) mbar_arrive(full + STAGES + ((it0 + ktiles - 1) % STAGES));
+#endif
   }
 
   __device__ __forceinline__ static void zero(Acc& acc) {
