@@ -32,7 +32,7 @@ CONFIGS = {
 }
 
 
-def run(engine, names, seeds):
+def run(engine, names, seeds, searches=None):
     out = {}
     if engine == 'oracle':
         from oracle import gp_numpy, refshim
@@ -80,6 +80,8 @@ def run(engine, names, seeds):
         cfg = CONFIGS[name]
         out[name] = {'capital': cfg['capital'], 'kind': cfg['kind']}
         for tag, (cands, rounds) in SEARCHES.items():
+            if searches and tag not in searches:
+                continue
             finals, secs = [], []
             for s in range(seeds):
                 np.random.seed(sc.SEED + s)
@@ -123,7 +125,8 @@ if __name__ == '__main__':
     ap.add_argument('--engine', default='b200', choices=['b200', 'oracle'])
     ap.add_argument('--seeds', type=int, default=5)
     ap.add_argument('--configs', default=None)
+    ap.add_argument('--searches', default=None, help='comma separated subset of ' + ','.join(SEARCHES))
     a = ap.parse_args()
     names = a.configs.split(',') if a.configs else (
         ['set2d', 'jointbran'] if a.engine == 'oracle' else list(CONFIGS))
-    print(json.dumps({'engine': a.engine, 'seeds': a.seeds, 'searches': SEARCHES, 'results': run(a.engine, names, a.seeds)}))
+    print(json.dumps({'engine': a.engine, 'seeds': a.seeds, 'searches': SEARCHES, 'results': run(a.engine, names, a.seeds, a.searches.split(',') if a.searches else None)}))
