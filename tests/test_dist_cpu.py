@@ -121,3 +121,27 @@ def test_driver_shards_trials_over_two_ranks(tmp_path, monkeypatch):
     o.EuclideanGPFitter._fit_counter = 0
     ref = _summary(ocbo.run(argv=_DRIVER_ARGV))
     assert got == ref
+
+
+def _stream_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ocbo_b200.dist import share_numpy_stream
+    np.random.seed(1000 + rank)          # an unseeded run: every rank starts from its own entropy
+    share_numpy_stream()                 # ... until rank 0's stream is shared
+    draws = np.random.uniform(size=5)
+    np.save(os.path.join(out_dir, 'draws_%d.npy' % rank), draws)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unseeded_ranks_share_rank_zeros_numpy_stream(tmp_path):
+    """--set_seed 0 under a launcher: the drivers assemble their task functions, risk-neutral grids and
+    evaluation sets from the global numpy stream on EVERY rank; they must all see rank 0's stream
+    (ocbo_b200/ocbo.py, cts_ocbo.py -> dist.share_numpy_stream)."""
+    mp.spawn(_stream_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    d0, d1 = np.load(str(tmp_path / 'draws_0.npy')), np.load(str(tmp_path / 'draws_1.npy'))
+    assert np.array_equal(d0, d1)
+    np.random.seed(1000)
+    assert np.array_equal(d0, np.random.uniform(size=5))
