@@ -299,6 +299,12 @@ int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream);
 int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n,
                         ocbo_stream_t stream);
 
+/* tcgen05 probe: C (m x n, int32, ld = ldc) = A (m x k, int8, ld = lda) B^T (B: n x k, int8, ld = ldb) on the
+ * 5th-generation tensor cores (tcgen05.mma kind::i8, TMA operands, TMEM accumulator) -- the building block of an
+ * Ozaki-split fp64 update; m, n, k multiples of 128, lda / ldb multiples of 16. */
+int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc,
+                        int m, int n, int k, ocbo_stream_t stream);
+
 #endif /* OCBO_NO_BENCH */
 
 #ifdef __cplusplus

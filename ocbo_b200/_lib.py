@@ -48,6 +48,7 @@ _PROTOS = {
     'ocbo_probe_dmma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dfma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dgemm_nt': (_I, [_VP, _VP, _VP, _I, _VP]),
+    'ocbo_probe_igemm_nt': (_I, [_VP, _L, _VP, _L, _VP, _L, _I, _I, _I, _VP]),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + ['ocbo_last_error_string'])
 

@@ -738,6 +738,16 @@ int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream) {
   CK(launch_probe_dfma(sink, blocks, iters, (cudaStream_t)stream), "ocbo_probe_dfma");
   return 0;
 }
+int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc, int m,
+                        int n, int k, ocbo_stream_t stream) {
+  if (!A || !B || !C) return fail_arg(1, "null");
+  if (m <= 0 || m % 128 || n <= 0 || n % 128) return fail_arg(7, "m and n must be positive multiples of 128");
+  if (k <= 0 || k % 128) return fail_arg(9, "k must be a positive multiple of 128");
+  if (lda < k || (lda & 15) || ldb < k || (ldb & 15)) return fail_arg(2, "lda / ldb must be multiples of 16 and >= k");
+  if (ldc < n || (ldc & 3)) return fail_arg(6, "ldc must be a multiple of 4 and >= n");
+  CK(launch_probe_igemm(A, lda, B, ldb, C, ldc, m, n, k, (cudaStream_t)stream), "ocbo_probe_igemm_nt");
+  return 0;
+}
 int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n, ocbo_stream_t stream) {
   if (!A || !B || !C) return fail_arg(1, "null");
   if (!tile_ok(n)) return fail_arg(4, "n must be a multiple of 128");

@@ -118,6 +118,8 @@ cudaError_t launch_joint_pick(const double* seg_max, const int32_t* seg_arg, int
                               double* out_gain, int batch, cudaStream_t st);
 cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_probe_igemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc,
+                               int m, int n, int k, cudaStream_t st);
 
 }  // namespace ocbo
 
