@@ -305,6 +305,13 @@ int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n,
 int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc,
                         int m, int n, int k, ocbo_stream_t stream);
 
+/* Ozaki probe: C (rows x rows, fp64) -= P P^T with P rows x kw fp64, computed on the int8 tensor cores from 8
+ * error-free int8 slices of P (csrc/ozaki.cu); tri != 0: only the 128 x 64 tiles on and below the diagonal.
+ * ws: device workspace of ocbo_ozaki_ws_bytes(rows, kw, 1) bytes, 256-byte aligned. */
+int64_t ocbo_ozaki_ws_bytes(int rows, int kw, int batch);
+int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* C, int ldc, void* ws,
+                            int64_t ws_bytes, int tri, ocbo_stream_t stream);
+
 #endif /* OCBO_NO_BENCH */
 
 #ifdef __cplusplus

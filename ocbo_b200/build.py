@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libocbo_b200.so')
 SOURCES = ['gemm_kernels.cu', 'gram.cu', 'potrf.cu', 'potrf_diag_reg.cu', 'potrf_diag_blk.cu', 'ladder.cu', 'sampling.cu', 'ei.cu', 'kg.cu',
-           'igemm_probe.cu', 'capi.cu']
+           'igemm_probe.cu', 'ozaki.cu', 'capi.cu']
 HEADERS = ['common.cuh', 'gemm_core.cuh', 'kernels.h', 'philox.cuh', 'tma.cuh',
            os.path.join('..', '..', 'include', 'ocbo_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

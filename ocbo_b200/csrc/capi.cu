@@ -748,6 +748,24 @@ int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t l
   CK(launch_probe_igemm(A, lda, B, ldb, C, ldc, m, n, k, (cudaStream_t)stream), "ocbo_probe_igemm_nt");
   return 0;
 }
+int64_t ocbo_ozaki_ws_bytes(int rows, int kw, int batch) {
+  if (rows <= 0 || kw <= 0 || batch <= 0) return 0;
+  return (int64_t)ozaki_ws_bytes(rows, kw, batch);
+}
+int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* C, int ldc, void* ws, int64_t ws_bytes,
+                            int tri, ocbo_stream_t stream) {
+  if (!P || !C || !ws) return fail_arg(1, "null");
+  if (rows <= 0 || rows % 128) return fail_arg(3, "rows must be a positive multiple of 128");
+  if (kw <= 0 || kw % 64 || kw > 32768) return fail_arg(4, "kw must be a multiple of 64 in [64, 32768]");
+  if (ldp < kw || (ldp & 1)) return fail_arg(2, "ldp");
+  if (ldc < rows || (ldc & 1)) return fail_arg(6, "ldc");
+  if (ws_bytes < (int64_t)ozaki_ws_bytes(rows, kw, 1)) return fail_arg(8, "workspace too small (ocbo_ozaki_ws_bytes)");
+  CK(launch_ozaki_split(P, ldp, 0, rows, kw, ws, nullptr, 1, (cudaStream_t)stream), "ozaki split");
+  CK(launch_ozaki_update(ws, rows, kw, 0, 0, C, ldc, 0, rows / 128, rows / 64, tri, 0, 0, 0, nullptr, 1,
+                         (cudaStream_t)stream),
+     "ozaki update");
+  return 0;
+}
 int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n, ocbo_stream_t stream) {
   if (!A || !B || !C) return fail_arg(1, "null");
   if (!tile_ok(n)) return fail_arg(4, "n must be a multiple of 128");

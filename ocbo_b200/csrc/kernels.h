@@ -118,6 +118,14 @@ cudaError_t launch_joint_pick(const double* seg_max, const int32_t* seg_arg, int
                               double* out_gain, int batch, cudaStream_t st);
 cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st);
+// fp64 rank-k updates through the int8 tensor cores (ozaki.cu): split a panel into int8 slices, then
+// C (region) -= P Q^T from the split workspace
+size_t ozaki_ws_bytes(int rows, int kw, int batch);
+cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
+                               int batch, cudaStream_t st);
+cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
+                                int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
+                                int batch, cudaStream_t st);
 cudaError_t launch_probe_igemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc,
                                int m, int n, int k, cudaStream_t st);
 

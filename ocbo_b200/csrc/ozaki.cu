@@ -1,0 +1,392 @@
+// FP64 rank-k updates on the 5th-generation tensor cores (tcgen05.mma kind::i8), Ozaki-style:
+//
+//   P (rows x k, fp64) = scale_r * sum_{t=0..7} 2^(-7 t) s_t        s_t: int8 slices in [-64, 64], row-wise exponent
+//   P Q^T              = scale_i scale_j * sum_{g=0..7} 2^(-7 g) [ sum_{t+u=g} s_t(P) s_u(Q)^T ]
+//
+// (slice pairs with t + u >= 8 are dropped: below 2^-56 of the row maxima; measured 1.7e-14 of max|P Q^T| on a
+// Cholesky panel, tests/tools/ozaki_probe.py.)  The integer products are EXACT: every group g is one int32
+// accumulator in tensor memory, |acc_g| <= (g + 1) k 2^12 < 2^31 for k <= 32768.
+//
+// Two kernels:
+//   ozaki_split_kernel   fp64 panel -> int8 slices + per-row scale, written as the shared-memory image of the
+//                        operand tiles (k blocks of 32 bytes, 32-byte swizzle applied), HBM bound
+//   ozaki_update_kernel  persistent, warp specialised: one thread streams those images with contiguous bulk copies
+//                        (cp.async.bulk: all 8 slices of a 128-row P tile in one 32 KiB copy, 8 x 2 KiB for the 64-row
+//                        Q tile; 4 stages of 48 KiB on mbarrier transaction counts), one thread issues the 36
+//                        slice-pair MMAs of each k step into 8 accumulators of 128 x 64 int32 (all 512 TMEM
+//                        columns), four warps read the accumulators back (tcgen05.ld), recombine them in fp64
+//                        (Horner in 2^-7, exact conversions) and apply C -= scale_i scale_j (...) through a
+//                        shared-memory transposition so that the read-modify-write of C is coalesced.
+// Why a fused kernel: with library int8 GEMMs the split / accumulate passes cost more than the GEMMs save
+// (0.78x); here the 8 int32 products never leave the SM and every operand byte staged in shared
+// memory feeds 36/16 as many MMAs as in a plain GEMM.
+#include "common.cuh"
+#include "gemm_core.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace ocbo {
+
+namespace {
+constexpr int OZ_S = 8;                      // slices per operand
+constexpr int OZ_BM = 128, OZ_BN = 64;       // C tile
+constexpr int OZ_BK = 32;                    // bytes of k per stage = one 32-byte swizzle row = one tcgen05.mma
+constexpr int OZ_STAGES = 4;
+constexpr int OZ_A_SLICE = OZ_BM * OZ_BK, OZ_B_SLICE = OZ_BN * OZ_BK;
+constexpr int OZ_A_STAGE = OZ_S * OZ_A_SLICE, OZ_B_STAGE = OZ_S * OZ_B_SLICE;
+constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;                 // 48 KiB
+constexpr int OZ_EPI_LD = 17;                                           // 16 columns + 1 pad (doubles)
+constexpr int OZ_EPI_BYTES = 4 * 32 * OZ_EPI_LD * 8;
+constexpr int OZ_BAR_BYTES = 256;
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + 1024;
+constexpr int OZ_THREADS = 192;              // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..5: epilogue
+constexpr uint32_t OZ_TMEM_COLS = 512;       // 8 accumulators x 64 columns
+
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = S8, both K-major, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t oz_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+}
+
+// K-major operand tile, 32-byte swizzle: 8-row groups 256 bytes apart (SBO), descriptor version 1, layout type 6
+__device__ __forceinline__ uint64_t oz_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
+// contiguous global -> shared bulk copy onto an mbarrier transaction count (SASS UBLKCP)
+__device__ __forceinline__ void oz_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void oz_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// exact int32 -> fp64 without the conversion pipe: 2^52 + 2^31 + x as a bit pattern, minus the bias
+__device__ __forceinline__ double oz_i2d(uint32_t x) {
+  return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+struct OzParams {
+  double* C; int ldc; int64_t sC;
+  const int8_t* S; int RB, KB;  // slice workspace (layout below), its 128-row blocks and 32-byte k blocks
+  const double* scaleA; const double* scaleB; int64_t sScale;  // per slice row; batch stride
+  int rowA0, rowB0;      // slice rows of the region's first row (multiple of 128) / first column (of 64)
+  int R, ntc, ntiles;    // tri: row tiles of the square region; rect: column tiles (64 wide); tiles per problem
+  int ktiles;            // k / 64
+  int tri, lower_skip, row0, col0;
+  const int32_t* info;
+  int total;             // ntiles * batch
+};
+
+// Work item w -> (problem, tile); false: nothing to do (parked problem, tile above the diagonal).  Every role
+// evaluates this identically, so skipped items never touch a pipeline.
+__device__ __forceinline__ bool oz_tile(const OzParams& p, int w, int& b, int& ti, int& tj) {
+  b = w / p.ntiles;
+  const int t = w - b * p.ntiles;
+  if (p.info && p.info[b] != 0) return false;
+  if (p.tri) {
+    tri_index_2to1_banded<8>(t, p.R, ti, tj);
+  } else {
+    ti = t / p.ntc;
+    tj = t - ti * p.ntc;
+    if (p.lower_skip && p.row0 + ti * OZ_BM + OZ_BM - 1 < p.col0 + tj * OZ_BN) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_update_kernel(OzParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  double* epi = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    mbar_init_fence();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(OZ_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {  // ---- TMA producer
+    int it = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+      int b, ti, tj;
+      if (!oz_tile(p, w, b, ti, tj)) continue;
+      // block (k block kt, row block rb) of the workspace = [slice][128 rows][32 bytes], already swizzled: the A tile
+      // is ONE contiguous 32 KiB copy, the B tile 8 copies of 2 KiB (64 of the 128 rows of every slice)
+      const int rbA = p.rowA0 / OZ_BM + ti, rB = p.rowB0 + tj * OZ_BN;
+      const int8_t* srcA = p.S + ((size_t)b * p.KB * p.RB + rbA) * OZ_A_STAGE;
+      const int8_t* srcB = p.S + ((size_t)b * p.KB * p.RB + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
+      const size_t kstep = (size_t)p.RB * OZ_A_STAGE;
+      for (int kt = 0; kt < p.ktiles; ++kt, ++it) {
+        const int s = it % OZ_STAGES;
+        if (it >= OZ_STAGES) mbar_wait(empty + s, (uint32_t)(((it / OZ_STAGES) - 1) & 1));
+        mbar_expect_tx(full + s, OZ_STAGE_BYTES);
+        uint8_t* dst = smem + s * OZ_STAGE_BYTES;
+        oz_bulk(dst, srcA + kt * kstep, OZ_A_STAGE, full + s);
+#pragma unroll
+        for (int u = 0; u < OZ_S; ++u)
+          oz_bulk(dst + OZ_A_STAGE + u * OZ_B_SLICE, srcB + kt * kstep + (size_t)u * OZ_A_SLICE, OZ_B_SLICE, full + s);
+      }
+    }
+  } else if (threadIdx.x == 32) {  // ---- MMA issuer
+    int it = 0, done = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+      int b, ti, tj;
+      if (!oz_tile(p, w, b, ti, tj)) continue;
+      if (done > 0) {  // the epilogue has drained the previous tile's accumulators
+        mbar_wait(tmem_empty, (uint32_t)((done - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int kt = 0; kt < p.ktiles; ++kt, ++it) {
+        const int s = it % OZ_STAGES;
+        mbar_wait(full + s, (uint32_t)((it / OZ_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da0 = oz_desc(smem_u32(smem + s * OZ_STAGE_BYTES));
+        const uint64_t db0 = oz_desc(smem_u32(smem + s * OZ_STAGE_BYTES + OZ_A_STAGE));
+        // Slice t of P meets slices u = 0 .. 7 - t of Q, whose results are the accumulators t .. 7 -- adjacent in
+        // tensor memory (64 columns each), as the Q slices are adjacent in shared memory (64 rows each).  One MMA
+        // of N = 64 L therefore serves L pairs (N <= 256: two MMAs when L > 4) and reads the P slice ONCE: with one
+        // N = 64 MMA per pair the kernel was bound by the tensor core's shared-memory reads (ncu: 48 wavefronts per
+        // MMA of 32 cycles).  12 MMAs per k step instead of 36.
+#pragma unroll
+        for (int t = 0; t < OZ_S; ++t) {
+          const int L = OZ_S - t, L0 = L > 4 ? 4 : L;
+          const uint64_t da = da0 + (uint64_t)((t * OZ_A_SLICE) >> 4);
+          // the first k step's t = 0 MMAs cover all 8 accumulators and overwrite them
+          oz_mma(tmem + (uint32_t)(t * OZ_BN), da, db0, oz_idesc(L0 * OZ_BN), (uint32_t)((kt | t) != 0));
+          if (L > 4)
+            oz_mma(tmem + (uint32_t)((t + 4) * OZ_BN), da, db0 + (uint64_t)((4 * OZ_B_SLICE) >> 4),
+                   oz_idesc((L - 4) * OZ_BN), (uint32_t)((kt | t) != 0));
+        }
+        oz_commit(empty + s);
+      }
+      oz_commit(tmem_full);
+      ++done;
+    }
+  } else if (warp >= 2) {  // ---- epilogue: TMEM -> fp64 recombination -> C
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    double* ebuf = epi + q * 32 * OZ_EPI_LD;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    const int rr = lane >> 4, cc = lane & 15;
+    int done = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+      int b, ti, tj;
+      if (!oz_tile(p, w, b, ti, tj)) continue;
+      const double sr = p.scaleA[(size_t)b * p.sScale + p.rowA0 + ti * OZ_BM + q * 32 + lane];
+      const double* scB = p.scaleB + (size_t)b * p.sScale + p.rowB0 + tj * OZ_BN;
+      double* Ct = p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN;
+      mbar_wait(tmem_full, (uint32_t)(done & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c16 = 0; c16 < OZ_BN / 16; ++c16) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[OZ_S][8];
+#pragma unroll
+          for (int g = 0; g < OZ_S; ++g) oz_ld8(tq + (uint32_t)(g * OZ_BN + c16 * 16 + h * 8), v[g]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            double x = oz_i2d(v[OZ_S - 1][j]);
+#pragma unroll
+            for (int g = OZ_S - 2; g >= 0; --g) x = fma(x, 0.0078125, oz_i2d(v[g][j]));
+            ebuf[lane * OZ_EPI_LD + h * 8 + j] = x * sr;
+          }
+        }
+        if (c16 == OZ_BN / 16 - 1) {  // every accumulator column has been read: hand TMEM back to the MMA thread
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        } else {
+          __syncwarp();
+        }
+        const double sc = scB[c16 * 16 + cc];
+        double* Cc = Ct + c16 * 16 + cc;
+        double cv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cv[i] = Cc[(size_t)(i * 2 + rr) * p.ldc];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, cv[i]);
+        __syncwarp();
+      }
+      ++done;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
+}
+
+// 8 rows per CTA: row maxima -> exponents, then 8 slices of 7 bits, rounded to nearest (|s| <= 64), written in the
+// layout the update kernel copies verbatim into shared memory:
+//   S[problem][k block of 32][row block of 128][slice][128 rows][32 bytes], 16-byte chunk c of row r at c ^ ((r >> 2) & 1)
+//   (the 32-byte swizzle of the UMMA operand descriptor);  scale[problem][row] = 2^(E - 7) with |P / 2^E| < 1/2.
+// Thread = (row r = lane & 7, chunk c = (lane >> 3) & 1, k block): 16 lanes write 256 contiguous bytes per slice.
+__global__ void __launch_bounds__(256)
+ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw, int8_t* __restrict__ S,
+                   double* __restrict__ scale, const int32_t* __restrict__ info) {
+  const int b = blockIdx.y;
+  if (info && info[b] != 0) return;
+  __shared__ double s_max[8][8];
+  __shared__ int s_bad[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane & 7, c = (lane >> 3) & 1;
+  const int row = blockIdx.x * 8 + r;
+  const int KB = kw / OZ_BK, RB = rows / OZ_BM;
+  const double* src = P + (size_t)b * sP + (size_t)row * ldp + c * 16;
+  double amax = 0.0;
+  bool bad = false;
+  for (int kb = warp * 2 + (lane >> 4); kb < KB; kb += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(src + kb * OZ_BK + j);
+      const double a0 = fabs(v.x), a1 = fabs(v.y);
+      bad |= !(a0 <= 1.7976931348623157e308) || !(a1 <= 1.7976931348623157e308);
+      amax = fmax(amax, fmax(a0, a1));
+    }
+  }
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
+  const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+  if (lane < 8) s_max[warp][lane] = amax;
+  if (lane == 0) s_bad[warp] = (int)((badmask | (badmask >> 8) | (badmask >> 16) | (badmask >> 24)) & 0xffu);
+  __syncthreads();
+  int badrows = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    amax = fmax(amax, s_max[w][r]);
+    badrows |= s_bad[w];
+  }
+  double inv = 0.0, sc = 0.0;
+  if ((badrows >> r) & 1) {
+    sc = CUDART_NAN;  // a NaN / Inf panel row poisons its rows and columns of C, like the fp64 update would
+  } else if (amax >= 1e-290) {
+    int e;
+    frexp(amax, &e);  // amax = f 2^e, f in [0.5, 1)  ->  |P| 2^-(e+1) < 1/2
+    inv = ldexp(1.0, -(e + 1));
+    sc = ldexp(1.0, e + 1 - 7);
+  }
+  if (threadIdx.x < 8) scale[(size_t)b * rows + row] = sc;
+  int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK +
+                ((c ^ ((row >> 2) & 1)) << 4);
+  const double RND = 6755399441055744.0;  // 1.5 * 2^52: (x + RND) - RND = rint(x), low word of (x + RND) = (int) rint(x)
+  for (int kb = warp * 2 + (lane >> 4); kb < KB; kb += 16) {
+    double x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(src + kb * OZ_BK + j);
+      x[j] = v.x * inv;
+      x[j + 1] = v.y * inv;
+    }
+    int8_t* d = dst + (size_t)kb * RB * OZ_A_STAGE;
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) {
+      uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const double y = x[j] * 128.0;
+        const double m = __dadd_rn(y, RND);
+        x[j] = __dsub_rn(y, __dsub_rn(m, RND));
+        wd[j >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (j & 3));
+      }
+      *reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
+}
+
+int oz_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+}  // namespace
+
+size_t ozaki_ws_bytes(int rows, int kw, int batch) {
+  // slices, then the row scales (kept 256-byte aligned)
+  const size_t slices = (size_t)batch * OZ_S * rows * kw;
+  return ((slices + 255) & ~(size_t)255) + (size_t)batch * rows * sizeof(double);
+}
+
+cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
+                               int batch, cudaStream_t st) {
+  if (rows <= 0 || kw <= 0 || batch <= 0) return cudaSuccess;
+  if ((kw & 31) || (rows & 127) || (ldp & 1) || (sP & 1) || ((uintptr_t)P & 15) || ((uintptr_t)ws & 255))
+    return cudaErrorInvalidValue;
+  int8_t* S = reinterpret_cast<int8_t*>(ws);
+  const size_t slices = (size_t)batch * OZ_S * rows * kw;
+  double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));
+  ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+  return counted(cudaGetLastError());
+}
+
+// C (region) -= P Q^T from a split workspace: rows of the region = slice rows rowA0 .., columns = slice rows rowB0 ..
+// tri: lower-triangular 128 x 64 tiles of a square region of R row tiles (banded order); otherwise R x ntc tiles,
+// lower_skip drops tiles entirely above the diagonal (row0 / col0: global coordinates of the region origin).
+cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
+                                int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
+                                int batch, cudaStream_t st) {
+  if (R <= 0 || batch <= 0 || (!tri && ntc <= 0)) return cudaSuccess;
+  if (kw > 32768) return cudaErrorInvalidValue;  // int32 accumulators
+  const int8_t* S = reinterpret_cast<const int8_t*>(ws);
+  const size_t slices = (size_t)batch * OZ_S * rows * kw;
+  const double* scale = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));
+  if ((rowA0 % OZ_BM) || (rowB0 % OZ_BN) || (kw % OZ_BK) || (rows % OZ_BM)) return cudaErrorInvalidValue;
+  static bool init = false;
+  if (!init) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    init = true;
+  }
+  OzParams p{};
+  p.C = C; p.ldc = ldc; p.sC = sC;
+  p.S = S; p.RB = rows / OZ_BM; p.KB = kw / OZ_BK;
+  p.scaleA = scale; p.scaleB = scale; p.sScale = rows;
+  p.rowA0 = rowA0; p.rowB0 = rowB0;
+  p.R = R; p.ntc = ntc; p.ntiles = tri ? R * (R + 1) : R * ntc;
+  p.ktiles = kw / OZ_BK;
+  p.tri = tri; p.lower_skip = lower_skip; p.row0 = row0; p.col0 = col0;
+  p.info = info;
+  p.total = p.ntiles * batch;
+  const int grid = p.total < oz_sm_count() ? p.total : oz_sm_count();
+  ozaki_update_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(p);
+  return counted(cudaGetLastError());
+}
+
+}  // namespace ocbo
