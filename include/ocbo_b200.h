@@ -87,6 +87,19 @@ int ocbo_diag_max(const double* A, int n, int lda, int64_t s_a, const int32_t* n
 int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
                double* invdiag, int32_t* info, int batch, ocbo_stream_t stream);
 
+/* ocbo_potrf with a device workspace (256-byte aligned, ocbo_potrf_ws_bytes(n, batch) bytes; NULL or
+ * too small: same as ocbo_potrf).  With it the rank-k trailing updates of long k run on the 5th-generation
+ * tensor cores: the finished panel is split error-free into 8 int8 slices of 7 bits with row-wise
+ * exponents, the slice products are formed by tcgen05.mma kind::i8 with exact int32 accumulation in tensor
+ * memory and recombined in fp64 in the epilogue (csrc/ozaki.cu).  Slice pairs below 2^-56 of the row maxima
+ * are dropped: the update differs from the fp64 one by <= ~1e-14 |P||P|^T element-wise (fp64's own bound
+ * for k = 2048 is 2e-13), so factors agree to rounding level but not bit for bit with ocbo_potrf.
+ * The library never allocates: ocbo_potrf_ws_bytes returns 0 when the shape would not use the workspace. */
+int64_t ocbo_potrf_ws_bytes(int n, int batch);
+int ocbo_potrf_ws(double* A, int n, int lda, int64_t s_a,
+                  double* invdiag, int32_t* info, int batch,
+                  void* ws, int64_t ws_bytes, ocbo_stream_t stream);
+
 /* ocbo_potrf for identity-padded problems: nv[b] (device, may be NULL) is the valid
  * size of problem b; elimination steps that would only touch the identity padding
  * are skipped (bit-identical result, shorter serial chain for small n). */

@@ -19,6 +19,8 @@ _PROTOS = {
     'ocbo_add_diag': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP]),
     'ocbo_diag_max': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP]),
     'ocbo_potrf': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP]),
+    'ocbo_potrf_ws_bytes': (_L, [_I, _I]),
+    'ocbo_potrf_ws': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP, _L, _VP]),
     'ocbo_potrf_nv': (_I, [_VP, _I, _I, _L, _VP, _VP, _VP, _I, _VP]),
     'ocbo_ladder_restore': (_I, [_VP, _VP, _I, _I, _L, _I, _L, _VP, _VP, ctypes.c_double, _I, _VP]),
     'ocbo_ladder_advance': (_I, [_VP, _VP, _I, _I, _I, _VP]),

@@ -153,8 +153,15 @@ static int potrf_outer_tiles(int nt) {
   return outer < nt ? outer : nt;
 }
 
+// Trailing updates through the int8 tensor cores (ozaki.cu) when the caller hands a workspace to
+// ocbo_potrf_ws: the finished outer panel is split into int8 slices once, then the rank-k update of the
+// trailing matrix runs as tcgen05.mma kind::i8 products recombined in fp64 (6144 x 2048: 0.9 ms
+// against 2.4 ms on the DMMA pipe).  Only worth it for long k and many tiles.
+static bool ozaki_wanted(int kw, int R) { return kw >= 512 && R >= 8; }
+
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
-                     int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr) {
+                     int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr,
+                     void* ws = nullptr, size_t ws_bytes = 0) {
   const int nt = n / TILE;
   const int64_t sInv = ocbo_invdiag_elems(n);
   const int NBO = potrf_outer_tiles(nt);
@@ -248,6 +255,18 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       }
     }
     const int R = nt - J1;
+    const int kw = (J1 - J0) * TILE;
+    const bool oz = ws && R > 0 && ozaki_wanted(kw, R) && ozaki_ws_bytes(R * TILE, kw, batch) <= ws_bytes;
+    if (oz) {
+      // (the helper stream's update of the previous panel read the workspace: it was joined at the end of this
+      // panel's first middle panel, or is joined here)
+      if (side_busy) {
+        CK(cudaStreamWaitEvent(st, la->join, 0), "potrf lookahead join");
+        side_busy = false;
+      }
+      CK(launch_ozaki_split(A + (size_t)J1 * TILE * lda + (size_t)J0 * TILE, lda, s_a, R * TILE, kw, ws, info, batch, st),
+         "potrf ozaki split");
+    }
     if (R > 0 && la) {
       // look-ahead: (b) A[J2:, J2:] -= L[J2:, J0:J1] L[J2:, J0:J1]^T on the helper stream ...
       // (J2 = end of the next outer panel's FIRST middle panel: the narrower (a) is, the sooner the
@@ -264,7 +283,12 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.C = A + (size_t)J2 * TILE * lda + (size_t)J2 * TILE; u.ldc = lda; u.sC = s_a;
         u.ntc = Rb * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1;
         u.info = info;
-        CK(launch_gemm_nt(u, Rb * (Rb + 1), batch, la->side), "potrf outer update (b)");
+        if (oz)
+          CK(launch_ozaki_update(ws, R * TILE, kw, (J2 - J1) * TILE, (J2 - J1) * TILE, u.C, lda, s_a, Rb, 0, 1, 0, 0, 0,
+                                 info, batch, la->side),
+             "potrf outer update (b), ozaki");
+        else
+          CK(launch_gemm_nt(u, Rb * (Rb + 1), batch, la->side), "potrf outer update (b)");
         CK(cudaEventRecord(la->join, la->side), "potrf lookahead join record");
       }
       side_busy = Rb > 0;
@@ -276,7 +300,11 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       u.ntc = (J2 - J1) * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK);
       u.row0 = J1 * TILE; u.col0 = J1 * TILE;
       u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
-      CK(launch_gemm_nt(u, R * u.ntc, batch, st), "potrf outer update (a)");
+      if (oz)
+        CK(launch_ozaki_update(ws, R * TILE, kw, 0, 0, u.C, lda, s_a, R, u.ntc, 0, 1, J1 * TILE, J1 * TILE, info, batch, st),
+           "potrf outer update (a), ozaki");
+      else
+        CK(launch_gemm_nt(u, R * u.ntc, batch, st), "potrf outer update (a)");
     } else if (R > 0) {
       // outer update: A[J1:, J1:] -= L[J1:, J0:J1] L[J1:, J0:J1]^T  (lower tiles)
       NtParams u{};
@@ -285,7 +313,11 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       u.C = A + (size_t)J1 * TILE * lda + (size_t)J1 * TILE; u.ldc = lda; u.sC = s_a;
       u.ntc = R * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1;
       u.info = info;
-      CK(launch_gemm_nt(u, R * (R + 1), batch, st), "potrf outer update");  // 2:1 lower tiles
+      if (oz)
+        CK(launch_ozaki_update(ws, R * TILE, kw, 0, 0, u.C, lda, s_a, R, 0, 1, 0, 0, 0, info, batch, st),
+           "potrf outer update, ozaki");
+      else
+        CK(launch_gemm_nt(u, R * (R + 1), batch, st), "potrf outer update");  // 2:1 lower tiles
       if (tm) tm->mark(st, 3);
     }
   }
@@ -302,6 +334,26 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t*
   if (!info) return fail_arg(6, "info null");
   if (batch <= 0) return fail_arg(7, "batch");
   return potrf_run(A, n, lda, s_a, invdiag, info, batch, (cudaStream_t)stream, nullptr);
+}
+
+int64_t ocbo_potrf_ws_bytes(int n, int batch) {
+  if (!tile_ok(n) || batch <= 0) return 0;
+  const int nt = n / TILE, NBO = potrf_outer_tiles(nt);
+  if (nt <= NBO || !ozaki_wanted(NBO * TILE, nt - NBO)) return 0;
+  return (int64_t)ozaki_ws_bytes((nt - NBO) * TILE, NBO * TILE, batch);
+}
+
+int ocbo_potrf_ws(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info, int batch,
+                  void* ws, int64_t ws_bytes, ocbo_stream_t stream) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (lda < n || (lda & 1)) return fail_arg(3, "lda must be even and >= n");
+  if (!invdiag) return fail_arg(5, "invdiag null");
+  if (!info) return fail_arg(6, "info null");
+  if (batch <= 0) return fail_arg(7, "batch");
+  if (ws && (((uintptr_t)ws & 255) || ws_bytes < 0)) return fail_arg(8, "workspace must be 256-byte aligned");
+  return potrf_run(A, n, lda, s_a, invdiag, info, batch, (cudaStream_t)stream, nullptr, nullptr, ws,
+                   ws ? (size_t)ws_bytes : 0);
 }
 
 int ocbo_potrf_nv(double* A, int n, int lda, int64_t s_a, const int32_t* nv, double* invdiag,

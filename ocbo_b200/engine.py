@@ -330,12 +330,17 @@ def gram(kind, X1, nv1, X2, nv2, theta, out, flags):
     _count(1)
 
 
-def potrf(A, invd, info, nv=None):
+def potrf(A, invd, info, nv=None, ws=None):
     """Batched in-place Cholesky; ``nv`` (device int32 [B]) marks identity padding whose
-    elimination steps the diagonal-block kernel may skip."""
+    elimination steps the diagonal-block kernel may skip; ``ws`` (uint8 device tensor of
+    ocbo_potrf_ws_bytes, full-size problems only): trailing updates on the int8 tensor cores."""
     B, n, _ = A.shape
-    call('ocbo_potrf_nv', _p(A), n, A.stride(1), A.stride(0), _p(nv), _p(invd), _p(info), B,
-         _stream())
+    if ws is not None and nv is None:
+        call('ocbo_potrf_ws', _p(A), n, A.stride(1), A.stride(0), _p(invd), _p(info), B, _p(ws), ws.numel(),
+             _stream())
+    else:
+        call('ocbo_potrf_nv', _p(A), n, A.stride(1), A.stride(0), _p(nv), _p(invd), _p(info), B,
+             _stream())
     _count(3 * (n // TILE) - 2)
 
 
@@ -606,7 +611,7 @@ NO_RUNG = -100          # rung[b] while no jitter has been needed
 LADDER = range(-11, 5)  # stable_cholesky's exponents
 
 
-def ladder_rungs(A, A0, invd, info, rung, nv, exponents):
+def ladder_rungs(A, A0, invd, info, rung, nv, exponents, ws=None):
     """Enqueue ladder rungs for a whole batch (include/ocbo_b200.h, ocbo_ladder_*): problems
     whose last attempt failed are restored from ``A0`` with jitter 10^p max(diag) and
     refactored; the others are parked.  No synchronisation."""
@@ -617,7 +622,7 @@ def ladder_rungs(A, A0, invd, info, rung, nv, exponents):
              A0.stride(0), _p(nv), _p(info), float(10.0 ** p), B, st)
         call('ocbo_ladder_advance', _p(info), _p(rung), int(p), 0, B, st)
         _count(2)
-        potrf(A, invd, info, nv)
+        potrf(A, invd, info, nv, ws)
     call('ocbo_ladder_advance', _p(info), _p(rung), 0, 1, B, st)
     _count(1)
 

@@ -20,6 +20,7 @@ trailing updates of another.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -37,7 +38,7 @@ class SweepStep(object):
 
     def __init__(self, n=1024, T=64, A=128, S=256, dim=6, batch=1, kernel_type='se',
                  scale=1.0, bandwidths=SWEEP_BANDWIDTHS, noise_var=1e-2, mu0=0.0, seed=SEED,
-                 stream=None, fused_tail=None, ladder_rungs=0):
+                 stream=None, fused_tail=None, ladder_rungs=0, ozaki=None):
         engine.require_cuda()
         if n % TILE or (T * A) % TILE:
             raise ValueError('n and T*A must be multiples of %d' % TILE)
@@ -67,6 +68,16 @@ class SweepStep(object):
             raise ValueError('the fused sampling tail needs A == %d and S %% 32 == 0' % TILE)
         self.fused_tail = can_fuse if fused_tail is None else bool(fused_tail)
         self.Z = e(B, m, S)
+        # Trailing updates of chol(Sigma) on the int8 tensor cores (ocbo_potrf_ws, csrc/ozaki.cu): the
+        # library never allocates, the step owns the slice workspace.  OCBO_OZAKI=0/1 sets the default.
+        if ozaki is None:
+            ozaki = os.environ.get('OCBO_OZAKI', '0') != '0'
+        self.ozaki = bool(ozaki)
+        self.ws = None
+        if self.ozaki:
+            nb = int(_lib.LIB.ocbo_potrf_ws_bytes(m, B))
+            if nb > 0:
+                self.ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
         # stable_cholesky's jitter ladder for Sigma walked on the device (engine.ladder_rungs):
         # the plain attempt and the first ``ladder_rungs`` rungs (10^-11, 10^-10, ... x max diag)
         # are enqueued without a host round trip; a trial that fails them all is redone from the
@@ -131,17 +142,26 @@ class SweepStep(object):
                 # keep Sigma's lower blocks: restore with an all-pass gate and zero jitter, Sigma0 <- Sigma
                 call('ocbo_ladder_restore', _p(self.Sigma0), _p(self.Sigma), m, m, self.Sigma0.stride(0),
                      m, self.Sigma.stride(0), None, _p(self.every), 0.0, B, st)
-        call('ocbo_potrf', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(infoS), B, st)
+        self._potrf_sigma(st)
         if self.ladder_rungs:
             with torch.cuda.stream(self.stream):
                 engine.ladder_rungs(self.Sigma, self.Sigma0, self.invdS, infoS, self.rung, None,
-                                    engine.LADDER[:self.ladder_rungs])
+                                    engine.LADDER[:self.ladder_rungs], ws=self.ws)
         call('ocbo_philox_normal', _p(self.Z), m, S, S, self.Z.stride(0),
              ctypes.c_uint64(self.seed), _p(self.trial_ids), B, st)
         self._sample_and_reduce(slice(0, B), st)
         call('ocbo_joint_pick', _p(self.seg_max), _p(self.seg_arg), T, 0, T, S, _p(self.task),
              _p(self.action), _p(self.gain), B, st)
         engine._count(self.launches_per_run)
+
+    def _potrf_sigma(self, st):
+        m = self.m
+        if self.ws is not None:
+            call('ocbo_potrf_ws', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(self.info[1]),
+                 self.B, _p(self.ws), self.ws.numel(), st)
+        else:
+            call('ocbo_potrf', _p(self.Sigma), m, m, self.Sigma.stride(0), _p(self.invdS), _p(self.info[1]),
+                 self.B, st)
 
     @property
     def F(self):
