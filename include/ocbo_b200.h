@@ -180,6 +180,16 @@ int ocbo_post_cov(int kind, int dim,
                   double* Sigma, int lds, int64_t s_sigma,
                   int lower_only, int batch, ocbo_stream_t stream);
 
+/* ocbo_post_cov with a device workspace (256-byte aligned, ocbo_post_cov_ws_bytes(m, n, batch) bytes; NULL, too
+ * small, lower_only == 0 or a small shape: same as ocbo_post_cov).  With it V^T V runs on the int8 tensor cores
+ * (see ocbo_potrf_ws): K(Xs, Xs) is written first, V is split column-wise into int8 slices and the fused update
+ * subtracts the product; V's padded columns must be zero (they are after ocbo_gram / ocbo_trsm_lower). */
+int64_t ocbo_post_cov_ws_bytes(int m, int n, int batch);
+int ocbo_post_cov_ws(int kind, int dim, const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                     const double* V, int n, int ldv, int64_t s_v, const double* theta,
+                     int64_t s_theta, double* Sigma, int lds, int64_t s_sigma, int lower_only,
+                     int batch, void* ws, int64_t ws_bytes, ocbo_stream_t stream);
+
 /* Cross form of the above for two point sets (get_pt_relations, :112-119):
  * C = K(A, B) - V1^T V2, V1 (n x ma), V2 (n x mb). */
 int ocbo_post_cross_cov(int kind, int dim,

@@ -32,6 +32,8 @@ _PROTOS = {
                                     _VP, _I, _VP]),
     'ocbo_post_mean': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _L, _VP, _L, _VP, _L, _I, _VP]),
     'ocbo_post_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _I, _L, _VP, _L, _VP, _I, _L, _I, _I, _VP]),
+    'ocbo_post_cov_ws_bytes': (_L, [_I, _I, _I]),
+    'ocbo_post_cov_ws': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _I, _L, _VP, _L, _VP, _I, _L, _I, _I, _VP, _L, _VP]),
     'ocbo_post_cross_cov': (_I, [_I, _I, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _VP, _I, _L, _VP, _I, _L,
                                  _I, _VP, _L, _VP, _I, _L, _I, _VP]),
     'ocbo_solve_forward_lml': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _VP, _L, _VP, _L, _VP, _VP, _I,

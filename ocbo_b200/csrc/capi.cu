@@ -142,15 +142,18 @@ static bool lookahead_enabled(int batch) {
   return v == 2 ? batch == 1 : v == 1;
 }
 
-static int potrf_outer_tiles(int nt) {
+// outer panel width in tiles: OCBO_POTRF_OUTER, else 2048 columns for fp64 (DMMA) trailing updates and 1024 when
+// they run on the int8 tensor cores (they are ~2.5x faster there, so more of the flops should be theirs:
+// measured 41.3 k against 39.3 k samples/s)
+static int potrf_outer_tiles(int nt, bool ozaki = false) {
   static int outer = -1;
   if (outer < 0) {
     const char* e = getenv("OCBO_POTRF_OUTER");
-    int v = e ? atoi(e) : 2048;
-    if (v < TILE) v = TILE;
-    outer = v / TILE;
+    int v = e ? atoi(e) : 0;
+    outer = v < TILE ? 0 : v / TILE;
   }
-  return outer < nt ? outer : nt;
+  const int o = outer ? outer : (ozaki ? 1024 / TILE : 2048 / TILE);
+  return o < nt ? o : nt;
 }
 
 // Trailing updates through the int8 tensor cores (ozaki.cu) when the caller hands a workspace to
@@ -164,7 +167,7 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
                      void* ws = nullptr, size_t ws_bytes = 0) {
   const int nt = n / TILE;
   const int64_t sInv = ocbo_invdiag_elems(n);
-  const int NBO = potrf_outer_tiles(nt);
+  const int NBO = potrf_outer_tiles(nt, ws != nullptr);
   static int left_env = -1;  // OCBO_POTRF_INNER=right|left forces the in-panel variant
   if (left_env < 0) {
     const char* e = getenv("OCBO_POTRF_INNER");
@@ -338,7 +341,7 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t*
 
 int64_t ocbo_potrf_ws_bytes(int n, int batch) {
   if (!tile_ok(n) || batch <= 0) return 0;
-  const int nt = n / TILE, NBO = potrf_outer_tiles(nt);
+  const int nt = n / TILE, NBO = potrf_outer_tiles(nt, true);
   if (nt <= NBO || !ozaki_wanted(NBO * TILE, nt - NBO)) return 0;
   return (int64_t)ozaki_ws_bytes((nt - NBO) * TILE, NBO * TILE, batch);
 }
@@ -573,6 +576,36 @@ int ocbo_post_cov(int kind, int dim, const double* Xs, int m, int64_t s_xs, cons
   p.ntc = m / TN; p.ktiles = n / BK; p.dim = dim; p.kind = kind; p.sym = 1; p.tri = lower_only ? 1 : 0;
   CK(launch_postcov(p, lower_only ? nt * (nt + 1) : nt * (m / TN), batch, (cudaStream_t)stream),
      "ocbo_post_cov");
+  return 0;
+}
+
+// Sigma = K(Xs, Xs) - V^T V with the product on the int8 tensor cores: the Gram matrix is written first (lower
+// tiles), V is split column-wise into int8 slices, and the fused update kernel subtracts V^T V from it.
+static bool post_cov_ozaki_wanted(int m, int n) { return n >= 512 && m / TILE >= 8; }
+
+int64_t ocbo_post_cov_ws_bytes(int m, int n, int batch) {
+  if (!tile_ok(m) || n <= 0 || n % TILE || batch <= 0 || !post_cov_ozaki_wanted(m, n)) return 0;
+  return (int64_t)ozaki_ws_bytes(m, n, batch);
+}
+
+int ocbo_post_cov_ws(int kind, int dim, const double* Xs, int m, int64_t s_xs, const int32_t* mv,
+                     const double* V, int n, int ldv, int64_t s_v, const double* theta,
+                     int64_t s_theta, double* Sigma, int lds, int64_t s_sigma, int lower_only,
+                     int batch, void* ws, int64_t ws_bytes, ocbo_stream_t stream) {
+  if (!ws || !lower_only || !tile_ok(m) || n <= 0 || n % TILE || !post_cov_ozaki_wanted(m, n) || batch <= 0 ||
+      ws_bytes < (int64_t)ozaki_ws_bytes(m, n, batch))
+    return ocbo_post_cov(kind, dim, Xs, m, s_xs, mv, V, n, ldv, s_v, theta, s_theta, Sigma, lds, s_sigma,
+                         lower_only, batch, stream);
+  if ((uintptr_t)ws & 255) return fail_arg(18, "workspace must be 256-byte aligned");
+  if (!V) return fail_arg(7, "V null");
+  if (ldv < m || (ldv & 1)) return fail_arg(9, "ldv");
+  int rc = ocbo_gram(kind, dim, Xs, m, s_xs, mv, Xs, m, s_xs, mv, theta, s_theta, Sigma, lds, s_sigma, batch,
+                     OCBO_GRAM_SYM | OCBO_GRAM_LOWER, stream);
+  if (rc) return rc;
+  CK(launch_ozaki_split(V, ldv, s_v, m, n, ws, nullptr, batch, (cudaStream_t)stream, 1), "post_cov ozaki split");
+  CK(launch_ozaki_update(ws, m, n, 0, 0, Sigma, lds, s_sigma, m / TILE, 0, 1, 0, 0, 0, nullptr, batch,
+                         (cudaStream_t)stream),
+     "post_cov ozaki update");
   return 0;
 }
 

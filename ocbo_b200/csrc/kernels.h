@@ -122,7 +122,7 @@ cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t 
 // C (region) -= P Q^T from the split workspace
 size_t ozaki_ws_bytes(int rows, int kw, int batch);
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
-                               int batch, cudaStream_t st);
+                               int batch, cudaStream_t st, int transposed = 0);
 cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
                                 int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
                                 int batch, cudaStream_t st);

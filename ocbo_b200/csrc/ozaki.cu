@@ -327,6 +327,76 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
   }
 }
 
+// The same split for an operand stored k-major the other way round (V: k rows x operand rows, row-major, as the
+// posterior covariance's V^T V needs it): CTA = 32 operand rows (lane = row, loads of one k are 256 contiguous
+// bytes), warp w handles the k blocks w, w + 8, ...; a thread converts 32 k values of its row and writes the
+// full 32-byte row of every slice (the swizzle only orders the two 16-byte halves): 1 KiB per warp and slice.
+__global__ void __launch_bounds__(256)
+ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows, int kw, int8_t* __restrict__ S,
+                     double* __restrict__ scale, const int32_t* __restrict__ info) {
+  const int b = blockIdx.y;
+  if (info && info[b] != 0) return;
+  __shared__ double s_max[8][32];
+  __shared__ unsigned s_bad[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 32 + lane;
+  const int KB = kw / OZ_BK, RB = rows / OZ_BM;
+  const double* src = V + (size_t)b * sV + row;
+  double amax = 0.0;
+  bool bad = false;
+  for (int kb = warp; kb < KB; kb += 8) {
+#pragma unroll 8
+    for (int j = 0; j < OZ_BK; ++j) {
+      const double a = fabs(src[(size_t)(kb * OZ_BK + j) * ldv]);
+      bad |= !(a <= 1.7976931348623157e308);
+      amax = fmax(amax, a);
+    }
+  }
+  s_max[warp][lane] = amax;
+  const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) s_bad[warp] = badmask;
+  __syncthreads();
+  unsigned badrows = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    amax = fmax(amax, s_max[w][lane]);
+    badrows |= s_bad[w];
+  }
+  double inv = 0.0, sc = 0.0;
+  if ((badrows >> lane) & 1u) {
+    sc = CUDART_NAN;
+  } else if (amax >= 1e-290) {
+    int e;
+    frexp(amax, &e);
+    inv = ldexp(1.0, -(e + 1));
+    sc = ldexp(1.0, e + 1 - 7);
+  }
+  if (warp == 0) scale[(size_t)b * rows + row] = sc;
+  int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK;
+  const int flip = (row >> 2) & 1;
+  const double RND = 6755399441055744.0;
+  for (int kb = warp; kb < KB; kb += 8) {
+    double x[OZ_BK];
+#pragma unroll
+    for (int j = 0; j < OZ_BK; ++j) x[j] = src[(size_t)(kb * OZ_BK + j) * ldv] * inv;
+    int8_t* d = dst + (size_t)kb * RB * OZ_A_STAGE;
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) {
+      uint32_t wd[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < OZ_BK; ++j) {
+        const double y = x[j] * 128.0;
+        const double m = __dadd_rn(y, RND);
+        x[j] = __dsub_rn(y, __dsub_rn(m, RND));
+        wd[j >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (j & 3));
+      }
+      uint4* o = reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE);
+      o[flip] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      o[flip ^ 1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+    }
+  }
+}
+
 int oz_sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -345,14 +415,17 @@ size_t ozaki_ws_bytes(int rows, int kw, int batch) {
 }
 
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
-                               int batch, cudaStream_t st) {
+                               int batch, cudaStream_t st, int transposed) {
   if (rows <= 0 || kw <= 0 || batch <= 0) return cudaSuccess;
   if ((kw & 31) || (rows & 127) || (ldp & 1) || (sP & 1) || ((uintptr_t)P & 15) || ((uintptr_t)ws & 255))
     return cudaErrorInvalidValue;
   int8_t* S = reinterpret_cast<int8_t*>(ws);
   const size_t slices = (size_t)batch * OZ_S * rows * kw;
   double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));
-  ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+  if (transposed)  // P: kw rows x `rows` columns
+    ozaki_split_t_kernel<<<dim3(rows / 32, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+  else
+    ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
   return counted(cudaGetLastError());
 }
 

@@ -75,7 +75,7 @@ class SweepStep(object):
         self.ozaki = bool(ozaki)
         self.ws = None
         if self.ozaki:
-            nb = int(_lib.LIB.ocbo_potrf_ws_bytes(m, B))
+            nb = max(int(_lib.LIB.ocbo_potrf_ws_bytes(m, B)), int(_lib.LIB.ocbo_post_cov_ws_bytes(m, n, B)))
             if nb > 0:
                 self.ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
         # stable_cholesky's jitter ladder for Sigma walked on the device (engine.ladder_rungs):
@@ -134,8 +134,13 @@ class SweepStep(object):
         call('ocbo_post_mean_var_from_v', _p(self.V), n, m, self.V.stride(0), None, _p(self.alpha),
              self.alpha.stride(0), _p(th), th.stride(0), m, None, _p(self.mean), self.mean.stride(0),
              None, 0, B, st)
-        call('ocbo_post_cov', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
-             self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B, st)
+        if self.ws is not None:
+            call('ocbo_post_cov_ws', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
+                 self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B,
+                 _p(self.ws), self.ws.numel(), st)
+        else:
+            call('ocbo_post_cov', self.kind, D, _p(Xs), m, Xs.stride(0), None, _p(self.V), n, m,
+                 self.V.stride(0), _p(th), th.stride(0), _p(self.Sigma), m, self.Sigma.stride(0), 1, B, st)
         if self.ladder_rungs:
             with torch.cuda.stream(self.stream):
                 self.rung.fill_(engine.NO_RUNG)
