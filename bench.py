@@ -133,6 +133,28 @@ def load_traffic(batch):
         return None
 
 
+def load_measured_peaks():
+    """MEASURED_PEAKS.json (driver-written: HBM GB/s, dense bf16 TF/s of this pool's B200s) or None."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            d = json.load(fh)
+        return d if d.get('bf16_tflops') else None
+    except Exception:
+        return None
+
+
+def timed_default(torch, fn, reps=3):
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
 _BLAS_LIMIT = []
 
 
@@ -509,44 +531,49 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: Cholesky trailing update (DMMA) ------
+        # ---- roofline of the dominant kernels, CUDA events on the group's own stream ------
         grp = groups[0]
         grp.run()
         torch.cuda.synchronize()
         st = ctypes.c_void_p(grp.stream.cuda_stream)
-        # re-assemble Sigma (the factorisation above overwrote it) and time its kernels
-        lib_call('ocbo_post_cov', grp.kind, DIM, ctypes.c_void_p(grp.Xs.data_ptr()), m,
-                 grp.Xs.stride(0), None, ctypes.c_void_p(grp.V.data_ptr()), N_OBS, m, grp.V.stride(0),
-                 ctypes.c_void_p(grp.theta.data_ptr()), grp.theta.stride(0),
-                 ctypes.c_void_p(grp.Sigma.data_ptr()), m, grp.Sigma.stride(0), 1, B, st)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        oz = grp.ws is not None
+        ws_bytes = grp.ws.numel() if oz else 0
+
+        def postcov():
+            lib_call('ocbo_post_cov_ws', grp.kind, DIM, vp(grp.Xs), m, grp.Xs.stride(0), None, vp(grp.V), N_OBS, m,
+                     grp.V.stride(0), vp(grp.theta), grp.theta.stride(0), vp(grp.Sigma), m, grp.Sigma.stride(0), 1, B,
+                     vp(grp.ws), ws_bytes, st)
+        # re-assemble Sigma (the factorisation above overwrote it) and time its kernels per launch class
+        postcov()
         grp.info.zero_()
         torch.cuda.synchronize()
-        ms3 = (ctypes.c_float * 4)()
-        lib_call('ocbo_potrf_profile', ctypes.c_void_p(grp.Sigma.data_ptr()), m, m,
-                 grp.Sigma.stride(0), ctypes.c_void_p(grp.invdS.data_ptr()),
-                 ctypes.c_void_p(grp.info[1].data_ptr()), B, st, ms3)
+        ms7 = (ctypes.c_float * 7)()
+        lib_call('ocbo_potrf_ws_profile', vp(grp.Sigma), m, m, grp.Sigma.stride(0), vp(grp.invdS), vp(grp.info[1]), B,
+                 vp(grp.ws), ws_bytes, st, ms7)
         nt = m // 128
-        # algorithmic flops of the DMMA update launches of one chol(Sigma): m^3/3 minus the
+        # algorithmic flops of the update launches of one chol(Sigma): m^3/3 minus the
         # diagonal-block factorisations (128^3/3 each) and the panel solves (rows * 128^2)
         alg = (m ** 3 / 3.0 - nt * 128.0 ** 3 / 3.0
                - sum(r * 128.0 * 128.0 ** 2 for r in range(1, nt))) * B
-        ms_upd = ms3[2] + ms3[3]
+        ms_upd = ms7[2] + ms7[3] + ms7[4] + ms7[5] + ms7[6]
         all_updates_tflops = alg / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else None
-        # the kernel's dominant role: the rank-`outer` trailing updates (one launch per outer
-        # panel); algorithmic flops = lower triangle incl. diagonal of the trailing block, 2*k each
-        outer = int(os.environ.get('OCBO_POTRF_OUTER', 2048))
+        # the rank-`outer` trailing updates (one per outer panel): algorithmic flops = lower triangle incl. the
+        # diagonal of the trailing block, 2 k each
+        outer = int(os.environ.get('OCBO_POTRF_OUTER', 1024 if oz else 2048))
         ot = max(outer // 128, 1)
         alg_outer = 0.0
         for j1 in range(ot, nt, ot):
             rows = (nt - j1) * 128.0
             alg_outer += rows * (rows + 1.0) / 2.0 * 2.0 * (ot * 128.0)
         alg_outer *= B
-        trailing_tflops = alg_outer / (ms3[3] * 1e-3) / 1e12 if ms3[3] > 0 else all_updates_tflops
+        ms_outer = ms7[5] if oz else ms7[3]
+        trailing_tflops = alg_outer / (ms_outer * 1e-3) / 1e12 if ms_outer > 0 else all_updates_tflops
         peaks = {} if args.no_peaks else measure_fp64_peaks(torch, lib_call, dev)
         peak = peaks.get('cublas_dgemm_tflops')
         step_tflops = step_flops(N_OBS, m, N_DRAW) * trials_per_step * world * args.steps \
             / (ms_resident * 1e-3) / 1e12
-        # ---- the other DMMA launch classes of the step, CUDA events on the group's own stream ----
+
         def timed(fn, reps=3):
             best = 1e9
             for _ in range(reps):
@@ -557,12 +584,6 @@ def run_b200(args):
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
             return best
-
-        def postcov():
-            lib_call('ocbo_post_cov', grp.kind, DIM, ctypes.c_void_p(grp.Xs.data_ptr()), m,
-                     grp.Xs.stride(0), None, ctypes.c_void_p(grp.V.data_ptr()), N_OBS, m, grp.V.stride(0),
-                     ctypes.c_void_p(grp.theta.data_ptr()), grp.theta.stride(0),
-                     ctypes.c_void_p(grp.Sigma.data_ptr()), m, grp.Sigma.stride(0), 1, B, st)
         ms_cov = timed(postcov)
         grp.run()                       # leaves a valid factor in Sigma for the sampling product
         torch.cuda.synchronize()
@@ -571,38 +592,88 @@ def run_b200(args):
         frac = lambda v: (v / peak) if (peak and v) else None
         cov_tf, lz_tf = tf(float(N_OBS) * m * m, ms_cov), tf(float(m) * m * N_DRAW, ms_lz)
         step_per_gpu = step_tflops / world
-        roof = {
-            'bound': 'tensor',
-            # the step-level figure leads: every kernel of the path, 16 trials in flight, algorithmic
-            # (triangular-aware) flops of BASELINE.md section 4 over the timed region
-            'scope': 'whole step, all kernels (algorithmic 278.12 GFLOP per trial-step)',
-            'achieved': step_per_gpu, 'peak': peak, 'unit': 'TFLOP/s', 'frac': frac(step_per_gpu),
+        by_class = {
+            'chol_rank%d_trailing_updates' % (ot * 128): {
+                'tflops': trailing_tflops, 'frac': frac(trailing_tflops),
+                'share_of_update_flops': alg_outer / max(alg, 1.0), 'ms': ms_outer,
+                'path': 'int8 tensor cores (ozaki_update_kernel)' if oz else 'fp64 DMMA (gemm_nt_kernel)'},
+            'chol_all_update_launches': {'tflops': all_updates_tflops, 'frac': frac(all_updates_tflops),
+                                         'ms': ms_upd},
+            'posterior_covariance_k%d' % N_OBS: {
+                'tflops': cov_tf, 'frac': frac(cov_tf), 'ms': ms_cov,
+                'path': 'Gram + int8 split + ozaki_update_kernel' if oz else 'postcov_kernel (fp64 DMMA)'},
+            'sample_LZ_fused_argmax': {'tflops': lz_tf, 'frac': frac(lz_tf), 'ms': ms_lz,
+                                       'fused_tail': bool(grp.fused_tail)},
+        }
+        potrf_ms = {'diag': ms7[0], 'panel': ms7[1], 'inner_update_fp64': ms7[2], 'outer_update_fp64': ms7[3],
+                    'int8_split': ms7[4], 'outer_update_int8': ms7[5], 'middle_update_int8': ms7[6], 'batch': B,
+                    'outer_block': outer, 'inner': os.environ.get('OCBO_POTRF_INNER', 'left')}
+        if oz:
+            # Dominant kernel: ozaki_update_kernel (tcgen05.mma kind::i8).  Its roofline is the tensor pipe:
+            # int8 operations ISSUED (36 slice-pair products per fp64 product, exact int32 accumulation) over the
+            # CUDA-event time of the launches, against the dense int8 rate = 2 x the measured dense bf16 rate of
+            # MEASURED_PEAKS.json (same tcgen05 datapath at half the operand width; cuBLASLt's own int8 GEMM,
+            # measured in this run, is printed beside it).
+            mp = load_measured_peaks()
+            int8_peak = 2.0 * mp['bf16_tflops'] if mp else None
+            int8_lib = None
+            if not args.no_peaks:
+                try:
+                    a8 = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device=dev)
+                    torch._int_mm(a8, a8.t())
+                    ms_i8 = timed_default(torch, lambda: torch._int_mm(a8, a8.t()))
+                    int8_lib = 2.0 * 8192.0 ** 3 / (ms_i8 * 1e-3) / 1e12
+                    del a8
+                except Exception:
+                    int8_lib = None
+            if int8_peak is None:
+                int8_peak = int8_lib
+            tops = 36.0 * trailing_tflops if trailing_tflops else None
+            roof = {
+                'bound': 'tensor',
+                'scope': 'ozaki_update_kernel, the %d rank-%d trailing updates of one chol(Sigma) launch group '
+                         '(batch %d), CUDA events on the launching stream' % (max(nt // ot - 1, 0), ot * 128, B),
+                'achieved': tops, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
+                'frac': (tops / int8_peak) if (tops and int8_peak) else None,
+                'ops_counted': 'int8 multiply-adds x 2 of the 36 slice-pair products per fp64 product (8 slices of 7 '
+                               'bits per operand, pairs t + u <= 7): algorithmic fp64 flops (lower triangle incl. the '
+                               'diagonal blocks, 2 k each) x 36',
+                'peak_source': ('2 x bf16_tflops of MEASURED_PEAKS.json (%.1f TF/s burst; int8 runs on the same tcgen05 '
+                                'pipe at twice the bf16 rate)' % mp['bf16_tflops']) if mp else
+                               'cuBLASLt int8 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json absent)',
+                'cublaslt_int8_tops_this_run': int8_lib,
+                'fp64_equivalent_tflops': trailing_tflops,
+                'fp64_equivalent_over_cublas_dgemm': frac(trailing_tflops),
+                'traffic': load_traffic(B),
+                'dominant_kernel': 'ozaki_update_kernel (tcgen05.mma kind::i8, TMEM accumulators, bulk-copy operand '
+                                   'pipeline): Cholesky trailing updates + posterior covariance, ~55 % of the device '
+                                   'time of a step in flight',
+                'step': {'scope': 'whole step, all kernels (algorithmic 278.12 GFLOP fp64 per trial-step)',
+                         'fp64_equivalent_tflops_per_gpu': step_per_gpu, 'cublas_dgemm_tflops': peak,
+                         'over_cublas_dgemm': frac(step_per_gpu)},
+            }
+        else:
+            roof = {
+                'bound': 'tensor',
+                'scope': 'whole step, all kernels (algorithmic 278.12 GFLOP per trial-step)',
+                'achieved': step_per_gpu, 'peak': peak, 'unit': 'TFLOP/s', 'frac': frac(step_per_gpu),
+                'traffic': load_traffic(B),
+                'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
+                               'MEASURED_PEAKS.json has no FP64 row',
+                'dominant_kernel': 'gemm_nt_kernel<128,64> (DMMA.8x8x4 fp64): Cholesky rank-k updates, '
+                                   '~55 % of the device time of a step',
+            }
+        roof.update({
             'step_tflops_per_gpu': step_per_gpu, 'step_frac_of_peak': frac(step_per_gpu),
-            'traffic': load_traffic(B),
-            'peak_source': 'cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; '
-                           'MEASURED_PEAKS.json has no FP64 row',
-            'dominant_kernel': 'gemm_nt_kernel<128,64> (DMMA.8x8x4 fp64): Cholesky rank-k updates, '
-                               '~55 % of the device time of a step',
             # launches of ONE group (batch trials) serialised on an otherwise idle GPU: short-k / small-grid
-            # classes cannot fill 148 SMs alone -- in the timed region the other 7 streams do
-            'by_launch_class': {
-                'chol_rank%d_trailing_updates' % (ot * 128): {
-                    'tflops': trailing_tflops, 'frac': frac(trailing_tflops),
-                    'share_of_update_flops': alg_outer / max(alg, 1.0), 'ms': ms3[3]},
-                'chol_all_update_launches': {'tflops': all_updates_tflops, 'frac': frac(all_updates_tflops),
-                                             'ms': ms_upd},
-                'posterior_covariance_k%d' % N_OBS: {'tflops': cov_tf, 'frac': frac(cov_tf), 'ms': ms_cov},
-                'sample_LZ_fused_argmax': {'tflops': lz_tf, 'frac': frac(lz_tf), 'ms': ms_lz,
-                                           'fused_tail': bool(grp.fused_tail)},
-            },
-            'potrf_ms': {'diag': ms3[0], 'panel': ms3[1], 'inner_update': ms3[2],
-                         'outer_update': ms3[3], 'batch': B,
-                         'outer_block': int(os.environ.get('OCBO_POTRF_OUTER', 2048)),
-                         'inner': os.environ.get('OCBO_POTRF_INNER', 'left')},
+            # classes cannot fill 148 SMs alone -- in the timed region the other 7 streams do;
+            # tflops = fp64-equivalent (algorithmic fp64 flops / time), frac = over cuBLAS DGEMM of this run
+            'by_launch_class': by_class,
+            'potrf_ms': potrf_ms,
             'operand_loads': 'cp.async' if os.environ.get('OCBO_TMA', '1') == '0' else 'TMA (cp.async.bulk.tensor)',
             'all_update_launches_tflops': all_updates_tflops,
             'fp64_probes_tflops': peaks,
-        }
+        })
         ladder_variant = None
         if world == 1 and not args.no_ladder_variant:
             ladder_variant = run_ladder_variant(torch, sweep, streams, B, args)

@@ -312,6 +312,12 @@ int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a,
                        double* invdiag, int32_t* info, int batch, ocbo_stream_t stream,
                        float* ms_host);
 
+/* ocbo_potrf_ws instrumented the same way: ms_host[7] = { diagonal-block, panel-solve, in-panel fp64 update,
+ * outer fp64 update, int8 split, int8-tensor-core outer update, int8-tensor-core middle update }. */
+int ocbo_potrf_ws_profile(double* A, int n, int lda, int64_t s_a,
+                          double* invdiag, int32_t* info, int batch,
+                          void* ws, int64_t ws_bytes, ocbo_stream_t stream, float* ms_host);
+
 /* FP64 throughput probes used by bench.py to measure the DMMA / DFMA rate the
  * roofline is quoted against (MEASURED_PEAKS.json has no FP64 row).
  * Each thread block runs `iters` dependent-free DMMA.8x8x4 / DFMA chains. */

@@ -25,6 +25,7 @@ _PROTOS = {
     'ocbo_ladder_restore': (_I, [_VP, _VP, _I, _I, _L, _I, _L, _VP, _VP, ctypes.c_double, _I, _VP]),
     'ocbo_ladder_advance': (_I, [_VP, _VP, _I, _I, _I, _VP]),
     'ocbo_ladder_adopt': (_I, [_VP, _VP, _I, _I, _L, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
+    'ocbo_potrf_ws_profile': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP, _L, _VP, _VP]),
     'ocbo_potrf_profile': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _VP, _VP]),
     'ocbo_trsm_lower': (_I, [_VP, _I, _I, _L, _VP, _VP, _I, _I, _L, _VP, _I, _VP]),
     'ocbo_solve_alpha_lml': (_I, [_VP, _I, _I, _L, _VP, _VP, _L, _VP, _VP, _L, _VP, _L, _VP, _VP, _I, _VP]),

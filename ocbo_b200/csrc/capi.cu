@@ -160,7 +160,14 @@ static int potrf_outer_tiles(int nt, bool ozaki = false) {
 // ocbo_potrf_ws: the finished outer panel is split into int8 slices once, then the rank-k update of the
 // trailing matrix runs as tcgen05.mma kind::i8 products recombined in fp64 (6144 x 2048: 0.9 ms
 // against 2.4 ms on the DMMA pipe).  Only worth it for long k and many tiles.
-static bool ozaki_wanted(int kw, int R) { return kw >= 512 && R >= 8; }
+static bool ozaki_wanted(int kw, int R) {
+  static int mink = -1;
+  if (mink < 0) {
+    const char* e = getenv("OCBO_OZAKI_MINK");
+    mink = e ? atoi(e) : 512;
+  }
+  return kw >= mink && R >= 8;
+}
 
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
                      int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr,
@@ -185,12 +192,14 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
   // -- larger grids of medium k instead of long-k launches of few CTAs.  Measured (sweep shape):
   // one trial alone 17.0 -> 15.5 ms (14.8 with MID = 512), 2 streams x 2 trials +2 %, neutral
   // at the bench's 16 trials in flight, where the other streams fill the SMs anyway.
-  static int mid_env = -1;
-  if (mid_env < 0) {
+  // (with a workspace the default is 512: the rank-512 middle updates run on the int8 tensor cores too)
+  static int mid_env = -2;
+  if (mid_env == -2) {
     const char* e = getenv("OCBO_POTRF_MID");
-    mid_env = (e ? atoi(e) : 1024) / TILE;
+    mid_env = e ? atoi(e) / TILE : -1;
   }
-  const int NBM = (mid_env > 0 && mid_env < NBO) ? mid_env : NBO;
+  const int mid = mid_env >= 0 ? mid_env : (ws ? 512 : 1024) / TILE;
+  const int NBM = (mid > 0 && mid < NBO) ? mid : NBO;
   Lookahead* la = (!tm && nt > 2 * NBO && lookahead_enabled(batch)) ? lookahead_for(st) : nullptr;
   bool side_busy = false;  // a (b) update is in flight on the helper stream
   for (int J0 = 0; J0 < nt; J0 += NBO) {
@@ -253,8 +262,18 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.ntc = (J1 - M1) * (TILE / TN); u.ktiles = (M1 - M0) * (TILE / BK);
         u.row0 = M1 * TILE; u.col0 = M1 * TILE;
         u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
-        CK(launch_gemm_nt(u, (nt - M1) * u.ntc, batch, st), "potrf middle update");
-        if (tm) tm->mark(st, 2);
+        const int kwm = (M1 - M0) * TILE, Rm = nt - M1;
+        if (ws && ozaki_wanted(kwm, Rm) && ozaki_ws_bytes(Rm * TILE, kwm, batch) <= ws_bytes) {
+          CK(launch_ozaki_split(u.P, lda, s_a, Rm * TILE, kwm, ws, info, batch, st), "potrf middle ozaki split");
+          if (tm) tm->mark(st, 4);
+          CK(launch_ozaki_update(ws, Rm * TILE, kwm, 0, 0, u.C, lda, s_a, Rm, u.ntc, 0, 1, M1 * TILE, M1 * TILE, info,
+                                 batch, st),
+             "potrf middle update, ozaki");
+          if (tm) tm->mark(st, 6);
+        } else {
+          CK(launch_gemm_nt(u, (nt - M1) * u.ntc, batch, st), "potrf middle update");
+          if (tm) tm->mark(st, 2);
+        }
       }
     }
     const int R = nt - J1;
@@ -269,6 +288,7 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       }
       CK(launch_ozaki_split(A + (size_t)J1 * TILE * lda + (size_t)J0 * TILE, lda, s_a, R * TILE, kw, ws, info, batch, st),
          "potrf ozaki split");
+      if (tm) tm->mark(st, 4);
     }
     if (R > 0 && la) {
       // look-ahead: (b) A[J2:, J2:] -= L[J2:, J0:J1] L[J2:, J0:J1]^T on the helper stream ...
@@ -321,7 +341,7 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
            "potrf outer update, ozaki");
       else
         CK(launch_gemm_nt(u, R * (R + 1), batch, st), "potrf outer update");  // 2:1 lower tiles
-      if (tm) tm->mark(st, 3);
+      if (tm) tm->mark(st, oz ? 5 : 3);
     }
   }
   if (side_busy) CK(cudaStreamWaitEvent(st, la->join, 0), "potrf lookahead final join");
@@ -417,26 +437,22 @@ int ocbo_ladder_adopt(double* A, const double* A1, int n, int lda, int64_t s_a, 
 // Same factorisation, instrumented: CUDA events after every launch on `stream`,
 // summed per kernel class into ms_host[4] = {diag, panel, inner update, outer
 // update}.  Synchronous (bench.py's roofline leg only).
-int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
-                       int batch, ocbo_stream_t stream, float* ms_host) {
-  if (!A) return fail_arg(1, "A null");
-  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
-  if (!invdiag || !info || !ms_host) return fail_arg(5, "null");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int cap = 4 * (n / TILE) + 2;
+static int potrf_profile_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info, int batch,
+                             void* ws, size_t ws_bytes, cudaStream_t st, float* ms_host, int classes) {
+  const int cap = 6 * (n / TILE) + 2;
   cudaEvent_t* ev = new cudaEvent_t[cap];
   int* cls = new int[cap];
   for (int i = 0; i < cap; ++i) cudaEventCreate(&ev[i]);
   PotrfTimer tm{ev, cls, 0, cap};
   tm.mark(st, -1);
-  int rc = potrf_run(A, n, lda, s_a, invdiag, info, batch, st, &tm);
+  int rc = potrf_run(A, n, lda, s_a, invdiag, info, batch, st, &tm, nullptr, ws, ws_bytes);
   cudaError_t se = cudaStreamSynchronize(st);
-  for (int c = 0; c < 4; ++c) ms_host[c] = 0.f;
+  for (int c = 0; c < classes; ++c) ms_host[c] = 0.f;
   if (!rc && se == cudaSuccess) {
     for (int i = 1; i < tm.n; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      ms_host[cls[i]] += ms;
+      if (cls[i] >= 0 && cls[i] < classes) ms_host[cls[i]] += ms;
     }
   }
   for (int i = 0; i < cap; ++i) cudaEventDestroy(ev[i]);
@@ -444,6 +460,26 @@ int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, 
   delete[] cls;
   if (rc) return rc;
   return check(se, "ocbo_potrf_profile sync");
+}
+
+int ocbo_potrf_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
+                       int batch, ocbo_stream_t stream, float* ms_host) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (!invdiag || !info || !ms_host) return fail_arg(5, "null");
+  return potrf_profile_run(A, n, lda, s_a, invdiag, info, batch, nullptr, 0, (cudaStream_t)stream, ms_host, 4);
+}
+
+// ocbo_potrf_ws instrumented: ms_host[7] = {diag, panel, in-panel fp64 update, outer fp64 update, ozaki split,
+// ozaki outer update, ozaki middle update}
+int ocbo_potrf_ws_profile(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info, int batch,
+                          void* ws, int64_t ws_bytes, ocbo_stream_t stream, float* ms_host) {
+  if (!A) return fail_arg(1, "A null");
+  if (!tile_ok(n)) return fail_arg(2, "n must be a positive multiple of 128");
+  if (!invdiag || !info || !ms_host) return fail_arg(5, "null");
+  if (ws && ((uintptr_t)ws & 255)) return fail_arg(8, "workspace must be 256-byte aligned");
+  return potrf_profile_run(A, n, lda, s_a, invdiag, info, batch, ws, ws ? (size_t)ws_bytes : 0, (cudaStream_t)stream,
+                           ms_host, 7);
 }
 
 
@@ -841,7 +877,7 @@ int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* 
                             int tri, ocbo_stream_t stream) {
   if (!P || !C || !ws) return fail_arg(1, "null");
   if (rows <= 0 || rows % 128) return fail_arg(3, "rows must be a positive multiple of 128");
-  if (kw <= 0 || kw % 64 || kw > 32768) return fail_arg(4, "kw must be a multiple of 64 in [64, 32768]");
+  if (kw <= 0 || kw % 32 || kw > 32768) return fail_arg(4, "kw must be a multiple of 32 in [32, 32768]");
   if (ldp < kw || (ldp & 1)) return fail_arg(2, "ldp");
   if (ldc < rows || (ldc & 1)) return fail_arg(6, "ldc");
   if (ws_bytes < (int64_t)ozaki_ws_bytes(rows, kw, 1)) return fail_arg(8, "workspace too small (ocbo_ozaki_ws_bytes)");

@@ -20,6 +20,8 @@
 // Why a fused kernel: with library int8 GEMMs the split / accumulate passes cost more than the GEMMs save
 // (0.78x); here the 8 int32 products never leave the SM and every operand byte staged in shared
 // memory feeds 36/16 as many MMAs as in a plain GEMM.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_core.cuh"
 #include "kernels.h"
@@ -397,12 +399,16 @@ ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows
   }
 }
 
+// CTAs of the persistent update kernel (one per SM, it owns the SM's shared and tensor memory).  OCBO_OZAKI_SMS
+// leaves some SMs to the latency-bound chain kernels of the other streams (diagonal blocks, panel solves).
 int oz_sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    const char* e = getenv("OCBO_OZAKI_SMS");
+    if (e && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
   }
   return n;
 }

@@ -68,10 +68,12 @@ class SweepStep(object):
             raise ValueError('the fused sampling tail needs A == %d and S %% 32 == 0' % TILE)
         self.fused_tail = can_fuse if fused_tail is None else bool(fused_tail)
         self.Z = e(B, m, S)
-        # Trailing updates of chol(Sigma) on the int8 tensor cores (ocbo_potrf_ws, csrc/ozaki.cu): the
-        # library never allocates, the step owns the slice workspace.  OCBO_OZAKI=0/1 sets the default.
+        # V^T V of the posterior covariance and the trailing updates of chol(Sigma) on the int8 tensor cores
+        # (ocbo_post_cov_ws / ocbo_potrf_ws, csrc/ozaki.cu; shapes too small for it keep the fp64 DMMA
+        # kernels).  The library never allocates: the step owns the slice workspace.  Default on;
+        # OCBO_OZAKI=0 or ozaki=False keeps every product on the fp64 tensor path.
         if ozaki is None:
-            ozaki = os.environ.get('OCBO_OZAKI', '0') != '0'
+            ozaki = os.environ.get('OCBO_OZAKI', '1') != '0'
         self.ozaki = bool(ozaki)
         self.ws = None
         if self.ozaki:
