@@ -610,7 +610,7 @@ def run_b200(args):
                     'outer_block': outer, 'inner': os.environ.get('OCBO_POTRF_INNER', 'left')}
         if oz:
             # Dominant kernel: ozaki_update_kernel (tcgen05.mma kind::i8).  Its roofline is the tensor pipe:
-            # int8 operations ISSUED (36 slice-pair products per fp64 product, exact int32 accumulation) over the
+            # int8 operations ISSUED (28 slice-pair products per fp64 product, exact int32 accumulation) over the
             # CUDA-event time of the launches, against the dense int8 rate = 2 x the measured dense bf16 rate of
             # MEASURED_PEAKS.json (same tcgen05 datapath at half the operand width; cuBLASLt's own int8 GEMM,
             # measured in this run, is printed beside it).
@@ -628,16 +628,17 @@ def run_b200(args):
                     int8_lib = None
             if int8_peak is None:
                 int8_peak = int8_lib
-            tops = 36.0 * trailing_tflops if trailing_tflops else None
+            pairs = int(LIB.ocbo_ozaki_slice_pairs())
+            tops = pairs * trailing_tflops if trailing_tflops else None
             roof = {
                 'bound': 'tensor',
                 'scope': 'ozaki_update_kernel, the %d rank-%d trailing updates of one chol(Sigma) launch group '
                          '(batch %d), CUDA events on the launching stream' % (max(nt // ot - 1, 0), ot * 128, B),
                 'achieved': tops, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
                 'frac': (tops / int8_peak) if (tops and int8_peak) else None,
-                'ops_counted': 'int8 multiply-adds x 2 of the 36 slice-pair products per fp64 product (8 slices of 7 '
-                               'bits per operand, pairs t + u <= 7): algorithmic fp64 flops (lower triangle incl. the '
-                               'diagonal blocks, 2 k each) x 36',
+                'ops_counted': 'int8 multiply-adds x 2 of the %d slice-pair products per fp64 product (7 balanced '
+                               'radix-256 slices per operand, pairs t + u <= 6): algorithmic fp64 flops (lower triangle '
+                               'incl. the diagonal blocks, 2 k each) x %d' % (pairs, pairs),
                 'peak_source': ('2 x bf16_tflops of MEASURED_PEAKS.json (%.1f TF/s burst; int8 runs on the same tcgen05 '
                                 'pipe at twice the bf16 rate)' % mp['bf16_tflops']) if mp else
                                'cuBLASLt int8 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json absent)',

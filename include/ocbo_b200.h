@@ -89,8 +89,8 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
 
 /* ocbo_potrf with a device workspace (256-byte aligned, ocbo_potrf_ws_bytes(n, batch) bytes; NULL or
  * too small: same as ocbo_potrf).  With it the rank-k trailing updates of long k run on the 5th-generation
- * tensor cores: the finished panel is split error-free into 8 int8 slices of 7 bits with row-wise
- * exponents, the slice products are formed by tcgen05.mma kind::i8 with exact int32 accumulation in tensor
+ * tensor cores: the finished panel is split error-free into 7 int8 slices (balanced radix-256 digits) with
+ * row-wise exponents, the slice products are formed by tcgen05.mma kind::i8 with exact int32 accumulation in tensor
  * memory and recombined in fp64 in the epilogue (csrc/ozaki.cu).  Slice pairs below 2^-56 of the row maxima
  * are dropped: the update differs from the fp64 one by <= ~1e-14 |P||P|^T element-wise (fp64's own bound
  * for k = 2048 is 2e-13), so factors agree to rounding level but not bit for bit with ocbo_potrf.
@@ -338,6 +338,7 @@ int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t l
  * error-free int8 slices of P (csrc/ozaki.cu); tri != 0: only the 128 x 64 tiles on and below the diagonal.
  * ws: device workspace of ocbo_ozaki_ws_bytes(rows, kw, 1) bytes, 256-byte aligned. */
 int64_t ocbo_ozaki_ws_bytes(int rows, int kw, int batch);
+int ocbo_ozaki_slice_pairs(void);  /* int8 slice-pair products issued per fp64 product (28) */
 int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* C, int ldc, void* ws,
                             int64_t ws_bytes, int tri, ocbo_stream_t stream);
 

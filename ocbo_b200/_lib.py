@@ -55,6 +55,7 @@ _PROTOS = {
     'ocbo_probe_dgemm_nt': (_I, [_VP, _VP, _VP, _I, _VP]),
     'ocbo_probe_igemm_nt': (_I, [_VP, _L, _VP, _L, _VP, _L, _I, _I, _I, _VP]),
     'ocbo_ozaki_ws_bytes': (_L, [_I, _I, _I]),
+    'ocbo_ozaki_slice_pairs': (_I, []),
     'ocbo_probe_ozaki_update': (_I, [_VP, _I, _I, _I, _VP, _I, _VP, _L, _I, _VP]),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + ['ocbo_last_error_string'])

@@ -869,6 +869,7 @@ int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t l
   CK(launch_probe_igemm(A, lda, B, ldb, C, ldc, m, n, k, (cudaStream_t)stream), "ocbo_probe_igemm_nt");
   return 0;
 }
+int ocbo_ozaki_slice_pairs(void) { return ozaki_slice_pairs(); }
 int64_t ocbo_ozaki_ws_bytes(int rows, int kw, int batch) {
   if (rows <= 0 || kw <= 0 || batch <= 0) return 0;
   return (int64_t)ozaki_ws_bytes(rows, kw, batch);
@@ -877,7 +878,7 @@ int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* 
                             int tri, ocbo_stream_t stream) {
   if (!P || !C || !ws) return fail_arg(1, "null");
   if (rows <= 0 || rows % 128) return fail_arg(3, "rows must be a positive multiple of 128");
-  if (kw <= 0 || kw % 32 || kw > 32768) return fail_arg(4, "kw must be a multiple of 32 in [32, 32768]");
+  if (kw <= 0 || kw % 32 || kw > 16384) return fail_arg(4, "kw must be a multiple of 32 in [32, 16384]");
   if (ldp < kw || (ldp & 1)) return fail_arg(2, "ldp");
   if (ldc < rows || (ldc & 1)) return fail_arg(6, "ldc");
   if (ws_bytes < (int64_t)ozaki_ws_bytes(rows, kw, 1)) return fail_arg(8, "workspace too small (ocbo_ozaki_ws_bytes)");

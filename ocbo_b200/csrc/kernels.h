@@ -121,6 +121,7 @@ cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t 
 // fp64 rank-k updates through the int8 tensor cores (ozaki.cu): split a panel into int8 slices, then
 // C (region) -= P Q^T from the split workspace
 size_t ozaki_ws_bytes(int rows, int kw, int batch);
+int ozaki_slice_pairs();  // int8 products issued per fp64 product
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
                                int batch, cudaStream_t st, int transposed = 0);
 cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,

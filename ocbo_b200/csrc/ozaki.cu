@@ -1,25 +1,28 @@
 // FP64 rank-k updates on the 5th-generation tensor cores (tcgen05.mma kind::i8), Ozaki-style:
 //
-//   P (rows x k, fp64) = scale_r * sum_{t=0..7} 2^(-7 t) s_t        s_t: int8 slices in [-64, 64], row-wise exponent
-//   P Q^T              = scale_i scale_j * sum_{g=0..7} 2^(-7 g) [ sum_{t+u=g} s_t(P) s_u(Q)^T ]
+//   P (rows x k, fp64) = scale_r * sum_{t=0..6} 2^(-8 t) s_t        s_t: int8 slices, row-wise exponent
+//   P Q^T              = scale_i scale_j * sum_{g=0..6} 2^(-8 g) [ sum_{t+u=g} s_t(P) s_u(Q)^T ]
 //
-// (slice pairs with t + u >= 8 are dropped: below 2^-56 of the row maxima; measured 1.7e-14 of max|P Q^T| on a
-// Cholesky panel, tests/tools/ozaki_probe.py.)  The integer products are EXACT: every group g is one int32
-// accumulator in tensor memory, |acc_g| <= (g + 1) k 2^12 < 2^31 for k <= 32768.
+// The slices are the BALANCED radix-256 digits (in [-128, 127], the full int8 range) of the 57-bit integer
+// rint(P / 2^E * 2^56), |P / 2^E| <= 0.498: 7 slices carry 56 bits below the row maximum, so 28 slice pairs do
+// what 36 pairs of 7-bit slices (8 x 7 = 56 bits) would.  Pairs with t + u >= 7 are dropped: below 2^-55 of the
+// product of the row maxima per term (measured <= 1e-14 |P||Q|^T element-wise on Cholesky panels; fp64's own
+// bound for k = 2048 is 2e-13).  The integer products are EXACT: every group g is one int32 accumulator in
+// tensor memory, |acc_g| <= (g + 1) k 2^14 < 2^31 for k <= 16384.
 //
 // Two kernels:
 //   ozaki_split_kernel   fp64 panel -> int8 slices + per-row scale, written as the shared-memory image of the
 //                        operand tiles (k blocks of 32 bytes, 32-byte swizzle applied), HBM bound
 //   ozaki_update_kernel  persistent, warp specialised: one thread streams those images with contiguous bulk copies
-//                        (cp.async.bulk: all 8 slices of a 128-row P tile in one 32 KiB copy, 8 x 2 KiB for the 64-row
-//                        Q tile; 4 stages of 48 KiB on mbarrier transaction counts), one thread issues the 36
-//                        slice-pair MMAs of each k step into 8 accumulators of 128 x 64 int32 (all 512 TMEM
+//                        (cp.async.bulk: all 7 slices of a 128-row P tile in one 28 KiB copy, 7 x 2 KiB for the 64-row
+//                        Q tile; 4 stages of 42 KiB on mbarrier transaction counts), one thread issues the 28
+//                        slice-pair products of each k step into 7 accumulators of 128 x 64 int32 (448 TMEM
 //                        columns), four warps read the accumulators back (tcgen05.ld), recombine them in fp64
-//                        (Horner in 2^-7, exact conversions) and apply C -= scale_i scale_j (...) through a
+//                        (Horner in 2^-8, exact conversions) and apply C -= scale_i scale_j (...) through a
 //                        shared-memory transposition so that the read-modify-write of C is coalesced.
 // Why a fused kernel: with library int8 GEMMs the split / accumulate passes cost more than the GEMMs save
 // (0.78x); here the 8 int32 products never leave the SM and every operand byte staged in shared
-// memory feeds 36/16 as many MMAs as in a plain GEMM.
+// memory feeds 28/14 as many MMAs as in a plain GEMM.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,19 +33,19 @@
 namespace ocbo {
 
 namespace {
-constexpr int OZ_S = 8;                      // slices per operand
+constexpr int OZ_S = 7;                      // slices per operand (8 bits each)
 constexpr int OZ_BM = 128, OZ_BN = 64;       // C tile
 constexpr int OZ_BK = 32;                    // bytes of k per stage = one 32-byte swizzle row = one tcgen05.mma
 constexpr int OZ_STAGES = 4;
 constexpr int OZ_A_SLICE = OZ_BM * OZ_BK, OZ_B_SLICE = OZ_BN * OZ_BK;
 constexpr int OZ_A_STAGE = OZ_S * OZ_A_SLICE, OZ_B_STAGE = OZ_S * OZ_B_SLICE;
-constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;                 // 48 KiB
+constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;                 // 42 KiB
 constexpr int OZ_EPI_LD = 17;                                           // 16 columns + 1 pad (doubles)
 constexpr int OZ_EPI_BYTES = 4 * 32 * OZ_EPI_LD * 8;
 constexpr int OZ_BAR_BYTES = 256;
 constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + 1024;
 constexpr int OZ_THREADS = 192;              // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..5: epilogue
-constexpr uint32_t OZ_TMEM_COLS = 512;       // 8 accumulators x 64 columns
+constexpr uint32_t OZ_TMEM_COLS = 512;       // 7 accumulators x 64 columns (allocations are powers of two)
 
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = S8, both K-major, N >> 3, M >> 4
 __host__ __device__ constexpr uint32_t oz_idesc(int n) {
@@ -79,6 +82,33 @@ __device__ __forceinline__ void oz_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // exact int32 -> fp64 without the conversion pipe: 2^52 + 2^31 + x as a bit pattern, minus the bias
 __device__ __forceinline__ double oz_i2d(uint32_t x) {
   return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// Row exponent: amax = f 2^e, f in [0.5, 1).  E = e + 1 gives |P| 2^-E < 1/2; the balanced 7-digit radix-256
+// range is +-0.498 2^0, so the top 0.4 % of f takes one more bit.  inv = 2^(56 - E), scale = 2^(E - 8).
+__device__ __forceinline__ void oz_exponent(double amax, bool bad, double& inv, double& sc) {
+  inv = 0.0;
+  sc = 0.0;
+  if (bad) {
+    sc = CUDART_NAN;  // a NaN / Inf panel row poisons its rows and columns of C, like the fp64 update would
+  } else if (amax >= 1e-290) {
+    int e;
+    const double f = frexp(amax, &e);
+    const int E = e + (f > 0.996 ? 2 : 1);
+    inv = ldexp(1.0, 56 - E);
+    sc = ldexp(1.0, E - 8);
+  }
+}
+// Balanced radix-256 digits of Y = rint(x 2^56) (|Y| <= 0.498 2^56), most significant first: s[0] .. s[6],
+// Y = sum_t s[t] 256^(6 - t), every s[t] in [-128, 127].
+__device__ __forceinline__ void oz_digits(double y, uint32_t (&d)[OZ_S]) {
+  long long Y = __double2ll_rn(y);
+#pragma unroll
+  for (int t = OZ_S - 1; t >= 0; --t) {
+    const int b = (int)(signed char)(Y & 0xff);
+    d[t] = (uint32_t)b & 0xffu;
+    Y = (Y - b) >> 8;
+  }
 }
 
 struct OzParams {
@@ -181,7 +211,7 @@ ozaki_update_kernel(OzParams p) {
         // tensor memory (64 columns each), as the Q slices are adjacent in shared memory (64 rows each).  One MMA
         // of N = 64 L therefore serves L pairs (N <= 256: two MMAs when L > 4) and reads the P slice ONCE: with one
         // N = 64 MMA per pair the kernel was bound by the tensor core's shared-memory reads (ncu: 48 wavefronts per
-        // MMA of 32 cycles).  12 MMAs per k step instead of 36.
+        // MMA of 32 cycles).  10 MMAs per k step instead of 28.
 #pragma unroll
         for (int t = 0; t < OZ_S; ++t) {
           const int L = OZ_S - t, L0 = L > 4 ? 4 : L;
@@ -223,7 +253,7 @@ ozaki_update_kernel(OzParams p) {
           for (int j = 0; j < 8; ++j) {
             double x = oz_i2d(v[OZ_S - 1][j]);
 #pragma unroll
-            for (int g = OZ_S - 2; g >= 0; --g) x = fma(x, 0.0078125, oz_i2d(v[g][j]));
+            for (int g = OZ_S - 2; g >= 0; --g) x = fma(x, 0.00390625, oz_i2d(v[g][j]));
             ebuf[lane * OZ_EPI_LD + h * 8 + j] = x * sr;
           }
         }
@@ -252,10 +282,10 @@ ozaki_update_kernel(OzParams p) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
 }
 
-// 8 rows per CTA: row maxima -> exponents, then 8 slices of 7 bits, rounded to nearest (|s| <= 64), written in the
+// 8 rows per CTA: row maxima -> exponents, then the 7 balanced radix-256 digits of every element, written in the
 // layout the update kernel copies verbatim into shared memory:
 //   S[problem][k block of 32][row block of 128][slice][128 rows][32 bytes], 16-byte chunk c of row r at c ^ ((r >> 2) & 1)
-//   (the 32-byte swizzle of the UMMA operand descriptor);  scale[problem][row] = 2^(E - 7) with |P / 2^E| < 1/2.
+//   (the 32-byte swizzle of the UMMA operand descriptor);  scale[problem][row] = 2^(E - 8) with |P / 2^E| <= 0.498.
 // Thread = (row r = lane & 7, chunk c = (lane >> 3) & 1, k block): 16 lanes write 256 contiguous bytes per slice.
 __global__ void __launch_bounds__(256)
 ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw, int8_t* __restrict__ S,
@@ -292,40 +322,28 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
     amax = fmax(amax, s_max[w][r]);
     badrows |= s_bad[w];
   }
-  double inv = 0.0, sc = 0.0;
-  if ((badrows >> r) & 1) {
-    sc = CUDART_NAN;  // a NaN / Inf panel row poisons its rows and columns of C, like the fp64 update would
-  } else if (amax >= 1e-290) {
-    int e;
-    frexp(amax, &e);  // amax = f 2^e, f in [0.5, 1)  ->  |P| 2^-(e+1) < 1/2
-    inv = ldexp(1.0, -(e + 1));
-    sc = ldexp(1.0, e + 1 - 7);
-  }
+  double inv, sc;
+  oz_exponent(amax, (badrows >> r) & 1, inv, sc);
   if (threadIdx.x < 8) scale[(size_t)b * rows + row] = sc;
   int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK +
                 ((c ^ ((row >> 2) & 1)) << 4);
-  const double RND = 6755399441055744.0;  // 1.5 * 2^52: (x + RND) - RND = rint(x), low word of (x + RND) = (int) rint(x)
   for (int kb = warp * 2 + (lane >> 4); kb < KB; kb += 16) {
-    double x[16];
+    uint32_t wd[OZ_S][4];
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) wd[t][0] = wd[t][1] = wd[t][2] = wd[t][3] = 0u;
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
       const double2 v = *reinterpret_cast<const double2*>(src + kb * OZ_BK + j);
-      x[j] = v.x * inv;
-      x[j + 1] = v.y * inv;
+      uint32_t d0[OZ_S], d1[OZ_S];
+      oz_digits(v.x * inv, d0);
+      oz_digits(v.y * inv, d1);
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) wd[t][j >> 2] |= (d0[t] << (8 * (j & 3))) | (d1[t] << (8 * ((j + 1) & 3)));
     }
     int8_t* d = dst + (size_t)kb * RB * OZ_A_STAGE;
 #pragma unroll
-    for (int t = 0; t < OZ_S; ++t) {
-      uint32_t wd[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const double y = x[j] * 128.0;
-        const double m = __dadd_rn(y, RND);
-        x[j] = __dsub_rn(y, __dsub_rn(m, RND));
-        wd[j >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (j & 3));
-      }
-      *reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-    }
+    for (int t = 0; t < OZ_S; ++t)
+      *reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE) = make_uint4(wd[t][0], wd[t][1], wd[t][2], wd[t][3]);
   }
 }
 
@@ -364,37 +382,30 @@ ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows
     amax = fmax(amax, s_max[w][lane]);
     badrows |= s_bad[w];
   }
-  double inv = 0.0, sc = 0.0;
-  if ((badrows >> lane) & 1u) {
-    sc = CUDART_NAN;
-  } else if (amax >= 1e-290) {
-    int e;
-    frexp(amax, &e);
-    inv = ldexp(1.0, -(e + 1));
-    sc = ldexp(1.0, e + 1 - 7);
-  }
+  double inv, sc;
+  oz_exponent(amax, (badrows >> lane) & 1u, inv, sc);
   if (warp == 0) scale[(size_t)b * rows + row] = sc;
   int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK;
   const int flip = (row >> 2) & 1;
-  const double RND = 6755399441055744.0;
   for (int kb = warp; kb < KB; kb += 8) {
-    double x[OZ_BK];
+    uint32_t wd[OZ_S][8];
 #pragma unroll
-    for (int j = 0; j < OZ_BK; ++j) x[j] = src[(size_t)(kb * OZ_BK + j) * ldv] * inv;
+    for (int t = 0; t < OZ_S; ++t)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wd[t][q] = 0u;
+#pragma unroll
+    for (int j = 0; j < OZ_BK; ++j) {
+      uint32_t dg[OZ_S];
+      oz_digits(src[(size_t)(kb * OZ_BK + j) * ldv] * inv, dg);
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) wd[t][j >> 2] |= dg[t] << (8 * (j & 3));
+    }
     int8_t* d = dst + (size_t)kb * RB * OZ_A_STAGE;
 #pragma unroll
     for (int t = 0; t < OZ_S; ++t) {
-      uint32_t wd[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int j = 0; j < OZ_BK; ++j) {
-        const double y = x[j] * 128.0;
-        const double m = __dadd_rn(y, RND);
-        x[j] = __dsub_rn(y, __dsub_rn(m, RND));
-        wd[j >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (j & 3));
-      }
       uint4* o = reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE);
-      o[flip] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-      o[flip ^ 1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+      o[flip] = make_uint4(wd[t][0], wd[t][1], wd[t][2], wd[t][3]);
+      o[flip ^ 1] = make_uint4(wd[t][4], wd[t][5], wd[t][6], wd[t][7]);
     }
   }
 }
@@ -413,6 +424,8 @@ int oz_sm_count() {
   return n;
 }
 }  // namespace
+
+int ozaki_slice_pairs() { return OZ_S * (OZ_S + 1) / 2; }
 
 size_t ozaki_ws_bytes(int rows, int kw, int batch) {
   // slices, then the row scales (kept 256-byte aligned)
@@ -442,7 +455,7 @@ cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int
                                 int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
                                 int batch, cudaStream_t st) {
   if (R <= 0 || batch <= 0 || (!tri && ntc <= 0)) return cudaSuccess;
-  if (kw > 32768) return cudaErrorInvalidValue;  // int32 accumulators
+  if (kw > 16384) return cudaErrorInvalidValue;  // int32 accumulators
   const int8_t* S = reinterpret_cast<const int8_t*>(ws);
   const size_t slices = (size_t)batch * OZ_S * rows * kw;
   const double* scale = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));

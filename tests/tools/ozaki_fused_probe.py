@@ -77,7 +77,7 @@ def main():
                          'ozaki_fp64_equivalent_tflops': flops_tri / ms_oz / 1e9,
                          'cublas_dgemm_full_square_ms': ms_lib,
                          'cublas_dgemm_tflops': 2.0 * rows * rows * kw / ms_lib / 1e9,
-                         'int8_tops': 36.0 * flops_tri / ms_oz / 1e9})
+                         'int8_tops': float(LIB.ocbo_ozaki_slice_pairs()) * flops_tri / ms_oz / 1e9})
     sys.stderr.write('ozaki 6144x2048 lower: %.3f ms (%.1f TF/s fp64-equivalent); cuBLAS full square %.3f ms\n'
                      % (ms_oz, flops_tri / ms_oz / 1e9, ms_lib))
     print(json.dumps(out))
