@@ -17,9 +17,10 @@
 //                        (cp.async.bulk: all 7 slices of a 128-row P tile in one 28 KiB copy, 7 x 2 KiB for the 64-row
 //                        Q tile; 4 stages of 42 KiB on mbarrier transaction counts), one thread issues the 28
 //                        slice-pair products of each k step into 7 accumulators of 128 x 64 int32 (448 TMEM
-//                        columns), four warps read the accumulators back (tcgen05.ld), recombine them in fp64
-//                        (Horner in 2^-8, exact conversions) and apply C -= scale_i scale_j (...) through a
-//                        shared-memory transposition so that the read-modify-write of C is coalesced.
+//                        columns), eight warps read the accumulators back (tcgen05.ld), recombine them in fp64
+//                        (Horner in 2^-8, exact conversions) into registers, release tensor memory for the next
+//                        tile, and apply C -= scale_i scale_j (...) through a shared-memory transposition
+//                        (coalesced read-modify-write of C) while the next tile's products are issued.
 // Why a fused kernel: with library int8 GEMMs the split / accumulate passes cost more than the GEMMs save
 // (0.78x); here the 8 int32 products never leave the SM and every operand byte staged in shared
 // memory feeds 28/14 as many MMAs as in a plain GEMM.
@@ -41,10 +42,11 @@ constexpr int OZ_A_SLICE = OZ_BM * OZ_BK, OZ_B_SLICE = OZ_BN * OZ_BK;
 constexpr int OZ_A_STAGE = OZ_S * OZ_A_SLICE, OZ_B_STAGE = OZ_S * OZ_B_SLICE;
 constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;                 // 42 KiB
 constexpr int OZ_EPI_LD = 17;                                           // 16 columns + 1 pad (doubles)
-constexpr int OZ_EPI_BYTES = 4 * 32 * OZ_EPI_LD * 8;
+constexpr int OZ_EPI_WARPS = 8;                                         // two per TMEM lane quarter: 32 columns each
+constexpr int OZ_EPI_BYTES = OZ_EPI_WARPS * 32 * OZ_EPI_LD * 8;
 constexpr int OZ_BAR_BYTES = 256;
 constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + 1024;
-constexpr int OZ_THREADS = 192;              // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..5: epilogue
+constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..9: epilogue
 constexpr uint32_t OZ_TMEM_COLS = 512;       // 7 accumulators x 64 columns (allocations are powers of two)
 
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = S8, both K-major, N >> 3, M >> 4
@@ -156,7 +158,7 @@ ozaki_update_kernel(OzParams p) {
       mbar_init(empty + s, 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, OZ_EPI_WARPS);
     mbar_init_fence();
   }
   if (warp == 1) {
@@ -228,42 +230,47 @@ ozaki_update_kernel(OzParams p) {
       ++done;
     }
   } else if (warp >= 2) {  // ---- epilogue: TMEM -> fp64 recombination -> C
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    double* ebuf = epi + q * 32 * OZ_EPI_LD;
-    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    // Warp = (TMEM lane quarter q, column half): thread = one row of the tile x 32 columns.  Phase (a) reads the 7
+    // accumulators of those columns and recombines them into 32 doubles in registers, then hands tensor memory back
+    // to the MMA thread; phase (b), the coalesced read-modify-write of C through a shared-memory transposition,
+    // runs beside the NEXT tile's main loop.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    double* ebuf = epi + (warp - 2) * 32 * OZ_EPI_LD;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     const int rr = lane >> 4, cc = lane & 15;
     int done = 0;
     for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
       int b, ti, tj;
       if (!oz_tile(p, w, b, ti, tj)) continue;
       const double sr = p.scaleA[(size_t)b * p.sScale + p.rowA0 + ti * OZ_BM + q * 32 + lane];
-      const double* scB = p.scaleB + (size_t)b * p.sScale + p.rowB0 + tj * OZ_BN;
-      double* Ct = p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN;
+      const double* scB = p.scaleB + (size_t)b * p.sScale + p.rowB0 + tj * OZ_BN + half * 32;
+      double* Ct = p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN + half * 32;
+      double acc[32];
       mbar_wait(tmem_full, (uint32_t)(done & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int c16 = 0; c16 < OZ_BN / 16; ++c16) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[OZ_S][8];
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t v[OZ_S][8];
 #pragma unroll
-          for (int g = 0; g < OZ_S; ++g) oz_ld8(tq + (uint32_t)(g * OZ_BN + c16 * 16 + h * 8), v[g]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int g = 0; g < OZ_S; ++g) oz_ld8(tq + (uint32_t)(g * OZ_BN + c8 * 8), v[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double x = oz_i2d(v[OZ_S - 1][j]);
+        for (int j = 0; j < 8; ++j) {
+          double x = oz_i2d(v[OZ_S - 1][j]);
 #pragma unroll
-            for (int g = OZ_S - 2; g >= 0; --g) x = fma(x, 0.00390625, oz_i2d(v[g][j]));
-            ebuf[lane * OZ_EPI_LD + h * 8 + j] = x * sr;
-          }
+          for (int g = OZ_S - 2; g >= 0; --g) x = fma(x, 0.00390625, oz_i2d(v[g][j]));
+          acc[c8 * 8 + j] = x * sr;
         }
-        if (c16 == OZ_BN / 16 - 1) {  // every accumulator column has been read: hand TMEM back to the MMA thread
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty);
-        } else {
-          __syncwarp();
-        }
+      }
+      // every accumulator column of this warp has been read: hand TMEM back to the MMA thread
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ebuf[lane * OZ_EPI_LD + j] = acc[c16 * 16 + j];
+        __syncwarp();
         const double sc = scB[c16 * 16 + cc];
         double* Cc = Ct + c16 * 16 + cc;
         double cv[16];
