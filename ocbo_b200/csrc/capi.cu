@@ -172,6 +172,7 @@ static bool ozaki_wanted(int kw, int R) {
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
                      int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr,
                      void* ws = nullptr, size_t ws_bytes = 0) {
+  if (ws && ((lda & 3) || (s_a & 3) || ((uintptr_t)A & 31))) ws = nullptr;  // the split reads 256 bits at a time
   const int nt = n / TILE;
   const int64_t sInv = ocbo_invdiag_elems(n);
   const int NBO = potrf_outer_tiles(nt, ws != nullptr);
@@ -879,7 +880,7 @@ int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* 
   if (!P || !C || !ws) return fail_arg(1, "null");
   if (rows <= 0 || rows % 128) return fail_arg(3, "rows must be a positive multiple of 128");
   if (kw <= 0 || kw % 32 || kw > 16384) return fail_arg(4, "kw must be a multiple of 32 in [32, 16384]");
-  if (ldp < kw || (ldp & 1)) return fail_arg(2, "ldp");
+  if (ldp < kw || (ldp & 3)) return fail_arg(2, "ldp must be a multiple of 4 and >= kw");
   if (ldc < rows || (ldc & 1)) return fail_arg(6, "ldc");
   if (ws_bytes < (int64_t)ozaki_ws_bytes(rows, kw, 1)) return fail_arg(8, "workspace too small (ocbo_ozaki_ws_bytes)");
   CK(launch_ozaki_split(P, ldp, 0, rows, kw, ws, nullptr, 1, (cudaStream_t)stream), "ozaki split");

@@ -289,68 +289,64 @@ ozaki_update_kernel(OzParams p) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
 }
 
-// 8 rows per CTA: row maxima -> exponents, then the 7 balanced radix-256 digits of every element, written in the
-// layout the update kernel copies verbatim into shared memory:
+// One warp per row, 8 rows per CTA: row maximum -> exponent, then the 7 balanced radix-256 digits of every element,
+// written in the layout the update kernel copies verbatim into shared memory:
 //   S[problem][k block of 32][row block of 128][slice][128 rows][32 bytes], 16-byte chunk c of row r at c ^ ((r >> 2) & 1)
 //   (the 32-byte swizzle of the UMMA operand descriptor);  scale[problem][row] = 2^(E - 8) with |P / 2^E| <= 0.498.
-// Thread = (row r = lane & 7, chunk c = (lane >> 3) & 1, k block): 16 lanes write 256 contiguous bytes per slice.
+// A lane reads 4 consecutive doubles with one 256-bit load (a warp instruction covers 1 KiB of the row: 8 full
+// lines) and writes their digits as one 32-bit word per slice; 4 lanes fill a 16-byte chunk, 8 lanes a 32-byte row of
+// a slice image.  (The first version -- 16 consecutive k per lane, 128-bit loads -- spent 32 LSU wavefronts per load
+// instruction: ncu had it LSU-bound at 73 % with 2 TB/s of traffic.)
+__device__ __forceinline__ void oz_ld4(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
 __global__ void __launch_bounds__(256)
 ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw, int8_t* __restrict__ S,
                    double* __restrict__ scale, const int32_t* __restrict__ info) {
   const int b = blockIdx.y;
   if (info && info[b] != 0) return;
-  __shared__ double s_max[8][8];
-  __shared__ int s_bad[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = lane & 7, c = (lane >> 3) & 1;
-  const int row = blockIdx.x * 8 + r;
+  const int row = blockIdx.x * 8 + warp;
   const int KB = kw / OZ_BK, RB = rows / OZ_BM;
-  const double* src = P + (size_t)b * sP + (size_t)row * ldp + c * 16;
+  const double* src = P + (size_t)b * sP + (size_t)row * ldp + lane * 4;
   double amax = 0.0;
   bool bad = false;
-  for (int kb = warp * 2 + (lane >> 4); kb < KB; kb += 16) {
+  for (int k0 = 0; k0 + lane * 4 < kw; k0 += 128) {
+    double v[4];
+    oz_ld4(src + k0, v);
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(src + kb * OZ_BK + j);
-      const double a0 = fabs(v.x), a1 = fabs(v.y);
-      bad |= !(a0 <= 1.7976931348623157e308) || !(a1 <= 1.7976931348623157e308);
-      amax = fmax(amax, fmax(a0, a1));
+    for (int j = 0; j < 4; ++j) {
+      const double a = fabs(v[j]);
+      bad |= !(a <= 1.7976931348623157e308);
+      amax = fmax(amax, a);
     }
   }
-  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
-  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
-  const unsigned badmask = __ballot_sync(0xffffffffu, bad);
-  if (lane < 8) s_max[warp][lane] = amax;
-  if (lane == 0) s_bad[warp] = (int)((badmask | (badmask >> 8) | (badmask >> 16) | (badmask >> 24)) & 0xffu);
-  __syncthreads();
-  int badrows = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    amax = fmax(amax, s_max[w][r]);
-    badrows |= s_bad[w];
-  }
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  bad = __any_sync(0xffffffffu, bad);
   double inv, sc;
-  oz_exponent(amax, (badrows >> r) & 1, inv, sc);
-  if (threadIdx.x < 8) scale[(size_t)b * rows + row] = sc;
+  oz_exponent(amax, bad, inv, sc);
+  if (lane == 0) scale[(size_t)b * rows + row] = sc;
+  // lane -> (k block within the 128-k step, chunk, word of the chunk)
+  const int kbl = lane >> 3, c = (lane >> 2) & 1, wq = lane & 3;
   int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK +
-                ((c ^ ((row >> 2) & 1)) << 4);
-  for (int kb = warp * 2 + (lane >> 4); kb < KB; kb += 16) {
-    uint32_t wd[OZ_S][4];
+                ((c ^ ((row >> 2) & 1)) << 4) + (wq << 2) + (size_t)kbl * RB * OZ_A_STAGE;
+  for (int k0 = 0; k0 + lane * 4 < kw; k0 += 128) {
+    double v[4];
+    oz_ld4(src + k0, v);
+    uint32_t wd[OZ_S];
 #pragma unroll
-    for (int t = 0; t < OZ_S; ++t) wd[t][0] = wd[t][1] = wd[t][2] = wd[t][3] = 0u;
+    for (int t = 0; t < OZ_S; ++t) wd[t] = 0u;
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(src + kb * OZ_BK + j);
-      uint32_t d0[OZ_S], d1[OZ_S];
-      oz_digits(v.x * inv, d0);
-      oz_digits(v.y * inv, d1);
+    for (int j = 0; j < 4; ++j) {
+      uint32_t dg[OZ_S];
+      oz_digits(v[j] * inv, dg);
 #pragma unroll
-      for (int t = 0; t < OZ_S; ++t) wd[t][j >> 2] |= (d0[t] << (8 * (j & 3))) | (d1[t] << (8 * ((j + 1) & 3)));
+      for (int t = 0; t < OZ_S; ++t) wd[t] |= dg[t] << (8 * j);
     }
-    int8_t* d = dst + (size_t)kb * RB * OZ_A_STAGE;
+    int8_t* d = dst + (size_t)(k0 / OZ_BK) * RB * OZ_A_STAGE;
 #pragma unroll
-    for (int t = 0; t < OZ_S; ++t)
-      *reinterpret_cast<uint4*>(d + (size_t)t * OZ_A_SLICE) = make_uint4(wd[t][0], wd[t][1], wd[t][2], wd[t][3]);
+    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(d + (size_t)t * OZ_A_SLICE) = wd[t];
   }
 }
 
@@ -443,8 +439,10 @@ size_t ozaki_ws_bytes(int rows, int kw, int batch) {
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
                                int batch, cudaStream_t st, int transposed) {
   if (rows <= 0 || kw <= 0 || batch <= 0) return cudaSuccess;
-  if ((kw & 31) || (rows & 127) || (ldp & 1) || (sP & 1) || ((uintptr_t)P & 15) || ((uintptr_t)ws & 255))
-    return cudaErrorInvalidValue;
+  if ((kw & 31) || (rows & 127) || ((uintptr_t)ws & 255)) return cudaErrorInvalidValue;
+  // row-major panels are read with 256-bit loads
+  if (!transposed && ((ldp & 3) || (sP & 3) || ((uintptr_t)P & 31))) return cudaErrorInvalidValue;
+  if (transposed && ((ldp & 1) || (sP & 1))) return cudaErrorInvalidValue;
   int8_t* S = reinterpret_cast<int8_t*>(ws);
   const size_t slices = (size_t)batch * OZ_S * rows * kw;
   double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));

@@ -3,20 +3,20 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 run() {
   tag=$1; shift
-  env "$@" OCBO_OZAKI=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-ladder-variant --sweep-trials 0 --no-one-thread --no-cpu-baseline --no-peaks > gpurun_out/r02_oztune_$tag.json 2> gpurun_out/r02_oztune_$tag.err
+  env "$@" timeout 300 python bench.py --steps 8 --warmup 3 --no-ladder-variant --sweep-trials 0 --no-one-thread --no-cpu-baseline --no-peaks > gpurun_out/r02_oztune_$tag.json 2> gpurun_out/r02_oztune_$tag.err
   python - "$tag" <<'PY'
 import json, sys
 try:
     d = json.loads(open('gpurun_out/r02_oztune_%s.json' % sys.argv[1]).read().strip().splitlines()[-1])
-    print(sys.argv[1], round(d['value']), round(d['ms_per_step'], 2), d.get('clocks', {}).get('sm_mhz'), d.get('clocks', {}).get('reasons'), d.get('parity_checked'), (d.get('parity') or {}).get('max_rel_err_samples'))
+    print(sys.argv[1], round(d['value']), round(d['ms_per_step'], 2), d.get('clocks', {}).get('sm_mhz'), d.get('clocks', {}).get('reasons'))
 except Exception as e:
     print(sys.argv[1], 'ERR', e)
 PY
 }
-run o1024_nomid OCBO_POTRF_OUTER=1024 OCBO_POTRF_MID=1024
-run o1024_m512 OCBO_POTRF_OUTER=1024 OCBO_POTRF_MID=512
+run default X=1
 run o1024_m256_k256 OCBO_POTRF_OUTER=1024 OCBO_POTRF_MID=256 OCBO_OZAKI_MINK=256
-run o2048_m512 OCBO_POTRF_OUTER=2048 OCBO_POTRF_MID=512
-run o2048_m1024 OCBO_POTRF_OUTER=2048 OCBO_POTRF_MID=1024
 run o1024_m512_k256 OCBO_POTRF_OUTER=1024 OCBO_POTRF_MID=512 OCBO_OZAKI_MINK=256
+run o2048_m512 OCBO_POTRF_OUTER=2048 OCBO_POTRF_MID=512
+run o2048_m256_k256 OCBO_POTRF_OUTER=2048 OCBO_POTRF_MID=256 OCBO_OZAKI_MINK=256
 run o512_m256_k256 OCBO_POTRF_OUTER=512 OCBO_POTRF_MID=256 OCBO_OZAKI_MINK=256
+run o768_m256_k256 OCBO_POTRF_OUTER=768 OCBO_POTRF_MID=256 OCBO_OZAKI_MINK=256
