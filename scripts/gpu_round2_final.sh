@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 artefacts (int8-tensor-core path default): parity tests, smoke, default bench line, ncu launch list of a
+# short bench command, DRAM traffic and --set full captures of the Ozaki kernels.  Each ncu command runs only after
+# the same command has exited 0 without ncu; no number printed under ncu is a bench value.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
+echo "bench exit $?"; tail -2 gpurun_out/bench.err
+BENCH_SHORT="python bench.py --steps 1 --warmup 1 --streams 1 --no-cpu-baseline --no-peaks --sweep-trials 0 --no-ladder-variant"
+$BENCH_SHORT > gpurun_out/plain_short.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/bench_launches.csv \
+    $BENCH_SHORT > gpurun_out/ncu_bench.log 2>&1
+echo "ncu bench exit $?"
+python scripts/profile_step.py 2 > gpurun_out/plain.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:"ozaki_update" --csv --log-file gpurun_out/r02_traffic_ozaki.csv \
+    python scripts/profile_step.py 2 > gpurun_out/ncu_traffic.log 2>&1
+echo "ncu traffic exit $?"
+NCU="timeout 600 ncu --set full --clock-control none --import-source on"
+OCBO_POTRF_LOOKAHEAD=0 python scripts/potrf_ws_once.py > gpurun_out/plain_potrf_ws.log 2>&1 || { echo "potrf_ws_once failed"; exit 1; }
+# first trailing update of the m = 8192 factorisation (7168 x 1024, lower tiles): the first ozaki_update launch is the
+# rank-512 middle update of panel 0, the second the trailing update
+OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_update_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_full_ozaki_update \
+    python scripts/potrf_ws_once.py > gpurun_out/ncu_f1.log 2>&1; echo "ozaki update exit $?"
+OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_split_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_full_ozaki_split \
+    python scripts/potrf_ws_once.py > gpurun_out/ncu_f2.log 2>&1; echo "ozaki split exit $?"
+$NCU -k regex:"ozaki_update_kernel|ozaki_split_t_kernel" --launch-count 2 -o gpurun_out/r02_full_ozaki_postcov \
+    python scripts/profile_step.py 1 > gpurun_out/ncu_f3.log 2>&1; echo "postcov exit $?"
+$NCU -k regex:"sample_argmax_kernel" --launch-count 1 -o gpurun_out/r02_full_sample_argmax \
+    python scripts/profile_step.py 1 > gpurun_out/ncu_f5.log 2>&1; echo "sample exit $?"
+ls -la gpurun_out/r02_full_*.ncu-rep

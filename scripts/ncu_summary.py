@@ -15,7 +15,12 @@ WANT = [('gpu__time_duration.sum', 'dur'), ('launch__grid_size', 'grid'),
         ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'st_wait'),
         ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'fp64_pct_active'),
         ('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'xu_pct_active'),
-        ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_conflicts')]
+        ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_conflicts'),
+        ('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor_pipe_pct_elapsed'),
+        ('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'tc_smem_wavefronts_pct'),
+        ('l1tex__m_xbar2l1tex_read_bytes.sum', 'l2_to_sm_read'),
+        ('l1tex__m_xbar2l1tex_read_sectors.sum.pct_of_peak_sustained_elapsed', 'l2_to_sm_pct'),
+        ('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'lsu_wavefronts_pct')]
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h, u = rows[0], rows[1]
@@ -25,7 +30,7 @@ for r in rows[2:]:
     for name, short in WANT:
         if name in h:
             i = h.index(name)
-            parts.append('%s=%s%s' % (short, r[i][:9], u[i] if short in ('dur', 'dram_rd', 'dram_wr') else ''))
+            parts.append('%s=%s%s' % (short, r[i][:9], u[i] if short in ('dur', 'dram_rd', 'dram_wr', 'l2_to_sm_read') else ''))
     try:  # achieved DRAM GB/s = (read + write bytes) / duration, in the units ncu printed
         def val(name):
             i = h.index(name)
