@@ -267,6 +267,16 @@ int ocbo_sample_tile_argmax(const double* mean, int64_t s_mean,
                             double* tile_max, int32_t* tile_arg,
                             const int32_t* info, int batch, ocbo_stream_t stream);
 
+/* ocbo_sample_tile_argmax with a device workspace (256-byte aligned, ocbo_sample_ws_bytes(m, S, batch) bytes; NULL,
+ * too small or a small shape: same as ocbo_sample_tile_argmax).  With it L (lower triangular: only the blocks up to
+ * the diagonal) and Z^T are split into int8 slices and mean + L Z runs on the int8 tensor cores (see ocbo_potrf_ws);
+ * max / first arg-max per (128-row tile, column) come out of the tensor-memory epilogue, same np.argmax rule. */
+int64_t ocbo_sample_ws_bytes(int m, int S, int batch);
+int ocbo_sample_tile_argmax_ws(const double* mean, int64_t s_mean, const double* L, int m, int ldl,
+                               int64_t s_l, const double* Z, int S, int ldz, int64_t s_z,
+                               double* tile_max, int32_t* tile_arg, const int32_t* info, int batch,
+                               void* ws, int64_t ws_bytes, ocbo_stream_t stream);
+
 /* Segmented max / first-index argmax per sample column:
  * seg_ptr[b][0..nseg] row offsets; out_max/out_arg are [batch][nseg][S]
  * (arg relative to the segment start; empty segment -> -inf / -1).

@@ -801,6 +801,36 @@ int ocbo_sample_tile_argmax(const double* mean, int64_t s_mean, const double* L,
   return 0;
 }
 
+// The same tail with the product on the int8 tensor cores (csrc/ozaki.cu): L and Z^T are split into int8 slices in
+// the caller's workspace, the per-tile max / arg-max come out of the tensor-memory epilogue.
+static bool sample_ozaki_wanted(int m, int S) { return m / TILE >= 8 && S % 64 == 0 && m <= 16384; }
+
+int64_t ocbo_sample_ws_bytes(int m, int S, int batch) {
+  if (!tile_ok(m) || S <= 0 || batch <= 0 || !sample_ozaki_wanted(m, S)) return 0;
+  return (int64_t)ozaki_sample_ws_bytes(m, S, batch);
+}
+
+int ocbo_sample_tile_argmax_ws(const double* mean, int64_t s_mean, const double* L, int m, int ldl,
+                               int64_t s_l, const double* Z, int S, int ldz, int64_t s_z,
+                               double* tile_max, int32_t* tile_arg, const int32_t* info, int batch,
+                               void* ws, int64_t ws_bytes, ocbo_stream_t stream) {
+  if (!ws || !tile_ok(m) || S <= 0 || batch <= 0 || !sample_ozaki_wanted(m, S) || (ldl & 3) || (s_l & 3) ||
+      ((uintptr_t)L & 31) || ws_bytes < (int64_t)ozaki_sample_ws_bytes(m, S, batch))
+    return ocbo_sample_tile_argmax(mean, s_mean, L, m, ldl, s_l, Z, S, ldz, s_z, tile_max, tile_arg, info, batch,
+                                   stream);
+  if ((uintptr_t)ws & 255) return fail_arg(15, "workspace must be 256-byte aligned");
+  if (!mean) return fail_arg(1, "mean null");
+  if (!L) return fail_arg(3, "L null");
+  if (ldl < m) return fail_arg(5, "ldl must be >= m");
+  if (!Z) return fail_arg(7, "Z null");
+  if (ldz < S || (ldz & 1)) return fail_arg(9, "ldz must be even and >= S");
+  if (!tile_max || !tile_arg) return fail_arg(11, "outputs null");
+  CK(launch_ozaki_sample(mean, s_mean, L, m, ldl, s_l, Z, S, ldz, s_z, tile_max, tile_arg, info, batch, ws,
+                         (cudaStream_t)stream),
+     "ocbo_sample_tile_argmax_ws");
+  return 0;
+}
+
 int ocbo_segment_argmax(const double* F, int S, int ldf, int64_t s_f, const int32_t* seg_ptr,
                         int nseg, double* out_max, int32_t* out_arg, int batch,
                         ocbo_stream_t stream) {

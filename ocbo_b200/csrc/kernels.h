@@ -123,7 +123,11 @@ cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t 
 size_t ozaki_ws_bytes(int rows, int kw, int batch);
 int ozaki_slice_pairs();  // int8 products issued per fp64 product
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
-                               int batch, cudaStream_t st, int transposed = 0);
+                               int batch, cudaStream_t st, int transposed = 0, int tri = 0);
+size_t ozaki_sample_ws_bytes(int m, int S, int batch);
+cudaError_t launch_ozaki_sample(const double* mean, int64_t sMean, const double* L, int m, int ldl, int64_t sL,
+                                const double* Z, int S, int ldz, int64_t sZ, double* tile_max, int32_t* tile_arg,
+                                const int32_t* info, int batch, void* ws, cudaStream_t st);
 cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
                                 int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
                                 int batch, cudaStream_t st);

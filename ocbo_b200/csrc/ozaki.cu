@@ -45,7 +45,8 @@ constexpr int OZ_EPI_LD = 17;                                           // 16 co
 constexpr int OZ_EPI_WARPS = 8;                                         // two per TMEM lane quarter: 32 columns each
 constexpr int OZ_EPI_BYTES = OZ_EPI_WARPS * 32 * OZ_EPI_LD * 8;
 constexpr int OZ_BAR_BYTES = 256;
-constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + 1024;
+constexpr int OZ_RED_BYTES = 2 * OZ_EPI_WARPS * 32 * (8 + 4);              // sampling mode: per-warp column maxima
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + OZ_RED_BYTES + 1024;
 constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..9: epilogue
 constexpr uint32_t OZ_TMEM_COLS = 512;       // 7 accumulators x 64 columns (allocations are powers of two)
 
@@ -116,7 +117,10 @@ __device__ __forceinline__ void oz_digits(double y, uint32_t (&d)[OZ_S]) {
 struct OzParams {
   double* C; int ldc; int64_t sC;
   const int8_t* S; int RB, KB;  // slice workspace (layout below), its 128-row blocks and 32-byte k blocks
-  const double* scaleA; const double* scaleB; int64_t sScale;  // per slice row; batch stride
+  const int8_t* SB; int RBb;    // the Q operand's slices (the same workspace for the symmetric updates)
+  const double* scaleA; const double* scaleB; int64_t sScale, sScaleB;  // per slice row; batch strides
+  // sampling mode: max / first arg-max over the 128 rows of mean + P Q^T, per column
+  const double* mean; int64_t sMean; double* tile_max; int32_t* tile_arg; int out_ld;
   int rowA0, rowB0;      // slice rows of the region's first row (multiple of 128) / first column (of 64)
   int R, ntc, ntiles;    // tri: row tiles of the square region; rect: column tiles (64 wide); tiles per problem
   int ktiles;            // k / 64
@@ -125,9 +129,23 @@ struct OzParams {
   int total;             // ntiles * batch
 };
 
-// Work item w -> (problem, tile); false: nothing to do (parked problem, tile above the diagonal).  Every role
-// evaluates this identically, so skipped items never touch a pipeline.
-__device__ __forceinline__ bool oz_tile(const OzParams& p, int w, int& b, int& ti, int& tj) {
+// Work item w -> (problem, tile, k steps); false: nothing to do (parked problem, tile above the diagonal).  Every
+// role evaluates this identically, so skipped items never touch a pipeline.
+// MODE 0: C -= P Q^T.  MODE 1 (sampling): tiles of mean + L Z with L lower triangular -- k stops at the row tile's
+// diagonal block, so the tiles differ in length: items are numbered by DESCENDING length over all problems and
+// dealt to the CTAs in snake order (round r: CTA c takes item r G + c, or r G + G - 1 - c when r is odd).
+template <int MODE>
+__device__ __forceinline__ bool oz_tile(const OzParams& p, int w, int& b, int& ti, int& tj, int& ktiles) {
+  if (MODE == 1) {
+    const int per_row = p.ntc * (p.total / p.ntiles);  // column tiles x problems
+    ti = p.R - 1 - w / per_row;
+    const int rem = w % per_row;
+    b = rem / p.ntc;
+    tj = rem - b * p.ntc;
+    ktiles = (ti + 1) * (OZ_BM / OZ_BK);
+    return !(p.info && p.info[b] != 0);
+  }
+  ktiles = p.ktiles;
   b = w / p.ntiles;
   const int t = w - b * p.ntiles;
   if (p.info && p.info[b] != 0) return false;
@@ -140,12 +158,20 @@ __device__ __forceinline__ bool oz_tile(const OzParams& p, int w, int& b, int& t
   }
   return true;
 }
+template <int MODE>
+__device__ __forceinline__ int oz_item(int round) {
+  const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  return round * G + ((MODE == 1 && (round & 1)) ? G - 1 - c : c);
+}
 
+template <int MODE>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_update_kernel(OzParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   double* epi = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+  double* red_v = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES);  // [2][8][32]
+  int* red_r = reinterpret_cast<int*>(red_v + 2 * OZ_EPI_WARPS * 32);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES);
   uint64_t* empty = full + OZ_STAGES;
   uint64_t* tmem_full = empty + OZ_STAGES;
@@ -174,16 +200,19 @@ ozaki_update_kernel(OzParams p) {
 
   if (threadIdx.x == 0) {  // ---- TMA producer
     int it = 0;
-    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
-      int b, ti, tj;
-      if (!oz_tile(p, w, b, ti, tj)) continue;
+    for (int round = 0;; ++round) {
+      const int w = oz_item<MODE>(round);
+      if (round * (int)gridDim.x >= p.total) break;
+      if (w >= p.total) continue;
+      int b, ti, tj, ktiles;
+      if (!oz_tile<MODE>(p, w, b, ti, tj, ktiles)) continue;
       // block (k block kt, row block rb) of the workspace = [slice][128 rows][32 bytes], already swizzled: the A tile
       // is ONE contiguous 32 KiB copy, the B tile 8 copies of 2 KiB (64 of the 128 rows of every slice)
       const int rbA = p.rowA0 / OZ_BM + ti, rB = p.rowB0 + tj * OZ_BN;
       const int8_t* srcA = p.S + ((size_t)b * p.KB * p.RB + rbA) * OZ_A_STAGE;
-      const int8_t* srcB = p.S + ((size_t)b * p.KB * p.RB + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
-      const size_t kstep = (size_t)p.RB * OZ_A_STAGE;
-      for (int kt = 0; kt < p.ktiles; ++kt, ++it) {
+      const int8_t* srcB = p.SB + ((size_t)b * p.KB * p.RBb + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
+      const size_t kstep = (size_t)p.RB * OZ_A_STAGE, kstepB = (size_t)p.RBb * OZ_A_STAGE;
+      for (int kt = 0; kt < ktiles; ++kt, ++it) {
         const int s = it % OZ_STAGES;
         if (it >= OZ_STAGES) mbar_wait(empty + s, (uint32_t)(((it / OZ_STAGES) - 1) & 1));
         mbar_expect_tx(full + s, OZ_STAGE_BYTES);
@@ -191,19 +220,22 @@ ozaki_update_kernel(OzParams p) {
         oz_bulk(dst, srcA + kt * kstep, OZ_A_STAGE, full + s);
 #pragma unroll
         for (int u = 0; u < OZ_S; ++u)
-          oz_bulk(dst + OZ_A_STAGE + u * OZ_B_SLICE, srcB + kt * kstep + (size_t)u * OZ_A_SLICE, OZ_B_SLICE, full + s);
+          oz_bulk(dst + OZ_A_STAGE + u * OZ_B_SLICE, srcB + kt * kstepB + (size_t)u * OZ_A_SLICE, OZ_B_SLICE, full + s);
       }
     }
   } else if (threadIdx.x == 32) {  // ---- MMA issuer
     int it = 0, done = 0;
-    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
-      int b, ti, tj;
-      if (!oz_tile(p, w, b, ti, tj)) continue;
+    for (int round = 0;; ++round) {
+      const int w = oz_item<MODE>(round);
+      if (round * (int)gridDim.x >= p.total) break;
+      if (w >= p.total) continue;
+      int b, ti, tj, ktiles;
+      if (!oz_tile<MODE>(p, w, b, ti, tj, ktiles)) continue;
       if (done > 0) {  // the epilogue has drained the previous tile's accumulators
         mbar_wait(tmem_empty, (uint32_t)((done - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      for (int kt = 0; kt < p.ktiles; ++kt, ++it) {
+      for (int kt = 0; kt < ktiles; ++kt, ++it) {
         const int s = it % OZ_STAGES;
         mbar_wait(full + s, (uint32_t)((it / OZ_STAGES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -239,12 +271,16 @@ ozaki_update_kernel(OzParams p) {
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     const int rr = lane >> 4, cc = lane & 15;
     int done = 0;
-    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
-      int b, ti, tj;
-      if (!oz_tile(p, w, b, ti, tj)) continue;
+    for (int round = 0;; ++round) {
+      const int w = oz_item<MODE>(round);
+      if (round * (int)gridDim.x >= p.total) break;
+      if (w >= p.total) continue;
+      int b, ti, tj, ktiles;
+      if (!oz_tile<MODE>(p, w, b, ti, tj, ktiles)) continue;
       const double sr = p.scaleA[(size_t)b * p.sScale + p.rowA0 + ti * OZ_BM + q * 32 + lane];
-      const double* scB = p.scaleB + (size_t)b * p.sScale + p.rowB0 + tj * OZ_BN + half * 32;
-      double* Ct = p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN + half * 32;
+      const double* scB = p.scaleB + (size_t)b * p.sScaleB + p.rowB0 + tj * OZ_BN + half * 32;
+      double* Ct = MODE == 0 ? p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN + half * 32
+                             : nullptr;
       double acc[32];
       mbar_wait(tmem_full, (uint32_t)(done & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -266,19 +302,74 @@ ozaki_update_kernel(OzParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
+      if (MODE == 0) {
 #pragma unroll
-      for (int c16 = 0; c16 < 2; ++c16) {
+        for (int c16 = 0; c16 < 2; ++c16) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ebuf[lane * OZ_EPI_LD + j] = acc[c16 * 16 + j];
-        __syncwarp();
-        const double sc = scB[c16 * 16 + cc];
-        double* Cc = Ct + c16 * 16 + cc;
-        double cv[16];
+          for (int j = 0; j < 16; ++j) ebuf[lane * OZ_EPI_LD + j] = acc[c16 * 16 + j];
+          __syncwarp();
+          const double sc = scB[c16 * 16 + cc];
+          double* Cc = Ct + c16 * 16 + cc;
+          double cv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cv[i] = Cc[(size_t)(i * 2 + rr) * p.ldc];
+          for (int i = 0; i < 16; ++i) cv[i] = Cc[(size_t)(i * 2 + rr) * p.ldc];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, cv[i]);
-        __syncwarp();
+          for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, cv[i]);
+          __syncwarp();
+        }
+      } else {
+        // F = mean + scale_i scale_j (...) is never written: per column, max / FIRST arg-max (np.argmax's rule,
+        // arg_better) over the warp's 32 rows, then over the four lane quarters through shared memory
+        const double* mu = p.mean + (size_t)b * p.sMean + (size_t)ti * OZ_BM + q * 32;
+        double* rv = red_v + ((done & 1) * OZ_EPI_WARPS + (warp - 2)) * 32;
+        int* ra = red_r + ((done & 1) * OZ_EPI_WARPS + (warp - 2)) * 32;
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ebuf[lane * OZ_EPI_LD + j] = acc[c16 * 16 + j];
+          __syncwarp();
+          const double sc = scB[c16 * 16 + cc];
+          double bv = 0.0;
+          int br = -1;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {  // rows ascending: a later equal value never wins
+            const int r = i * 2 + rr;
+            const double v = fma(ebuf[r * OZ_EPI_LD + cc], sc, mu[r]);
+            if (br < 0 || arg_better(v, q * 32 + r, bv, br)) {
+              bv = v;
+              br = q * 32 + r;
+            }
+          }
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, 16);
+          const int orr = __shfl_xor_sync(0xffffffffu, br, 16);
+          if (arg_better(ov, orr, bv, br)) {
+            bv = ov;
+            br = orr;
+          }
+          if (rr == 0) {
+            rv[c16 * 16 + cc] = bv;
+            ra[c16 * 16 + cc] = br;
+          }
+          __syncwarp();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");  // the eight epilogue warps
+        if (q == 2) {  // warps 2 and 6 (lane quarter 2): one per column half, lane = column
+          double bv = 0.0;
+          int br = -1;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {  // lane quarter qq is epilogue warp (qq + 2) % 4 + 4 * half
+            const int ew = ((qq + 2) & 3) + 4 * half;
+            const double v = red_v[((done & 1) * OZ_EPI_WARPS + ew) * 32 + lane];
+            const int r = red_r[((done & 1) * OZ_EPI_WARPS + ew) * 32 + lane];
+            if (br < 0 || arg_better(v, r, bv, br)) {
+              bv = v;
+              br = r;
+            }
+          }
+          const size_t o = ((size_t)b * p.R + ti) * p.out_ld + (size_t)tj * OZ_BN + half * 32 + lane;
+          p.tile_max[o] = bv;
+          p.tile_arg[o] = br;
+        }
       }
       ++done;
     }
@@ -301,13 +392,15 @@ __device__ __forceinline__ void oz_ld4(const double* p, double (&v)[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 __global__ void __launch_bounds__(256)
-ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw, int8_t* __restrict__ S,
-                   double* __restrict__ scale, const int32_t* __restrict__ info) {
+ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw_full, int8_t* __restrict__ S,
+                   double* __restrict__ scale, const int32_t* __restrict__ info, int tri) {
   const int b = blockIdx.y;
   if (info && info[b] != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
-  const int KB = kw / OZ_BK, RB = rows / OZ_BM;
+  const int KB = kw_full / OZ_BK, RB = rows / OZ_BM;
+  // tri: P is lower triangular (a Cholesky factor) -- only the k blocks up to the row's diagonal block exist
+  const int kw = tri ? min(kw_full, (row / OZ_BM + 1) * OZ_BM) : kw_full;
   const double* src = P + (size_t)b * sP + (size_t)row * ldp + lane * 4;
   double amax = 0.0;
   bool bad = false;
@@ -363,7 +456,7 @@ ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows
   __shared__ unsigned s_bad[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 32 + lane;
-  const int KB = kw / OZ_BK, RB = rows / OZ_BM;
+  const int KB = kw / OZ_BK, RB = (rows + OZ_BM - 1) / OZ_BM;
   const double* src = V + (size_t)b * sV + row;
   double amax = 0.0;
   bool bad = false;
@@ -430,26 +523,41 @@ int oz_sm_count() {
 
 int ozaki_slice_pairs() { return OZ_S * (OZ_S + 1) / 2; }
 
+static size_t oz_slices_bytes(int rows, int kw, int batch) {  // rows rounded up to whole 128-row blocks
+  const size_t rb = (size_t)(rows + OZ_BM - 1) / OZ_BM;
+  return (((size_t)batch * OZ_S * rb * OZ_BM * kw) + 255) & ~(size_t)255;
+}
 size_t ozaki_ws_bytes(int rows, int kw, int batch) {
   // slices, then the row scales (kept 256-byte aligned)
-  const size_t slices = (size_t)batch * OZ_S * rows * kw;
-  return ((slices + 255) & ~(size_t)255) + (size_t)batch * rows * sizeof(double);
+  return oz_slices_bytes(rows, kw, batch) + ((((size_t)batch * rows * sizeof(double)) + 255) & ~(size_t)255);
 }
 
 cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, int kw, void* ws, const int32_t* info,
-                               int batch, cudaStream_t st, int transposed) {
+                               int batch, cudaStream_t st, int transposed, int tri) {
   if (rows <= 0 || kw <= 0 || batch <= 0) return cudaSuccess;
-  if ((kw & 31) || (rows & 127) || ((uintptr_t)ws & 255)) return cudaErrorInvalidValue;
+  if ((kw & 31) || ((uintptr_t)ws & 255)) return cudaErrorInvalidValue;
   // row-major panels are read with 256-bit loads
-  if (!transposed && ((ldp & 3) || (sP & 3) || ((uintptr_t)P & 31))) return cudaErrorInvalidValue;
-  if (transposed && ((ldp & 1) || (sP & 1))) return cudaErrorInvalidValue;
+  if (!transposed && ((rows & 127) || (ldp & 3) || (sP & 3) || ((uintptr_t)P & 31))) return cudaErrorInvalidValue;
+  if (transposed && ((rows & 31) || (ldp & 1) || (sP & 1))) return cudaErrorInvalidValue;
   int8_t* S = reinterpret_cast<int8_t*>(ws);
-  const size_t slices = (size_t)batch * OZ_S * rows * kw;
-  double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));
+  double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + oz_slices_bytes(rows, kw, batch));
   if (transposed)  // P: kw rows x `rows` columns
     ozaki_split_t_kernel<<<dim3(rows / 32, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
   else
-    ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+    ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info, tri);
+  return counted(cudaGetLastError());
+}
+
+template <int MODE>
+static cudaError_t oz_launch(const OzParams& p, cudaStream_t st) {
+  static bool init = false;
+  if (!init) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    init = true;
+  }
+  const int grid = p.total < oz_sm_count() ? p.total : oz_sm_count();
+  ozaki_update_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM, st>>>(p);
   return counted(cudaGetLastError());
 }
 
@@ -462,28 +570,48 @@ cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int
   if (R <= 0 || batch <= 0 || (!tri && ntc <= 0)) return cudaSuccess;
   if (kw > 16384) return cudaErrorInvalidValue;  // int32 accumulators
   const int8_t* S = reinterpret_cast<const int8_t*>(ws);
-  const size_t slices = (size_t)batch * OZ_S * rows * kw;
-  const double* scale = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(ws) + ((slices + 255) & ~(size_t)255));
+  const double* scale = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(ws) + oz_slices_bytes(rows, kw, batch));
   if ((rowA0 % OZ_BM) || (rowB0 % OZ_BN) || (kw % OZ_BK) || (rows % OZ_BM)) return cudaErrorInvalidValue;
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
   OzParams p{};
   p.C = C; p.ldc = ldc; p.sC = sC;
   p.S = S; p.RB = rows / OZ_BM; p.KB = kw / OZ_BK;
-  p.scaleA = scale; p.scaleB = scale; p.sScale = rows;
+  p.SB = S; p.RBb = p.RB;
+  p.scaleA = scale; p.scaleB = scale; p.sScale = rows; p.sScaleB = rows;
   p.rowA0 = rowA0; p.rowB0 = rowB0;
   p.R = R; p.ntc = ntc; p.ntiles = tri ? R * (R + 1) : R * ntc;
   p.ktiles = kw / OZ_BK;
   p.tri = tri; p.lower_skip = lower_skip; p.row0 = row0; p.col0 = col0;
   p.info = info;
   p.total = p.ntiles * batch;
-  const int grid = p.total < oz_sm_count() ? p.total : oz_sm_count();
-  ozaki_update_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(p);
-  return counted(cudaGetLastError());
+  return oz_launch<0>(p, st);
+}
+
+// Fused sampling tail on the int8 tensor cores: per (row tile of 128, column) max / first arg-max of mean + L Z.
+// ws holds the slices of L (m rows, k = m, lower triangular: ozaki_ws_bytes(m, m, batch)) followed by those of
+// Z^T (S rows, k = m: ozaki_ws_bytes(S, m, batch)).
+size_t ozaki_sample_ws_bytes(int m, int S, int batch) { return ozaki_ws_bytes(m, m, batch) + ozaki_ws_bytes(S, m, batch); }
+
+cudaError_t launch_ozaki_sample(const double* mean, int64_t sMean, const double* L, int m, int ldl, int64_t sL,
+                                const double* Z, int S, int ldz, int64_t sZ, double* tile_max, int32_t* tile_arg,
+                                const int32_t* info, int batch, void* ws, cudaStream_t st) {
+  if ((m % OZ_BM) || (S % OZ_BN) || m > 16384) return cudaErrorInvalidValue;
+  uint8_t* wsL = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* wsZ = wsL + ozaki_ws_bytes(m, m, batch);
+  cudaError_t e = launch_ozaki_split(L, ldl, sL, m, m, wsL, info, batch, st, 0, 1);
+  if (e != cudaSuccess) return e;
+  e = launch_ozaki_split(Z, ldz, sZ, S, m, wsZ, info, batch, st, 1, 0);
+  if (e != cudaSuccess) return e;
+  OzParams p{};
+  p.S = reinterpret_cast<const int8_t*>(wsL); p.RB = m / OZ_BM; p.KB = m / OZ_BK;
+  p.SB = reinterpret_cast<const int8_t*>(wsZ); p.RBb = (S + OZ_BM - 1) / OZ_BM;
+  p.scaleA = reinterpret_cast<const double*>(wsL + oz_slices_bytes(m, m, batch)); p.sScale = m;
+  p.scaleB = reinterpret_cast<const double*>(wsZ + oz_slices_bytes(S, m, batch)); p.sScaleB = S;
+  p.R = m / OZ_BM; p.ntc = S / OZ_BN; p.ntiles = p.R * p.ntc;
+  p.ktiles = m / OZ_BK;
+  p.info = info;
+  p.total = p.ntiles * batch;
+  p.mean = mean; p.sMean = sMean; p.tile_max = tile_max; p.tile_arg = tile_arg; p.out_ld = S;
+  return oz_launch<1>(p, st);
 }
 
 }  // namespace ocbo
