@@ -77,7 +77,9 @@ class SweepStep(object):
         self.ozaki = bool(ozaki)
         self.ws = None
         if self.ozaki:
-            nb = max(int(_lib.LIB.ocbo_potrf_ws_bytes(m, B)), int(_lib.LIB.ocbo_post_cov_ws_bytes(m, n, B)))
+            nb = max(int(_lib.LIB.ocbo_potrf_ws_bytes(m, B)), int(_lib.LIB.ocbo_post_cov_ws_bytes(m, n, B)),
+                     int(_lib.LIB.ocbo_sample_ws_bytes(m, S, B)) if (can_fuse and S % 64 == 0 and
+                                                                   os.environ.get('OCBO_OZAKI_SAMPLE', '1') != '0') else 0)
             if nb > 0:
                 self.ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
         # stable_cholesky's jitter ladder for Sigma walked on the device (engine.ladder_rungs):
@@ -192,8 +194,13 @@ class SweepStep(object):
         sd = lambda t: 0 if nb == 1 else t.stride(0)
         mean, Sig, Z, info = self.mean[s], self.Sigma[s], self.Z[s], self.info[1, s]
         if self.fused_tail:
-            call('ocbo_sample_tile_argmax', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
-                 sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, st)
+            if self.ws is not None and os.environ.get('OCBO_OZAKI_SAMPLE', '1') != '0':
+                # (too small a workspace or shape: the entry point is ocbo_sample_tile_argmax)
+                call('ocbo_sample_tile_argmax_ws', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
+                     sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, _p(self.ws), self.ws.numel(), st)
+            else:
+                call('ocbo_sample_tile_argmax', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
+                     sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, st)
             return
         F = self._F[s]
         call('ocbo_sample', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S, sd(Z), _p(F), S,
