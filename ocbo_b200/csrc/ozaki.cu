@@ -450,7 +450,10 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
 __global__ void __launch_bounds__(256)
 ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows, int kw, int8_t* __restrict__ S,
                      double* __restrict__ scale, const int32_t* __restrict__ info) {
-  const int b = blockIdx.y;
+  // grid = (operand rows / 32, k chunks, problems): with few operand rows (Z^T: 256) the k range is cut into
+  // chunks so that the GPU is filled; every CTA then finds the row maxima over the WHOLE k range itself (the
+  // operand is small and L2 resident) and converts only its chunk
+  const int b = blockIdx.z;
   if (info && info[b] != 0) return;
   __shared__ double s_max[8][32];
   __shared__ unsigned s_bad[8];
@@ -480,10 +483,12 @@ ozaki_split_t_kernel(const double* __restrict__ V, int ldv, int64_t sV, int rows
   }
   double inv, sc;
   oz_exponent(amax, (badrows >> lane) & 1u, inv, sc);
-  if (warp == 0) scale[(size_t)b * rows + row] = sc;
+  if (warp == 0 && blockIdx.y == 0) scale[(size_t)b * rows + row] = sc;
+  const int kb_per = (KB + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int kb0 = (int)blockIdx.y * kb_per, kb1 = min(KB, kb0 + kb_per);
   int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK;
   const int flip = (row >> 2) & 1;
-  for (int kb = warp; kb < KB; kb += 8) {
+  for (int kb = kb0 + warp; kb < kb1; kb += 8) {
     uint32_t wd[OZ_S][8];
 #pragma unroll
     for (int t = 0; t < OZ_S; ++t)
@@ -541,8 +546,13 @@ cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, i
   if (transposed && ((rows & 31) || (ldp & 1) || (sP & 1))) return cudaErrorInvalidValue;
   int8_t* S = reinterpret_cast<int8_t*>(ws);
   double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + oz_slices_bytes(rows, kw, batch));
-  if (transposed)  // P: kw rows x `rows` columns
-    ozaki_split_t_kernel<<<dim3(rows / 32, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+  if (transposed) {  // P: kw rows x `rows` columns
+    const int ctas = (rows / 32) * batch;
+    int ks = ctas >= 148 ? 1 : (296 + ctas - 1) / ctas;
+    if (ks > 16) ks = 16;
+    if (ks > kw / OZ_BK / 8) ks = kw / OZ_BK / 8 > 0 ? kw / OZ_BK / 8 : 1;
+    ozaki_split_t_kernel<<<dim3(rows / 32, ks, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info);
+  }
   else
     ozaki_split_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, S, scale, info, tri);
   return counted(cudaGetLastError());
