@@ -636,12 +636,21 @@ int ocbo_post_cov_ws(int kind, int dim, const double* Xs, int m, int64_t s_xs, c
   if ((uintptr_t)ws & 255) return fail_arg(18, "workspace must be 256-byte aligned");
   if (!V) return fail_arg(7, "V null");
   if (ldv < m || (ldv & 1)) return fail_arg(9, "ldv");
-  int rc = ocbo_gram(kind, dim, Xs, m, s_xs, mv, Xs, m, s_xs, mv, theta, s_theta, Sigma, lds, s_sigma, batch,
-                     OCBO_GRAM_SYM | OCBO_GRAM_LOWER, stream);
-  if (rc) return rc;
+  static int fuse_env = -1;  // OCBO_OZAKI_FUSE_GRAM=0: Gram written by ocbo_gram first (A/B switch)
+  if (fuse_env < 0) {
+    const char* e = getenv("OCBO_OZAKI_FUSE_GRAM");
+    fuse_env = e ? (atoi(e) != 0) : 1;
+  }
+  const bool fuse = fuse_env && !mv && dim <= ozaki_gram_max_dim();  // Gram term in the update kernel's epilogue
+  if (!fuse) {
+    int rc = ocbo_gram(kind, dim, Xs, m, s_xs, mv, Xs, m, s_xs, mv, theta, s_theta, Sigma, lds, s_sigma, batch,
+                       OCBO_GRAM_SYM | OCBO_GRAM_LOWER, stream);
+    if (rc) return rc;
+  }
   CK(launch_ozaki_split(V, ldv, s_v, m, n, ws, nullptr, batch, (cudaStream_t)stream, 1), "post_cov ozaki split");
+  OzGram g{Xs, s_xs, dim, kind, theta, s_theta};
   CK(launch_ozaki_update(ws, m, n, 0, 0, Sigma, lds, s_sigma, m / TILE, 0, 1, 0, 0, 0, nullptr, batch,
-                         (cudaStream_t)stream),
+                         (cudaStream_t)stream, fuse ? &g : nullptr),
      "post_cov ozaki update");
   return 0;
 }

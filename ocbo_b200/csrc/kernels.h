@@ -128,9 +128,13 @@ size_t ozaki_sample_ws_bytes(int m, int S, int batch);
 cudaError_t launch_ozaki_sample(const double* mean, int64_t sMean, const double* L, int m, int ldl, int64_t sL,
                                 const double* Z, int S, int ldz, int64_t sZ, double* tile_max, int32_t* tile_arg,
                                 const int32_t* info, int batch, void* ws, cudaStream_t st);
+struct OzGram {  // C = K(X, X) - P Q^T: points [rows][dim] per problem, kernel kind, theta
+  const double* X; int64_t sX; int dim, kind; const double* theta; int64_t sTheta;
+};
+int ozaki_gram_max_dim();
 cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
                                 int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
-                                int batch, cudaStream_t st);
+                                int batch, cudaStream_t st, const OzGram* gram = nullptr);
 cudaError_t launch_probe_igemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc,
                                int m, int n, int k, cudaStream_t st);
 

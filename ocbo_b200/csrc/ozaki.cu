@@ -21,6 +21,10 @@
 //                        (Horner in 2^-8, exact conversions) into registers, release tensor memory for the next
 //                        tile, and apply C -= scale_i scale_j (...) through a shared-memory transposition
 //                        (coalesced read-modify-write of C) while the next tile's products are issued.
+// What bounds the main loop: shared-memory bandwidth.  Per k step the tensor core reads 10 x 4 KiB of P slices and
+// 28 x 2 KiB of Q slices and the bulk copies write 42 KiB: 138 KiB at 128 B/clk = 1.1 k clocks against 0.9 k clocks of
+// MMA issue (28 x 32) -- measured 1.19 k per k step (ncu: tensor pipe 57-62 %, tensor-core shared-memory wavefronts 61 %).
+// A cta_group::2 pairing (each CTA reads half of the Q rows and receives half of the copies) would make it MMA bound.
 // Why a fused kernel: with library int8 GEMMs the split / accumulate passes cost more than the GEMMs save
 // (0.78x); here the 8 int32 products never leave the SM and every operand byte staged in shared
 // memory feeds 28/14 as many MMAs as in a plain GEMM.
@@ -45,7 +49,10 @@ constexpr int OZ_EPI_LD = 17;                                           // 16 co
 constexpr int OZ_EPI_WARPS = 8;                                         // two per TMEM lane quarter: 32 columns each
 constexpr int OZ_EPI_BYTES = OZ_EPI_WARPS * 32 * OZ_EPI_LD * 8;
 constexpr int OZ_BAR_BYTES = 256;
-constexpr int OZ_RED_BYTES = 2 * OZ_EPI_WARPS * 32 * (8 + 4);              // sampling mode: per-warp column maxima
+constexpr int OZ_GRAM_D = 8;                                            // covariance mode: point dimension staged at most
+// sampling mode: per-warp column maxima; covariance mode: scaled points and squared norms of the tile's rows / columns
+constexpr int OZ_RED_BYTES = (OZ_BM + OZ_BN) * (OZ_GRAM_D + 1) * 8;
+static_assert(OZ_RED_BYTES >= 2 * OZ_EPI_WARPS * 32 * (8 + 4), "scratch too small for the sampling reduction");
 constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES + OZ_RED_BYTES + 1024;
 constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM allocation, warps 2..9: epilogue
 constexpr uint32_t OZ_TMEM_COLS = 512;       // 7 accumulators x 64 columns (allocations are powers of two)
@@ -121,9 +128,11 @@ struct OzParams {
   const double* scaleA; const double* scaleB; int64_t sScale, sScaleB;  // per slice row; batch strides
   // sampling mode: max / first arg-max over the 128 rows of mean + P Q^T, per column
   const double* mean; int64_t sMean; double* tile_max; int32_t* tile_arg; int out_ld;
+  // covariance mode: C = K(x_i, x_j) - P Q^T with the Gram term evaluated in the epilogue
+  const double* X; int64_t sX; int dim, kind; const double* theta; int64_t sTheta;
   int rowA0, rowB0;      // slice rows of the region's first row (multiple of 128) / first column (of 64)
   int R, ntc, ntiles;    // tri: row tiles of the square region; rect: column tiles (64 wide); tiles per problem
-  int ktiles;            // k / 64
+  int ktiles;            // k / 32
   int tri, lower_skip, row0, col0;
   const int32_t* info;
   int total;             // ntiles * batch
@@ -131,7 +140,7 @@ struct OzParams {
 
 // Work item w -> (problem, tile, k steps); false: nothing to do (parked problem, tile above the diagonal).  Every
 // role evaluates this identically, so skipped items never touch a pipeline.
-// MODE 0: C -= P Q^T.  MODE 1 (sampling): tiles of mean + L Z with L lower triangular -- k stops at the row tile's
+// MODE 0: C -= P Q^T.  MODE 2: C = K(x_i, x_j) - P Q^T (posterior covariance, same tiles).  MODE 1 (sampling): tiles of mean + L Z with L lower triangular -- k stops at the row tile's
 // diagonal block, so the tiles differ in length: items are numbered by DESCENDING length over all problems and
 // dealt to the CTAs in snake order (round r: CTA c takes item r G + c, or r G + G - 1 - c when r is odd).
 template <int MODE>
@@ -207,7 +216,7 @@ ozaki_update_kernel(OzParams p) {
       int b, ti, tj, ktiles;
       if (!oz_tile<MODE>(p, w, b, ti, tj, ktiles)) continue;
       // block (k block kt, row block rb) of the workspace = [slice][128 rows][32 bytes], already swizzled: the A tile
-      // is ONE contiguous 32 KiB copy, the B tile 8 copies of 2 KiB (64 of the 128 rows of every slice)
+      // is ONE contiguous 28 KiB copy, the B tile 7 copies of 2 KiB (64 of the 128 rows of every slice)
       const int rbA = p.rowA0 / OZ_BM + ti, rB = p.rowB0 + tj * OZ_BN;
       const int8_t* srcA = p.S + ((size_t)b * p.KB * p.RB + rbA) * OZ_A_STAGE;
       const int8_t* srcB = p.SB + ((size_t)b * p.KB * p.RBb + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
@@ -241,7 +250,7 @@ ozaki_update_kernel(OzParams p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t da0 = oz_desc(smem_u32(smem + s * OZ_STAGE_BYTES));
         const uint64_t db0 = oz_desc(smem_u32(smem + s * OZ_STAGE_BYTES + OZ_A_STAGE));
-        // Slice t of P meets slices u = 0 .. 7 - t of Q, whose results are the accumulators t .. 7 -- adjacent in
+        // Slice t of P meets slices u = 0 .. 6 - t of Q, whose results are the accumulators t .. 6 -- adjacent in
         // tensor memory (64 columns each), as the Q slices are adjacent in shared memory (64 rows each).  One MMA
         // of N = 64 L therefore serves L pairs (N <= 256: two MMAs when L > 4) and reads the P slice ONCE: with one
         // N = 64 MMA per pair the kernel was bound by the tensor core's shared-memory reads (ncu: 48 wavefronts per
@@ -250,7 +259,7 @@ ozaki_update_kernel(OzParams p) {
         for (int t = 0; t < OZ_S; ++t) {
           const int L = OZ_S - t, L0 = L > 4 ? 4 : L;
           const uint64_t da = da0 + (uint64_t)((t * OZ_A_SLICE) >> 4);
-          // the first k step's t = 0 MMAs cover all 8 accumulators and overwrite them
+          // the first k step's t = 0 MMAs cover all 7 accumulators and overwrite them
           oz_mma(tmem + (uint32_t)(t * OZ_BN), da, db0, oz_idesc(L0 * OZ_BN), (uint32_t)((kt | t) != 0));
           if (L > 4)
             oz_mma(tmem + (uint32_t)((t + 4) * OZ_BN), da, db0 + (uint64_t)((4 * OZ_B_SLICE) >> 4),
@@ -279,7 +288,7 @@ ozaki_update_kernel(OzParams p) {
       if (!oz_tile<MODE>(p, w, b, ti, tj, ktiles)) continue;
       const double sr = p.scaleA[(size_t)b * p.sScale + p.rowA0 + ti * OZ_BM + q * 32 + lane];
       const double* scB = p.scaleB + (size_t)b * p.sScaleB + p.rowB0 + tj * OZ_BN + half * 32;
-      double* Ct = MODE == 0 ? p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN + half * 32
+      double* Ct = MODE != 1 ? p.C + (size_t)b * p.sC + (size_t)(ti * OZ_BM + q * 32) * p.ldc + (size_t)tj * OZ_BN + half * 32
                              : nullptr;
       double acc[32];
       mbar_wait(tmem_full, (uint32_t)(done & 1));
@@ -302,7 +311,65 @@ ozaki_update_kernel(OzParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
-      if (MODE == 0) {
+      if (MODE == 2) {
+        // Gram term in the epilogue (K(Xs, Xs) never exists in HBM): the tile's points, scaled by 1 / bandwidth, and
+        // their squared norms are staged once per tile by the eight epilogue warps; Dragonfly's expanded-form
+        // distance in numpy's operation order (common.cuh: sqnorm_np / dist2_np), like every Gram kernel here
+        const int D = p.dim;
+        const double* th = p.theta + (size_t)b * p.sTheta;
+        double* xa = red_v;                          // [D][128]
+        double* xb = xa + OZ_GRAM_D * OZ_BM;         // [D][64]
+        double* na = xb + OZ_GRAM_D * OZ_BN;         // [128] then [64]
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");  // the previous tile's points are dead
+        {
+          const int e = threadIdx.x - 64;  // 0 .. 255
+          if (e < OZ_BM + OZ_BN) {
+            const bool isa = e < OZ_BM;
+            const int r = isa ? e : e - OZ_BM;
+            const double* x = p.X + (size_t)b * p.sX + (size_t)((isa ? ti * OZ_BM : tj * OZ_BN) + r) * D;
+            double* dst = isa ? xa + r : xb + r;
+            const int ld = isa ? OZ_BM : OZ_BN;
+            double nrm = 0.0;
+            for (int d = 0; d < D; ++d) {
+              const double v = x[d] / th[TH_BW + d];
+              dst[d * ld] = v;
+              nrm = sqnorm_np(nrm, v);
+            }
+            na[e] = nrm;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+        const double kscale = th[TH_SCALE];
+        const double* nb = na + OZ_BM;
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ebuf[lane * OZ_EPI_LD + j] = acc[c16 * 16 + j];
+          __syncwarp();
+          const int col = half * 32 + c16 * 16 + cc;   // column within the tile
+          const double sc = scB[c16 * 16 + cc];
+          double xc[OZ_GRAM_D];
+#pragma unroll
+          for (int d = 0; d < OZ_GRAM_D; ++d) xc[d] = d < D ? xb[d * OZ_BN + col] : 0.0;
+          const double ncol = nb[col];
+          double* Cc = Ct + c16 * 16 + cc;
+          double kv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = q * 32 + i * 2 + rr;
+            double dot = 0.0;
+#pragma unroll
+            for (int d = 0; d < OZ_GRAM_D; ++d)
+              if (d < D) dot = fma(xa[d * OZ_BM + r], xc[d], dot);
+            kv[i] = dist2_np(na[r], ncol, dot);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) kv[i] = kern_eval(p.kind, kscale, kv[i]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, kv[i]);
+          __syncwarp();
+        }
+      } else if (MODE == 0) {
 #pragma unroll
         for (int c16 = 0; c16 < 2; ++c16) {
 #pragma unroll
@@ -576,7 +643,7 @@ static cudaError_t oz_launch(const OzParams& p, cudaStream_t st) {
 // lower_skip drops tiles entirely above the diagonal (row0 / col0: global coordinates of the region origin).
 cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int rowB0, double* C, int ldc, int64_t sC,
                                 int R, int ntc, int tri, int lower_skip, int row0, int col0, const int32_t* info,
-                                int batch, cudaStream_t st) {
+                                int batch, cudaStream_t st, const OzGram* gram) {
   if (R <= 0 || batch <= 0 || (!tri && ntc <= 0)) return cudaSuccess;
   if (kw > 16384) return cudaErrorInvalidValue;  // int32 accumulators
   const int8_t* S = reinterpret_cast<const int8_t*>(ws);
@@ -593,8 +660,15 @@ cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int
   p.tri = tri; p.lower_skip = lower_skip; p.row0 = row0; p.col0 = col0;
   p.info = info;
   p.total = p.ntiles * batch;
+  if (gram) {  // C = K(X, X) - P Q^T on the same tiles (rows / columns of the region = points rowA0 .. / rowB0 ..)
+    if (gram->dim < 1 || gram->dim > OZ_GRAM_D || rowA0 != 0 || rowB0 != 0) return cudaErrorInvalidValue;
+    p.X = gram->X; p.sX = gram->sX; p.dim = gram->dim; p.kind = gram->kind;
+    p.theta = gram->theta; p.sTheta = gram->sTheta;
+    return oz_launch<2>(p, st);
+  }
   return oz_launch<0>(p, st);
 }
+int ozaki_gram_max_dim() { return OZ_GRAM_D; }
 
 // Fused sampling tail on the int8 tensor cores: per (row tile of 128, column) max / first arg-max of mean + L Z.
 // ws holds the slices of L (m rows, k = m, lower triangular: ozaki_ws_bytes(m, m, batch)) followed by those of
