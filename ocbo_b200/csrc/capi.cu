@@ -920,6 +920,8 @@ int ocbo_probe_ozaki_update(const double* P, int ldp, int rows, int kw, double* 
   if (rows <= 0 || rows % 128) return fail_arg(3, "rows must be a positive multiple of 128");
   if (kw <= 0 || kw % 32 || kw > 16384) return fail_arg(4, "kw must be a multiple of 32 in [32, 16384]");
   if (ldp < kw || (ldp & 3)) return fail_arg(2, "ldp must be a multiple of 4 and >= kw");
+  if ((uintptr_t)P & 31) return fail_arg(1, "P must be 32-byte aligned");
+  if ((uintptr_t)ws & 255) return fail_arg(7, "workspace must be 256-byte aligned");
   if (ldc < rows || (ldc & 1)) return fail_arg(6, "ldc");
   if (ws_bytes < (int64_t)ozaki_ws_bytes(rows, kw, 1)) return fail_arg(8, "workspace too small (ocbo_ozaki_ws_bytes)");
   CK(launch_ozaki_split(P, ldp, 0, rows, kw, ws, nullptr, 1, (cudaStream_t)stream), "ozaki split");
