@@ -471,6 +471,7 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
   const double* src = P + (size_t)b * sP + (size_t)row * ldp + lane * 4;
   double amax = 0.0;
   bool bad = false;
+#pragma unroll 4
   for (int k0 = 0; k0 + lane * 4 < kw; k0 += 128) {
     double v[4];
     oz_ld4(src + k0, v);
@@ -491,22 +492,30 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
   const int kbl = lane >> 3, c = (lane >> 2) & 1, wq = lane & 3;
   int8_t* dst = S + (size_t)b * KB * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE + (size_t)(row % OZ_BM) * OZ_BK +
                 ((c ^ ((row >> 2) & 1)) << 4) + (wq << 2) + (size_t)kbl * RB * OZ_A_STAGE;
-  for (int k0 = 0; k0 + lane * 4 < kw; k0 += 128) {
-    double v[4];
-    oz_ld4(src + k0, v);
-    uint32_t wd[OZ_S];
+  // two 128-k steps per iteration: both loads are issued before the digit chains start (the loop was bound by the
+  // latency of one 256-bit load per iteration: ncu long-scoreboard stalls, 2.5 TB/s)
+  for (int k0 = 0; k0 + lane * 4 < kw; k0 += 256) {
+    double v[2][4];
+    const bool two = k0 + 128 + lane * 4 < kw;
+    oz_ld4(src + k0, v[0]);
+    if (two) oz_ld4(src + k0 + 128, v[1]);
 #pragma unroll
-    for (int t = 0; t < OZ_S; ++t) wd[t] = 0u;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      uint32_t wd[OZ_S];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t dg[OZ_S];
-      oz_digits(v[j] * inv, dg);
+      for (int t = 0; t < OZ_S; ++t) wd[t] = 0u;
 #pragma unroll
-      for (int t = 0; t < OZ_S; ++t) wd[t] |= dg[t] << (8 * j);
+      for (int j = 0; j < 4; ++j) {
+        uint32_t dg[OZ_S];
+        oz_digits(v[h][j] * inv, dg);
+#pragma unroll
+        for (int t = 0; t < OZ_S; ++t) wd[t] |= dg[t] << (8 * j);
+      }
+      int8_t* d = dst + (size_t)((k0 + h * 128) / OZ_BK) * RB * OZ_A_STAGE;
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(d + (size_t)t * OZ_A_SLICE) = wd[t];
     }
-    int8_t* d = dst + (size_t)(k0 / OZ_BK) * RB * OZ_A_STAGE;
-#pragma unroll
-    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(d + (size_t)t * OZ_A_SLICE) = wd[t];
   }
 }
 

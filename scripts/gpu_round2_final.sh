@@ -6,6 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
+OCBO_OZAKI=0 timeout 1200 python -m pytest tests/test_gpu_sweep.py tests/test_gpu_parity.py -m gpu -q --timeout=900 > gpurun_out/pytest_gpu_fp64_path.log 2>&1
+echo "pytest (OCBO_OZAKI=0: sweep + parity files) exit $?" >> gpurun_out/pytest_gpu_fp64_path.log; tail -2 gpurun_out/pytest_gpu_fp64_path.log
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -2 gpurun_out/bench.err
@@ -27,8 +29,10 @@ OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_update_kernel --launch-skip 1 --launc
     python scripts/potrf_ws_once.py > gpurun_out/ncu_f1.log 2>&1; echo "ozaki update exit $?"
 OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_split_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_full_ozaki_split \
     python scripts/potrf_ws_once.py > gpurun_out/ncu_f2.log 2>&1; echo "ozaki split exit $?"
+# the step's first ozaki_update launch is the posterior covariance (MODE 2), preceded by the column-wise split of V
 $NCU -k regex:"ozaki_update_kernel|ozaki_split_t_kernel" --launch-count 2 -o gpurun_out/r02_full_ozaki_postcov \
     python scripts/profile_step.py 1 > gpurun_out/ncu_f3.log 2>&1; echo "postcov exit $?"
-$NCU -k regex:"sample_argmax_kernel" --launch-count 1 -o gpurun_out/r02_full_sample_argmax \
+# the sampling tail: ozaki_update_kernel<1> (the only launch whose name ends in <1>)
+$NCU -k regex:"ozaki_update_kernel<1>" --launch-count 1 -o gpurun_out/r02_full_ozaki_sample \
     python scripts/profile_step.py 1 > gpurun_out/ncu_f5.log 2>&1; echo "sample exit $?"
 ls -la gpurun_out/r02_full_*.ncu-rep
