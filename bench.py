@@ -487,6 +487,10 @@ def run_b200(args):
         from ocbo_b200 import dist as odist
         ntr = args.sweep_trials
         mine = {t: make_trial_inputs(t, N_OBS, N_TASK, N_ACT) for t in odist.shard_trials(ntr, rank, world)}
+        # warm-up of the gather itself (same collective, same buffer shape, no trials): the first NCCL gather of a
+        # process sets up its send / receive channels -- 1.2-1.4 s at 8 ranks, more than the 512 trials take
+        odist.gather_picks([], np.zeros((0, N_DRAW), np.int32), np.zeros((0, N_DRAW), np.int32),
+                           np.zeros((0, N_DRAW)), ntr)
         barrier()
         t0 = time.perf_counter()
         res = odist.run_sweep(ntr, None, mine.__getitem__, groups=groups)
