@@ -94,6 +94,8 @@ int ocbo_potrf(double* A, int n, int lda, int64_t s_a,
  * memory and recombined in fp64 in the epilogue (csrc/ozaki.cu).  Slice pairs below 2^-56 of the row maxima
  * are dropped: the update differs from the fp64 one by <= ~1e-14 |P||P|^T element-wise (fp64's own bound
  * for k = 2048 is 2e-13), so factors agree to rounding level but not bit for bit with ocbo_potrf.
+ * The row scales are fixed before the factorisation from its diagonal (|L_ik| <= sqrt(A_ii)), so every element of
+ * the factor is split once and the slices stay in the workspace (ocbo_sample_tile_argmax_ws can reuse them).
  * The library never allocates: ocbo_potrf_ws_bytes returns 0 when the shape would not use the workspace. */
 int64_t ocbo_potrf_ws_bytes(int n, int batch);
 int ocbo_potrf_ws(double* A, int n, int lda, int64_t s_a,
@@ -270,12 +272,14 @@ int ocbo_sample_tile_argmax(const double* mean, int64_t s_mean,
 /* ocbo_sample_tile_argmax with a device workspace (256-byte aligned, ocbo_sample_ws_bytes(m, S, batch) bytes; NULL,
  * too small or a small shape: same as ocbo_sample_tile_argmax).  With it L (lower triangular: only the blocks up to
  * the diagonal) and Z^T are split into int8 slices and mean + L Z runs on the int8 tensor cores (see ocbo_potrf_ws);
- * max / first arg-max per (128-row tile, column) come out of the tensor-memory epilogue, same np.argmax rule. */
+ * max / first arg-max per (128-row tile, column) come out of the tensor-memory epilogue, same np.argmax rule.
+ * l_in_ws != 0: L was factored by ocbo_potrf_ws with THIS workspace and nothing has written to it since -- its
+ * slices (and row scales) are still at the head of the workspace and are not computed again. */
 int64_t ocbo_sample_ws_bytes(int m, int S, int batch);
 int ocbo_sample_tile_argmax_ws(const double* mean, int64_t s_mean, const double* L, int m, int ldl,
                                int64_t s_l, const double* Z, int S, int ldz, int64_t s_z,
                                double* tile_max, int32_t* tile_arg, const int32_t* info, int batch,
-                               void* ws, int64_t ws_bytes, ocbo_stream_t stream);
+                               void* ws, int64_t ws_bytes, int l_in_ws, ocbo_stream_t stream);
 
 /* Segmented max / first-index argmax per sample column:
  * seg_ptr[b][0..nseg] row offsets; out_max/out_arg are [batch][nseg][S]

@@ -48,7 +48,7 @@ _PROTOS = {
     'ocbo_sample': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _I, _L, _VP, _I, _VP]),
     'ocbo_sample_tile_argmax': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _VP, _VP, _I, _VP]),
     'ocbo_sample_ws_bytes': (_L, [_I, _I, _I]),
-    'ocbo_sample_tile_argmax_ws': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _VP, _VP, _I, _VP, _L, _VP]),
+    'ocbo_sample_tile_argmax_ws': (_I, [_VP, _L, _VP, _I, _I, _L, _VP, _I, _I, _L, _VP, _VP, _VP, _I, _VP, _L, _I, _VP]),
     'ocbo_segment_argmax': (_I, [_VP, _I, _I, _L, _VP, _I, _VP, _VP, _I, _VP]),
     'ocbo_joint_pick': (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP]),
     'ocbo_kg': (_I, [_VP, _I, _VP, _L, _VP, ctypes.c_double, _I, _I, _I, _VP, _VP]),

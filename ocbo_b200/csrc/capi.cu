@@ -169,6 +169,18 @@ static bool ozaki_wanted(int kw, int R) {
   return kw >= mink && R >= 8;
 }
 
+// OCBO_OZAKI_GLOBAL (default 1): ONE split of the factor, with row scales fixed from the diagonal before the
+// factorisation (|L_ik| <= sqrt(A_ii)), shared by the middle updates, the trailing updates and -- through
+// ocbo_sample_tile_argmax_ws(l_in_ws) -- the sampling tail.  0: every update splits its own panel (row maxima).
+static bool ozaki_global_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCBO_OZAKI_GLOBAL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
                      int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr,
                      void* ws = nullptr, size_t ws_bytes = 0) {
@@ -203,6 +215,21 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
   const int NBM = (mid > 0 && mid < NBO) ? mid : NBO;
   Lookahead* la = (!tm && nt > 2 * NBO && lookahead_enabled(batch)) ? lookahead_for(st) : nullptr;
   bool side_busy = false;  // a (b) update is in flight on the helper stream
+  // factor-wide slice workspace (see ozaki_global_enabled)
+  const bool glob = ws && !nv && nt > NBO && ozaki_global_enabled() && ozaki_wanted(NBO * TILE, nt - NBO) &&
+                    ozaki_ws_bytes(n, n, batch) <= ws_bytes;
+  if (glob) {
+    CK(launch_ozaki_diag_scale(A, lda, s_a, n, ws, info, batch, st), "potrf ozaki row scales");
+    if (tm) tm->mark(st, 4);
+  }
+  // split the finished middle panel [m0, m1) (all its rows: the diagonal region too, the sampling tail reads it)
+  auto split_mid = [&](int m0, int m1) -> int {
+    CK(launch_ozaki_split_fixed(A + (size_t)m0 * TILE * lda + (size_t)m0 * TILE, lda, s_a, (nt - m0) * TILE,
+                                (m1 - m0) * TILE, m0 * TILE, m0 * (TILE / 32), n, ws, info, batch, st),
+       "potrf ozaki split (factor-wide)");
+    if (tm) tm->mark(st, 4);
+    return 0;
+  };
   for (int J0 = 0; J0 < nt; J0 += NBO) {
     const int J1 = (J0 + NBO < nt) ? J0 + NBO : nt;
     for (int j = J0; j < J1; ++j) {
@@ -224,7 +251,13 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
          "potrf_diag");
       if (tm) tm->mark(st, 0);
       const int r = nt - 1 - j;
-      if (r == 0) break;
+      if (r == 0) {
+        if (glob) {
+          int rc = split_mid(M0, nt);
+          if (rc) return rc;
+        }
+        break;
+      }
       double* panel = A + (size_t)(j + 1) * TILE * lda + (size_t)j * TILE;
       NtParams p{};
       // panel solve: X <- X inv(L_jj)^T, in place (each CTA owns its 128 rows)
@@ -255,6 +288,10 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         CK(cudaStreamWaitEvent(st, la->join, 0), "potrf lookahead join");
         side_busy = false;
       }
+      if (glob && j + 1 == M1 && !(left && NBM < NBO && M1 < J1 && ozaki_wanted((M1 - M0) * TILE, nt - M1))) {
+        int rc = split_mid(M0, M1);
+        if (rc) return rc;
+      }
       if (left && NBM < NBO && j + 1 == M1 && M1 < J1) {
         NtParams u{};
         u.P = A + (size_t)M1 * TILE * lda + (size_t)M0 * TILE; u.ldp = lda; u.sP = s_a;
@@ -264,7 +301,14 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.row0 = M1 * TILE; u.col0 = M1 * TILE;
         u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
         const int kwm = (M1 - M0) * TILE, Rm = nt - M1;
-        if (ws && ozaki_wanted(kwm, Rm) && ozaki_ws_bytes(Rm * TILE, kwm, batch) <= ws_bytes) {
+        if (glob && ozaki_wanted(kwm, Rm)) {
+          int rc = split_mid(M0, M1);
+          if (rc) return rc;
+          CK(launch_ozaki_update_range(ws, n, M0 * (TILE / 32), (M1 - M0) * (TILE / 32), M1 * TILE, M1 * TILE, u.C, lda, s_a,
+                                       Rm, u.ntc, 0, 1, M1 * TILE, M1 * TILE, info, batch, st),
+             "potrf middle update, ozaki (factor-wide)");
+          if (tm) tm->mark(st, 6);
+        } else if (!glob && ws && ozaki_wanted(kwm, Rm) && ozaki_ws_bytes(Rm * TILE, kwm, batch) <= ws_bytes) {
           CK(launch_ozaki_split(u.P, lda, s_a, Rm * TILE, kwm, ws, info, batch, st), "potrf middle ozaki split");
           if (tm) tm->mark(st, 4);
           CK(launch_ozaki_update(ws, Rm * TILE, kwm, 0, 0, u.C, lda, s_a, Rm, u.ntc, 0, 1, M1 * TILE, M1 * TILE, info,
@@ -279,7 +323,9 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
     }
     const int R = nt - J1;
     const int kw = (J1 - J0) * TILE;
-    const bool oz = ws && R > 0 && ozaki_wanted(kw, R) && ozaki_ws_bytes(R * TILE, kw, batch) <= ws_bytes;
+    const bool ozg = glob && R > 0 && ozaki_wanted(kw, R);
+    const bool oz = !glob && ws && R > 0 && ozaki_wanted(kw, R) && ozaki_ws_bytes(R * TILE, kw, batch) <= ws_bytes;
+    const int kb0 = J0 * (TILE / 32), nkb = (J1 - J0) * (TILE / 32);
     if (oz) {
       // (the helper stream's update of the previous panel read the workspace: it was joined at the end of this
       // panel's first middle panel, or is joined here)
@@ -307,7 +353,11 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.C = A + (size_t)J2 * TILE * lda + (size_t)J2 * TILE; u.ldc = lda; u.sC = s_a;
         u.ntc = Rb * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1;
         u.info = info;
-        if (oz)
+        if (ozg)
+          CK(launch_ozaki_update_range(ws, n, kb0, nkb, J2 * TILE, J2 * TILE, u.C, lda, s_a, Rb, 0, 1, 0, 0, 0, info, batch,
+                                       la->side),
+             "potrf outer update (b), ozaki (factor-wide)");
+        else if (oz)
           CK(launch_ozaki_update(ws, R * TILE, kw, (J2 - J1) * TILE, (J2 - J1) * TILE, u.C, lda, s_a, Rb, 0, 1, 0, 0, 0,
                                  info, batch, la->side),
              "potrf outer update (b), ozaki");
@@ -324,7 +374,11 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       u.ntc = (J2 - J1) * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK);
       u.row0 = J1 * TILE; u.col0 = J1 * TILE;
       u.tri = 0; u.lower_skip = 1; u.mode = 1; u.info = info;
-      if (oz)
+      if (ozg)
+        CK(launch_ozaki_update_range(ws, n, kb0, nkb, J1 * TILE, J1 * TILE, u.C, lda, s_a, R, u.ntc, 0, 1, J1 * TILE,
+                                     J1 * TILE, info, batch, st),
+           "potrf outer update (a), ozaki (factor-wide)");
+      else if (oz)
         CK(launch_ozaki_update(ws, R * TILE, kw, 0, 0, u.C, lda, s_a, R, u.ntc, 0, 1, J1 * TILE, J1 * TILE, info, batch, st),
            "potrf outer update (a), ozaki");
       else
@@ -337,12 +391,15 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       u.C = A + (size_t)J1 * TILE * lda + (size_t)J1 * TILE; u.ldc = lda; u.sC = s_a;
       u.ntc = R * (TILE / TN); u.ktiles = (J1 - J0) * (TILE / BK); u.tri = 1; u.mode = 1;
       u.info = info;
-      if (oz)
+      if (ozg)
+        CK(launch_ozaki_update_range(ws, n, kb0, nkb, J1 * TILE, J1 * TILE, u.C, lda, s_a, R, 0, 1, 0, 0, 0, info, batch, st),
+           "potrf outer update, ozaki (factor-wide)");
+      else if (oz)
         CK(launch_ozaki_update(ws, R * TILE, kw, 0, 0, u.C, lda, s_a, R, 0, 1, 0, 0, 0, info, batch, st),
            "potrf outer update, ozaki");
       else
         CK(launch_gemm_nt(u, R * (R + 1), batch, st), "potrf outer update");  // 2:1 lower tiles
-      if (tm) tm->mark(st, oz ? 5 : 3);
+      if (tm) tm->mark(st, (oz || ozg) ? 5 : 3);
     }
   }
   if (side_busy) CK(cudaStreamWaitEvent(st, la->join, 0), "potrf lookahead final join");
@@ -364,6 +421,7 @@ int64_t ocbo_potrf_ws_bytes(int n, int batch) {
   if (!tile_ok(n) || batch <= 0) return 0;
   const int nt = n / TILE, NBO = potrf_outer_tiles(nt, true);
   if (nt <= NBO || !ozaki_wanted(NBO * TILE, nt - NBO)) return 0;
+  if (ozaki_global_enabled()) return (int64_t)ozaki_ws_bytes(n, n, batch);  // the whole factor's slices
   return (int64_t)ozaki_ws_bytes((nt - NBO) * TILE, NBO * TILE, batch);
 }
 
@@ -822,7 +880,7 @@ int64_t ocbo_sample_ws_bytes(int m, int S, int batch) {
 int ocbo_sample_tile_argmax_ws(const double* mean, int64_t s_mean, const double* L, int m, int ldl,
                                int64_t s_l, const double* Z, int S, int ldz, int64_t s_z,
                                double* tile_max, int32_t* tile_arg, const int32_t* info, int batch,
-                               void* ws, int64_t ws_bytes, ocbo_stream_t stream) {
+                               void* ws, int64_t ws_bytes, int l_in_ws, ocbo_stream_t stream) {
   if (!ws || !tile_ok(m) || S <= 0 || batch <= 0 || !sample_ozaki_wanted(m, S) || (ldl & 3) || (s_l & 3) ||
       ((uintptr_t)L & 31) || ws_bytes < (int64_t)ozaki_sample_ws_bytes(m, S, batch))
     return ocbo_sample_tile_argmax(mean, s_mean, L, m, ldl, s_l, Z, S, ldz, s_z, tile_max, tile_arg, info, batch,
@@ -834,8 +892,10 @@ int ocbo_sample_tile_argmax_ws(const double* mean, int64_t s_mean, const double*
   if (!Z) return fail_arg(7, "Z null");
   if (ldz < S || (ldz & 1)) return fail_arg(9, "ldz must be even and >= S");
   if (!tile_max || !tile_arg) return fail_arg(11, "outputs null");
+  // l_in_ws: only meaningful when ocbo_potrf_ws would have left the factor's slices there (same switches)
+  const bool reuse = l_in_ws && ozaki_global_enabled() && ocbo_potrf_ws_bytes(m, batch) == (int64_t)ozaki_ws_bytes(m, m, batch);
   CK(launch_ozaki_sample(mean, s_mean, L, m, ldl, s_l, Z, S, ldz, s_z, tile_max, tile_arg, info, batch, ws,
-                         (cudaStream_t)stream),
+                         (cudaStream_t)stream, reuse ? 1 : 0),
      "ocbo_sample_tile_argmax_ws");
   return 0;
 }

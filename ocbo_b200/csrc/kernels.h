@@ -127,7 +127,15 @@ cudaError_t launch_ozaki_split(const double* P, int ldp, int64_t sP, int rows, i
 size_t ozaki_sample_ws_bytes(int m, int S, int batch);
 cudaError_t launch_ozaki_sample(const double* mean, int64_t sMean, const double* L, int m, int ldl, int64_t sL,
                                 const double* Z, int S, int ldz, int64_t sZ, double* tile_max, int32_t* tile_arg,
-                                const int32_t* info, int batch, void* ws, cudaStream_t st);
+                                const int32_t* info, int batch, void* ws, cudaStream_t st, int l_in_ws = 0);
+// factor-wide workspace (row scales fixed from the diagonal before the factorisation; every element of L split once)
+cudaError_t launch_ozaki_diag_scale(const double* A, int lda, int64_t sA, int n, void* ws, const int32_t* info, int batch,
+                                    cudaStream_t st);
+cudaError_t launch_ozaki_split_fixed(const double* P, int ldp, int64_t sP, int rows, int kw, int row0, int kb0, int n,
+                                     void* ws, const int32_t* info, int batch, cudaStream_t st);
+cudaError_t launch_ozaki_update_range(const void* ws, int n, int kb0, int nkb, int rowA0, int rowB0, double* C, int ldc,
+                                      int64_t sC, int R, int ntc, int tri, int lower_skip, int row0, int col0,
+                                      const int32_t* info, int batch, cudaStream_t st);
 struct OzGram {  // C = K(X, X) - P Q^T: points [rows][dim] per problem, kernel kind, theta
   const double* X; int64_t sX; int dim, kind; const double* theta; int64_t sTheta;
 };

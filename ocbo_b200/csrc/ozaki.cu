@@ -133,6 +133,7 @@ struct OzParams {
   int rowA0, rowB0;      // slice rows of the region's first row (multiple of 128) / first column (of 64)
   int R, ntc, ntiles;    // tri: row tiles of the square region; rect: column tiles (64 wide); tiles per problem
   int ktiles;            // k / 32
+  int kb0;               // first k block of the product inside the workspace (0: the whole k range)
   int tri, lower_skip, row0, col0;
   const int32_t* info;
   int total;             // ntiles * batch
@@ -218,8 +219,8 @@ ozaki_update_kernel(OzParams p) {
       // block (k block kt, row block rb) of the workspace = [slice][128 rows][32 bytes], already swizzled: the A tile
       // is ONE contiguous 28 KiB copy, the B tile 7 copies of 2 KiB (64 of the 128 rows of every slice)
       const int rbA = p.rowA0 / OZ_BM + ti, rB = p.rowB0 + tj * OZ_BN;
-      const int8_t* srcA = p.S + ((size_t)b * p.KB * p.RB + rbA) * OZ_A_STAGE;
-      const int8_t* srcB = p.SB + ((size_t)b * p.KB * p.RBb + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
+      const int8_t* srcA = p.S + (((size_t)b * p.KB + p.kb0) * p.RB + rbA) * OZ_A_STAGE;
+      const int8_t* srcB = p.SB + (((size_t)b * p.KB + p.kb0) * p.RBb + rB / OZ_BM) * OZ_A_STAGE + (size_t)(rB % OZ_BM) * OZ_BK;
       const size_t kstep = (size_t)p.RB * OZ_A_STAGE, kstepB = (size_t)p.RBb * OZ_A_STAGE;
       for (int kt = 0; kt < ktiles; ++kt, ++it) {
         const int s = it % OZ_STAGES;
@@ -519,6 +520,78 @@ ozaki_split_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, 
   }
 }
 
+// ---- one workspace for a whole Cholesky factor (ocbo_potrf_ws, "global" mode) --------------------------------------
+// Row scales fixed BEFORE the factorisation from its diagonal: |L_ik| <= sqrt(A_ii) for every k, so
+// E_i = exponent of sqrt(A_ii) bounds the whole row i of L.  With one scale per row for all panels the slices of
+// different panels are compatible: every element of L is split ONCE, and the middle updates, the trailing updates
+// and the sampling tail (mean + L Z, k = m) all read the same images.  The absolute truncation, 2^-57 2^E_i per
+// element, is that of rounding A's own entries to fp64; a row whose elements exceed the bound (A not positive
+// definite: pivot i is about to fail) gets a NaN scale, which poisons row / column i of the trailing matrix only --
+// LAPACK's info (first failing pivot) is unchanged.
+__global__ void __launch_bounds__(256)
+ozaki_diag_scale_kernel(const double* __restrict__ A, int lda, int64_t sA, int n, double* __restrict__ scale,
+                        const int32_t* __restrict__ info) {
+  const int b = blockIdx.y;
+  if (info && info[b] != 0) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double d = A[(size_t)b * sA + (size_t)i * lda + i];
+  double inv, sc;
+  // (a hair above sqrt(A_ii): the computed L_ik may exceed the exact bound by rounding)
+  oz_exponent(sqrt(d) * 1.0000001, !(d > 0.0) || !(d <= 1.7976931348623157e308), inv, sc);
+  scale[(size_t)b * n + i] = sc;
+}
+
+// Split of the block columns [kb0 * 32, kb0 * 32 + kw) of L, rows row0 .. row0 + rows - 1 (P points at that
+// corner), with the given row scales, into the factor-wide layout S[problem][KB][RB][slice][128][32]; a row's
+// k range ends at its diagonal block (tri).  Same lane mapping as ozaki_split_kernel.
+__global__ void __launch_bounds__(256)
+ozaki_split_fixed_kernel(const double* __restrict__ P, int ldp, int64_t sP, int rows, int kw_full, int row0, int kb0,
+                         int n, int8_t* __restrict__ S, double* __restrict__ scale, const int32_t* __restrict__ info) {
+  const int b = blockIdx.y;
+  if (info && info[b] != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lrow = blockIdx.x * 8 + warp;
+  if (lrow >= rows) return;
+  const int row = row0 + lrow;
+  const int KB = n / OZ_BK, RB = n / OZ_BM;
+  const int kw = min(kw_full, (row / OZ_BM + 1) * OZ_BM - kb0 * OZ_BK);
+  const double* src = P + (size_t)b * sP + (size_t)lrow * ldp + lane * 4;
+  const double sc = scale[(size_t)b * n + row];
+  const double inv = 281474976710656.0 / sc;  // 2^48 / 2^(E - 8) = 2^(56 - E), exact (NaN scale: NaN)
+  const int kbl = lane >> 3, c = (lane >> 2) & 1, wq = lane & 3;
+  int8_t* dst = S + ((size_t)b * KB + kb0) * RB * OZ_A_STAGE + (size_t)(row / OZ_BM) * OZ_A_STAGE +
+                (size_t)(row % OZ_BM) * OZ_BK + ((c ^ ((row >> 2) & 1)) << 4) + (wq << 2) + (size_t)kbl * RB * OZ_A_STAGE;
+  bool over = false;
+  for (int k0 = 0; k0 + lane * 4 < kw; k0 += 256) {
+    double v[2][4];
+    const bool two = k0 + 128 + lane * 4 < kw;
+    oz_ld4(src + k0, v[0]);
+    if (two) oz_ld4(src + k0 + 128, v[1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      uint32_t wd[OZ_S];
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) wd[t] = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t dg[OZ_S];
+        const double y = v[h][j] * inv;
+        over |= !(fabs(y) <= 35886843558709250.0);  // 0.49803 * 2^56 (the digits reach 127/255): out of range, or NaN
+        oz_digits(y, dg);
+#pragma unroll
+        for (int t = 0; t < OZ_S; ++t) wd[t] |= dg[t] << (8 * j);
+      }
+      int8_t* d = dst + (size_t)((k0 + h * 128) / OZ_BK) * RB * OZ_A_STAGE;
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(d + (size_t)t * OZ_A_SLICE) = wd[t];
+    }
+  }
+  over = __any_sync(0xffffffffu, over);
+  if (over && lane == 0) scale[(size_t)b * n + row] = CUDART_NAN;
+}
+
 // The same split for an operand stored k-major the other way round (V: k rows x operand rows, row-major, as the
 // posterior covariance's V^T V needs it): CTA = 32 operand rows (lane = row, loads of one k are 256 contiguous
 // bytes), warp w handles the k blocks w, w + 8, ...; a thread converts 32 k values of its row and writes the
@@ -679,6 +752,49 @@ cudaError_t launch_ozaki_update(const void* ws, int rows, int kw, int rowA0, int
 }
 int ozaki_gram_max_dim() { return OZ_GRAM_D; }
 
+// ---- factor-wide workspace (see ozaki_diag_scale_kernel): layout of ozaki_ws_bytes(n, n, batch) ------------------
+cudaError_t launch_ozaki_diag_scale(const double* A, int lda, int64_t sA, int n, void* ws, const int32_t* info, int batch,
+                                    cudaStream_t st) {
+  double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + oz_slices_bytes(n, n, batch));
+  ozaki_diag_scale_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, n, scale, info);
+  return counted(cudaGetLastError());
+}
+
+// P = &L[row0][kb0 * 32]: rows x kw block of the factor (whole block columns, row0 and kw multiples of 128)
+cudaError_t launch_ozaki_split_fixed(const double* P, int ldp, int64_t sP, int rows, int kw, int row0, int kb0, int n,
+                                     void* ws, const int32_t* info, int batch, cudaStream_t st) {
+  if (rows <= 0 || kw <= 0 || batch <= 0) return cudaSuccess;
+  if ((kw & 127) || (rows & 127) || (row0 & 127) || (n & 127) || (ldp & 3) || (sP & 3) || ((uintptr_t)P & 31) ||
+      ((uintptr_t)ws & 255))
+    return cudaErrorInvalidValue;
+  int8_t* S = reinterpret_cast<int8_t*>(ws);
+  double* scale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) + oz_slices_bytes(n, n, batch));
+  ozaki_split_fixed_kernel<<<dim3(rows / 8, batch), 256, 0, st>>>(P, ldp, sP, rows, kw, row0, kb0, n, S, scale, info);
+  return counted(cudaGetLastError());
+}
+
+// C (region) -= L[rowA0.., k range] L[rowB0.., k range]^T from the factor-wide workspace; k range = nkb blocks of 32
+// from kb0; rowA0 / rowB0 are rows of the factor.
+cudaError_t launch_ozaki_update_range(const void* ws, int n, int kb0, int nkb, int rowA0, int rowB0, double* C, int ldc,
+                                      int64_t sC, int R, int ntc, int tri, int lower_skip, int row0, int col0,
+                                      const int32_t* info, int batch, cudaStream_t st) {
+  if (R <= 0 || batch <= 0 || nkb <= 0 || (!tri && ntc <= 0)) return cudaSuccess;
+  if ((rowA0 % OZ_BM) || (rowB0 % OZ_BN) || (n % OZ_BM) || nkb * OZ_BK > 16384) return cudaErrorInvalidValue;
+  OzParams p{};
+  p.C = C; p.ldc = ldc; p.sC = sC;
+  p.S = reinterpret_cast<const int8_t*>(ws); p.RB = n / OZ_BM; p.KB = n / OZ_BK;
+  p.SB = p.S; p.RBb = p.RB;
+  p.scaleA = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(ws) + oz_slices_bytes(n, n, batch));
+  p.scaleB = p.scaleA; p.sScale = n; p.sScaleB = n;
+  p.rowA0 = rowA0; p.rowB0 = rowB0;
+  p.R = R; p.ntc = ntc; p.ntiles = tri ? R * (R + 1) : R * ntc;
+  p.ktiles = nkb; p.kb0 = kb0;
+  p.tri = tri; p.lower_skip = lower_skip; p.row0 = row0; p.col0 = col0;
+  p.info = info;
+  p.total = p.ntiles * batch;
+  return oz_launch<0>(p, st);
+}
+
 // Fused sampling tail on the int8 tensor cores: per (row tile of 128, column) max / first arg-max of mean + L Z.
 // ws holds the slices of L (m rows, k = m, lower triangular: ozaki_ws_bytes(m, m, batch)) followed by those of
 // Z^T (S rows, k = m: ozaki_ws_bytes(S, m, batch)).
@@ -686,11 +802,13 @@ size_t ozaki_sample_ws_bytes(int m, int S, int batch) { return ozaki_ws_bytes(m,
 
 cudaError_t launch_ozaki_sample(const double* mean, int64_t sMean, const double* L, int m, int ldl, int64_t sL,
                                 const double* Z, int S, int ldz, int64_t sZ, double* tile_max, int32_t* tile_arg,
-                                const int32_t* info, int batch, void* ws, cudaStream_t st) {
+                                const int32_t* info, int batch, void* ws, cudaStream_t st, int l_in_ws) {
   if ((m % OZ_BM) || (S % OZ_BN) || m > 16384) return cudaErrorInvalidValue;
   uint8_t* wsL = reinterpret_cast<uint8_t*>(ws);
   uint8_t* wsZ = wsL + ozaki_ws_bytes(m, m, batch);
-  cudaError_t e = launch_ozaki_split(L, ldl, sL, m, m, wsL, info, batch, st, 0, 1);
+  cudaError_t e = cudaSuccess;
+  // l_in_ws: ocbo_potrf_ws left the slices of this very factor (and its row scales) at the head of the workspace
+  if (!l_in_ws) e = launch_ozaki_split(L, ldl, sL, m, m, wsL, info, batch, st, 0, 1);
   if (e != cudaSuccess) return e;
   e = launch_ozaki_split(Z, ldz, sZ, S, m, wsZ, info, batch, st, 1, 0);
   if (e != cudaSuccess) return e;

@@ -158,7 +158,7 @@ class SweepStep(object):
                                     engine.LADDER[:self.ladder_rungs], ws=self.ws)
         call('ocbo_philox_normal', _p(self.Z), m, S, S, self.Z.stride(0),
              ctypes.c_uint64(self.seed), _p(self.trial_ids), B, st)
-        self._sample_and_reduce(slice(0, B), st)
+        self._sample_and_reduce(slice(0, B), st, l_in_ws=True)
         call('ocbo_joint_pick', _p(self.seg_max), _p(self.seg_arg), T, 0, T, S, _p(self.task),
              _p(self.action), _p(self.gain), B, st)
         engine._count(self.launches_per_run)
@@ -187,8 +187,10 @@ class SweepStep(object):
             self.stream.synchronize()
         return self._F
 
-    def _sample_and_reduce(self, s, st):
-        """mu + L Z -> per-task max / first arg-max of every draw, for the trial slots ``s``."""
+    def _sample_and_reduce(self, s, st, l_in_ws=False):
+        """mu + L Z -> per-task max / first arg-max of every draw, for the trial slots ``s``.
+        ``l_in_ws``: Sigma was factored by ocbo_potrf_ws with this step's workspace just before (run()): the
+        factor's int8 slices are still there."""
         m, S, T = self.m, self.S, self.T
         nb = s.stop - s.start
         sd = lambda t: 0 if nb == 1 else t.stride(0)
@@ -197,7 +199,8 @@ class SweepStep(object):
             if self.ws is not None and os.environ.get('OCBO_OZAKI_SAMPLE', '1') != '0':
                 # (too small a workspace or shape: the entry point is ocbo_sample_tile_argmax)
                 call('ocbo_sample_tile_argmax_ws', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
-                     sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, _p(self.ws), self.ws.numel(), st)
+                     sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, _p(self.ws), self.ws.numel(),
+                     1 if (l_in_ws and nb == self.B) else 0, st)
             else:
                 call('ocbo_sample_tile_argmax', _p(mean), sd(mean), _p(Sig), m, m, sd(Sig), _p(Z), S, S,
                      sd(Z), _p(self.seg_max[s]), _p(self.seg_arg[s]), _p(info), nb, st)
