@@ -181,6 +181,18 @@ static bool ozaki_global_enabled() {
   return v != 0;
 }
 
+// OCBO_OZAKI_INPANEL (needs the factor-wide image): shortest k of a left-looking in-panel update that runs on the
+// int8 tensor cores too; the block columns are then split one by one as they are finished.  0 = never; default
+// 128 = all of them (measured in one box: 65.4 k -> 67.4 k samples/s in flight, one trial alone 8.68 -> 8.41 ms).
+static int ozaki_inpanel_mink() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCBO_OZAKI_INPANEL");
+    v = e ? atoi(e) : 128;
+  }
+  return v;
+}
+
 static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, int32_t* info,
                      int batch, cudaStream_t st, PotrfTimer* tm, const int32_t* nv = nullptr,
                      void* ws = nullptr, size_t ws_bytes = 0) {
@@ -222,8 +234,12 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
     CK(launch_ozaki_diag_scale(A, lda, s_a, n, ws, info, batch, st), "potrf ozaki row scales");
     if (tm) tm->mark(st, 4);
   }
+  // in-panel updates on the int8 path: block columns are split as they are finished, not whole middle panels
+  const int inp_mink = ozaki_inpanel_mink();
+  const bool percol = glob && left && inp_mink > 0;
   // split the finished middle panel [m0, m1) (all its rows: the diagonal region too, the sampling tail reads it)
   auto split_mid = [&](int m0, int m1) -> int {
+    if (percol) return 0;  // done column by column
     CK(launch_ozaki_split_fixed(A + (size_t)m0 * TILE * lda + (size_t)m0 * TILE, lda, s_a, (nt - m0) * TILE,
                                 (m1 - m0) * TILE, m0 * TILE, m0 * (TILE / 32), n, ws, info, batch, st),
        "potrf ozaki split (factor-wide)");
@@ -244,15 +260,32 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
         u.C = A + (size_t)j * TILE * lda + (size_t)j * TILE; u.ldc = lda; u.sC = s_a;
         u.ntc = TILE / TN; u.ktiles = (j - M0) * (TILE / BK);
         u.tri = 0; u.lower_skip = 0; u.mode = 1; u.info = info;
-        CK(launch_gemm_nt(u, (nt - j) * u.ntc, batch, st), "potrf panel update");
-        if (tm) tm->mark(st, 2);
+        if (percol && (j - M0) * TILE >= inp_mink && nt - j >= 8) {
+          CK(launch_ozaki_update_range(ws, n, M0 * (TILE / 32), (j - M0) * (TILE / 32), j * TILE, j * TILE, u.C, lda, s_a,
+                                       nt - j, u.ntc, 0, 0, 0, 0, info, batch, st),
+             "potrf panel update, ozaki");
+          if (tm) tm->mark(st, 6);
+        } else {
+          CK(launch_gemm_nt(u, (nt - j) * u.ntc, batch, st), "potrf panel update");
+          if (tm) tm->mark(st, 2);
+        }
       }
       CK(launch_potrf_diag(A, lda, s_a, j * TILE, invdiag, sInv, info, batch, st, nv),
          "potrf_diag");
       if (tm) tm->mark(st, 0);
       const int r = nt - 1 - j;
+      auto split_col = [&]() -> int {  // block column j, rows from its diagonal block down
+        CK(launch_ozaki_split_fixed(A + (size_t)j * TILE * lda + (size_t)j * TILE, lda, s_a, (nt - j) * TILE, TILE,
+                                    j * TILE, j * (TILE / 32), n, ws, info, batch, st),
+           "potrf ozaki split (block column)");
+        if (tm) tm->mark(st, 4);
+        return 0;
+      };
       if (r == 0) {
-        if (glob) {
+        if (percol) {
+          int rc = split_col();
+          if (rc) return rc;
+        } else if (glob) {
           int rc = split_mid(M0, nt);
           if (rc) return rc;
         }
@@ -267,6 +300,10 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
       p.ntc = 1; p.ktiles = TILE / BK; p.mode = 0; p.info = info;
       CK(launch_gemm_nt(p, 2 * r, batch, st, 1), "potrf panel");  // 64-row tiles, full rows
       if (tm) tm->mark(st, 1);
+      if (percol) {
+        int rc = split_col();
+        if (rc) return rc;
+      }
       // inner update: the remaining columns of this outer panel, all rows below
       const int ncols = J1 - 1 - j;
       if (!left && ncols > 0) {
