@@ -24,8 +24,10 @@ upd = upd[len(upd) // 2:]   # second run of the script
 dram = sum(l['dram__bytes_read.sum'] + l['dram__bytes_write.sum'] for l in upd)
 ns = sum(l['gpu__time_duration.sum'] for l in upd)
 
-# algorithmic bytes of the same launches (m = 8192, n = 1024, outer 1024, middle 512; 7 slices of 1 byte per element)
-M, N, OUT, MID, T = 8192, 1024, 1024, 512, 128
+# algorithmic bytes of the same launches (m = 8192, n = 1024, outer 1024, middle 512, in-panel updates on int8 too;
+# 7 slices of 1 byte per element): every C tile read and written once (the sampling tail writes nothing), the int8
+# slice images of the operand rows read once per launch, the row scales
+M, N, S, OUT, MID, T = 8192, 1024, 256, 1024, 512, 128
 tile = 128 * 64 * 8.0
 
 
@@ -33,21 +35,26 @@ def tri_tiles(r):        # lower 128 x 64 tiles of a square region of r row tile
     return r * (r + 1)
 
 
-alg = tri_tiles(M // T) * tile * 2 + M * N * 7.0 + M * 8.0            # posterior covariance: C (Gram) r+w, V slices
+alg = tri_tiles(M // T) * tile + M * N * 7.0 + M * 8.0                # posterior covariance: C written, V slices
 nt = M // T
 for J0 in range(0, nt, OUT // T):
     J1 = min(J0 + OUT // T, nt)
-    for M0 in range(J0, J1, MID // T):                                # middle updates inside the outer panel
+    for M0 in range(J0, J1, MID // T):
         M1 = min(M0 + MID // T, J1)
-        if M1 < J1 and nt - M1 >= 8:
+        for j in range(M0 + 1, M1):                                    # left-looking in-panel updates of block column j
+            if nt - j >= 8:
+                rws = nt - j
+                alg += rws * 2 * tile * 2 + rws * T * (j - M0) * T * 7.0 + rws * T * 8.0
+        if M1 < J1 and nt - M1 >= 8:                                    # middle update inside the outer panel
             rws, cols = nt - M1, J1 - M1
             tiles = sum(min(2 * cols, 2 * i + 2) for i in range(rws))  # lower_skip rectangle
             alg += tiles * tile * 2 + rws * T * (M1 - M0) * T * 7.0 + rws * T * 8.0
     R = nt - J1
-    if R >= 8:
+    if R >= 8:                                                         # trailing update
         alg += tri_tiles(R) * tile * 2 + R * T * (J1 - J0) * T * 7.0 + R * T * 8.0
-out = {'kernel': 'ozaki_update_kernel (tcgen05.mma kind::i8): V^T V of the posterior covariance + rank-1024 trailing and '
-                 'rank-512 middle updates of chol(Sigma)',
+alg += (M * (M + T) / 2.0) * 7.0 + S * M * 7.0 + (M + S) * 8.0         # sampling tail: L (lower blocks) and Z^T slices
+out = {'kernel': 'ozaki_update_kernel (tcgen05.mma kind::i8), all three modes: posterior covariance, in-panel / middle / '
+                 'trailing updates of chol(Sigma), fused sampling tail',
        'launches': len(upd), 'dram_bytes': dram, 'algorithmic_bytes': alg, 'ncu_ms': ns / 1e6,
        'dram_bytes_per_launch': dram / max(len(upd), 1), 'algorithmic_bytes_per_launch': alg / max(len(upd), 1),
        'scope': 'all %d launches of the kernel in ONE trial-step (m=8192, n=1024, batch 1: the look-ahead splits each '
