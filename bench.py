@@ -591,7 +591,7 @@ def run_b200(args):
         ms_cov = timed(postcov)
         grp.run()                       # leaves a valid factor in Sigma for the sampling product
         torch.cuda.synchronize()
-        ms_lz = timed(lambda: grp._sample_and_reduce(slice(0, B), st))
+        ms_lz = timed(lambda: grp._sample_and_reduce(slice(0, B), st, l_in_ws=True))  # as in run(): L's slices are in ws
         tf = lambda flops, ms: flops * B / (ms * 1e-3) / 1e12
         frac = lambda v: (v / peak) if (peak and v) else None
         cov_tf, lz_tf = tf(float(N_OBS) * m * m, ms_cov), tf(float(m) * m * N_DRAW, ms_lz)

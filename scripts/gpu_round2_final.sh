@@ -33,6 +33,6 @@ OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_split_fixed_kernel --launch-skip 1 --
 $NCU -k regex:"ozaki_update_kernel|ozaki_split_t_kernel" --launch-count 2 -o gpurun_out/r02_full_ozaki_postcov \
     python scripts/profile_step.py 1 > gpurun_out/ncu_f3.log 2>&1; echo "postcov exit $?"
 # the sampling tail: ozaki_update_kernel<1> (the only launch whose name ends in <1>)
-$NCU -k regex:"ozaki_update_kernel<1>" --launch-count 1 -o gpurun_out/r02_full_ozaki_sample \
+$NCU --kernel-name-base mangled -k regex:ozaki_update_kernelILi1E --launch-count 1 -o gpurun_out/r02_full_ozaki_sample \
     python scripts/profile_step.py 1 > gpurun_out/ncu_f5.log 2>&1; echo "sample exit $?"
 ls -la gpurun_out/r02_full_*.ncu-rep

@@ -58,7 +58,7 @@ def main():
              _p(grp.info[0]), B, st_of(grp))
 
     def sample(grp):
-        grp._sample_and_reduce(slice(0, B), st_of(grp))
+        grp._sample_and_reduce(slice(0, B), st_of(grp), l_in_ws=True)
 
     def whole(grp):
         grp.run()
