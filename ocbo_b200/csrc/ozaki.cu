@@ -359,13 +359,20 @@ ozaki_update_kernel(OzParams p) {
           for (int i = 0; i < 16; ++i) {
             const int r = q * 32 + i * 2 + rr;
             double dot = 0.0;
+#ifndef OCBO_OZ_NODOT   // diagnostic variant: what do the shared-memory reads of the row points cost?
 #pragma unroll
             for (int d = 0; d < OZ_GRAM_D; ++d)
               if (d < D) dot = fma(xa[d * OZ_BM + r], xc[d], dot);
+#endif
             kv[i] = dist2_np(na[r], ncol, dot);
           }
+#ifdef OCBO_OZ_NOEXP  // diagnostic variant (tests/tools/oz_gram_variants.py): what does the exp chain cost?
+#pragma unroll
+          for (int i = 0; i < 16; ++i) kv[i] = kscale - 0.5 * kv[i];
+#else
 #pragma unroll
           for (int i = 0; i < 16; ++i) kv[i] = kern_eval(p.kind, kscale, kv[i]);
+#endif
 #pragma unroll
           for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, kv[i]);
           __syncwarp();
