@@ -57,3 +57,47 @@ def test_engine_fails_loudly_without_cuda():
     from ocbo_b200.gp.gp_interface import make_gp
     with pytest.raises(RuntimeError):
         make_gp([[0.1, 0.2]], [1.0], 'se', 1.0, [0.3, 0.3], 0.01, 0.0)
+
+
+def test_workspace_sizes_need_no_gpu():
+    """The workspace queries of the int8-tensor-core entry points are pure host arithmetic: 0 for shapes that would
+    not use the path, 7 bytes per element of the factor (+ row scales) for the sweep's chol(Sigma), and the sampling
+    tail's workspace holds the factor's slices first (so ocbo_potrf_ws can leave them there)."""
+    from ocbo_b200 import _lib
+    L = _lib.LIB
+    assert L.ocbo_potrf_ws_bytes(1024, 2) == 0 and L.ocbo_post_cov_ws_bytes(1024, 256, 1) == 0
+    assert L.ocbo_sample_ws_bytes(512, 64, 1) == 0
+    m, B = 8192, 2
+    potrf, cov, smp = L.ocbo_potrf_ws_bytes(m, B), L.ocbo_post_cov_ws_bytes(m, 1024, B), L.ocbo_sample_ws_bytes(m, 256, B)
+    assert potrf >= 7 * m * m * B and potrf <= 7 * m * m * B + 2 * (8 * m * B + 512)
+    assert cov >= 7 * m * 1024 * B and smp >= potrf + 7 * 256 * m * B
+    assert L.ocbo_ozaki_slice_pairs() == 28
+
+
+def test_int8_kernel_is_compiled_to_tcgen05():
+    """SASS evidence in the shipped library (cuobjdump; skipped where the CUDA toolkit is absent): the update kernel
+    issues UTCIMMA (tcgen05.mma kind::i8), reads tensor memory with LDTM and is fed by UBLKCP bulk copies; the fp64
+    tile core still carries DMMA and UTMALDG."""
+    import shutil
+    import subprocess
+    import pytest
+    from ocbo_b200 import _lib
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([tool, '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    body, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            name = m.group(1)
+            body[name] = []
+        elif name:
+            body[name].append(line)
+    upd = [n for n in body if 'ozaki_update_kernel' in n]
+    assert len(upd) == 3                                   # the three modes
+    for n in upd:
+        text = '\n'.join(body[n])
+        assert 'UTCIMMA' in text and 'LDTM' in text and 'UBLKCP' in text, n
+    whole = '\n'.join('\n'.join(v) for v in body.values())
+    assert 'DMMA.8x8x4' in whole and 'UTMALDG' in whole
