@@ -564,7 +564,7 @@ def run_b200(args):
         all_updates_tflops = alg / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else None
         # the rank-`outer` trailing updates (one per outer panel): algorithmic flops = lower triangle incl. the
         # diagonal of the trailing block, 2 k each
-        outer = int(os.environ.get('OCBO_POTRF_OUTER', 1024 if oz else 2048))
+        outer = int(os.environ.get('OCBO_POTRF_OUTER', 2048))
         ot = max(outer // 128, 1)
         alg_outer = 0.0
         for j1 in range(ot, nt, ot):

@@ -142,9 +142,7 @@ static bool lookahead_enabled(int batch) {
   return v == 2 ? batch == 1 : v == 1;
 }
 
-// outer panel width in tiles: OCBO_POTRF_OUTER, else 2048 columns for fp64 (DMMA) trailing updates and 1024 when
-// they run on the int8 tensor cores (they are ~2.5x faster there, so more of the flops should be theirs:
-// measured 41.3 k against 39.3 k samples/s)
+// outer panel width in tiles: OCBO_POTRF_OUTER, else 2048 columns; 1024 for factors below m = 6144 on the int8 path
 static int potrf_outer_tiles(int nt, bool ozaki = false) {
   static int outer = -1;
   if (outer < 0) {
@@ -152,7 +150,9 @@ static int potrf_outer_tiles(int nt, bool ozaki = false) {
     int v = e ? atoi(e) : 0;
     outer = v < TILE ? 0 : v / TILE;
   }
-  const int o = outer ? outer : (ozaki ? 1024 / TILE : 2048 / TILE);
+  // (int8 path: 2048 again from m = 6144 on, now that the in-panel updates are int8 products too -- measured
+  // 68.7 k against 66.8 k samples/s at m = 8192; smaller factors keep 1024 so that they have a trailing update at all)
+  const int o = outer ? outer : ((ozaki && nt < 48) ? 1024 / TILE : 2048 / TILE);
   return o < nt ? o : nt;
 }
 
@@ -217,13 +217,13 @@ static int potrf_run(double* A, int n, int lda, int64_t s_a, double* invdiag, in
   // -- larger grids of medium k instead of long-k launches of few CTAs.  Measured (sweep shape):
   // one trial alone 17.0 -> 15.5 ms (14.8 with MID = 512), 2 streams x 2 trials +2 %, neutral
   // at the bench's 16 trials in flight, where the other streams fill the SMs anyway.
-  // (with a workspace the default is 512: the rank-512 middle updates run on the int8 tensor cores too)
+  // (with a workspace and 1024-wide outer panels the default is 512: the middle updates are int8 products too)
   static int mid_env = -2;
   if (mid_env == -2) {
     const char* e = getenv("OCBO_POTRF_MID");
     mid_env = e ? atoi(e) / TILE : -1;
   }
-  const int mid = mid_env >= 0 ? mid_env : (ws ? 512 : 1024) / TILE;
+  const int mid = mid_env >= 0 ? mid_env : ((ws && NBO * TILE < 2048) ? 512 : 1024) / TILE;
   const int NBM = (mid > 0 && mid < NBO) ? mid : NBO;
   Lookahead* la = (!tm && nt > 2 * NBO && lookahead_enabled(batch)) ? lookahead_for(st) : nullptr;
   bool side_busy = false;  // a (b) update is in flight on the helper stream
