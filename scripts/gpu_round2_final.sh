@@ -23,9 +23,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 echo "ncu traffic exit $?"
 NCU="timeout 600 ncu --set full --clock-control none --import-source on"
 OCBO_POTRF_LOOKAHEAD=0 python scripts/potrf_ws_once.py > gpurun_out/plain_potrf_ws.log 2>&1 || { echo "potrf_ws_once failed"; exit 1; }
-# first trailing update of the m = 8192 factorisation (7168 x 1024, lower tiles): before it come the in-panel updates
-# of block columns 1-3, the rank-512 middle update and the in-panel updates of block columns 5-7 (7 launches)
-OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_update_kernel --launch-skip 7 --launch-count 1 -o gpurun_out/r02_full_ozaki_update \
+# first trailing update of the m = 8192 factorisation (6144 x 2048, lower tiles): before it come the in-panel updates
+# of block columns 1-7, the rank-1024 middle update and the in-panel updates of block columns 9-15 (15 launches)
+OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_update_kernel --launch-skip 15 --launch-count 1 -o gpurun_out/r02_full_ozaki_update \
     python scripts/potrf_ws_once.py > gpurun_out/ncu_f1.log 2>&1; echo "ozaki update exit $?"
 OCBO_POTRF_LOOKAHEAD=0 $NCU -k regex:ozaki_split_fixed_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_full_ozaki_split \
     python scripts/potrf_ws_once.py > gpurun_out/ncu_f2.log 2>&1; echo "ozaki split exit $?"

@@ -24,10 +24,10 @@ upd = upd[len(upd) // 2:]   # second run of the script
 dram = sum(l['dram__bytes_read.sum'] + l['dram__bytes_write.sum'] for l in upd)
 ns = sum(l['gpu__time_duration.sum'] for l in upd)
 
-# algorithmic bytes of the same launches (m = 8192, n = 1024, outer 1024, middle 512, in-panel updates on int8 too;
+# algorithmic bytes of the same launches (m = 8192, n = 1024, outer 2048, middle 1024, in-panel updates on int8 too;
 # 7 slices of 1 byte per element): every C tile read and written once (the sampling tail writes nothing), the int8
 # slice images of the operand rows read once per launch, the row scales
-M, N, S, OUT, MID, T = 8192, 1024, 256, 1024, 512, 128
+M, N, S, OUT, MID, T = 8192, 1024, 256, 2048, 1024, 128
 tile = 128 * 64 * 8.0
 
 
