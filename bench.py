@@ -43,8 +43,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--streams', type=int, default=8, help='concurrent trial groups per GPU')
-    ap.add_argument('--batch', type=int, default=2, help='trials per kernel launch (grid.z)')
+    ap.add_argument('--streams', type=int, default=4, help='concurrent trial groups per GPU')
+    ap.add_argument('--batch', type=int, default=4, help='trials per kernel launch (grid.z)')
     ap.add_argument('--cpu-trials', type=int, default=2, help='trials timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-peaks', action='store_true')
@@ -440,6 +440,17 @@ def run_b200(args):
     launches = int(LIB.ocbo_launch_count()) - launches0
     clocks = sampler.stop()
 
+    # host time to ISSUE one group's launches from a drained device (outside the clocks): x G = the
+    # host's share of a step; well below ms_per_step means the device, not the issuing thread, bounds it
+    issue = []
+    for grp in groups[:4]:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        grp.run()
+        issue.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    host_issue_ms = float(np.median(issue)) * G
+
     # ---- (2) end to end: host buffers in, picks out, every step ----------------
     def run_e2e(first_step, nsteps):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -647,6 +658,10 @@ def run_b200(args):
                                 'pipe at twice the bf16 rate)' % mp['bf16_tflops']) if mp else
                                'cuBLASLt int8 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json absent)',
                 'cublaslt_int8_tops_this_run': int8_lib,
+                # nominal dense 8-bit rate of a B200 (B200_PROFILING.md: 4.5 PFLOP/s fp8, int8 on the same pipe) for
+                # context: the measured bf16 burst figure is itself taken at the power cap, so a kernel that moves
+                # fewer operand bytes per product than the bf16 GEMM of the probe can pass 2 x that figure
+                'frac_of_nominal_4500': (tops / 4500.0) if tops else None,
                 'fp64_equivalent_tflops': trailing_tflops,
                 'fp64_equivalent_over_cublas_dgemm': frac(trailing_tflops),
                 'traffic': load_traffic(B),
@@ -671,7 +686,7 @@ def run_b200(args):
         roof.update({
             'step_tflops_per_gpu': step_per_gpu, 'step_frac_of_peak': frac(step_per_gpu),
             # launches of ONE group (batch trials) serialised on an otherwise idle GPU: short-k / small-grid
-            # classes cannot fill 148 SMs alone -- in the timed region the other 7 streams do;
+            # classes cannot fill 148 SMs alone -- in the timed region the other streams do;
             # tflops = fp64-equivalent (algorithmic fp64 flops / time), frac = over cuBLAS DGEMM of this run
             'by_launch_class': by_class,
             'potrf_ms': potrf_ms,
@@ -705,7 +720,9 @@ def run_b200(args):
             'config': workload_config(),
             'run': {'trials_per_step_per_gpu': trials_per_step, 'streams': G, 'batch': B,
                     'parallelism': 'trials sharded r mod W, no collective inside the step, one gather '
-                                   'of picks', 'rng': 'device Philox4x32-10 keyed (seed, trial)'},
+                                   'of picks', 'rng': 'device Philox4x32-10 keyed (seed, trial)',
+                    'host_issue_ms_per_step': host_issue_ms,
+                    'launches_per_step': launches / max(1, args.steps)},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': sum(g.h2d_bytes for g in groups),

@@ -337,6 +337,12 @@ int ocbo_potrf_ws_profile(double* A, int n, int lda, int64_t s_a,
  * Each thread block runs `iters` dependent-free DMMA.8x8x4 / DFMA chains. */
 int ocbo_probe_dmma(double* sink, int blocks, int iters, ocbo_stream_t stream);
 int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream);
+/* SE kernel values scale * exp(-d2 / 2) of n scaled squared distances, twice: `lockstep` through the branch-free
+ * exp chain the covariance epilogue of the int8 kernel evaluates eight at a time (csrc/common.cuh: exp_core), `plain`
+ * through libdevice's exp, one call per element, like every other Gram kernel.  The two must be bit-identical
+ * (tests/test_gpu_ozaki.py); replaces nothing in the reference. */
+int ocbo_probe_kern_se(const double* d2, double scale, int64_t n, double* lockstep, double* plain,
+                       ocbo_stream_t stream);
 /* Plain C = A B^T DGEMM (n x n x n, multiples of 128) through the library's
  * DMMA tile core -- the GEMM-shaped roofline reference for the core itself. */
 int ocbo_probe_dgemm_nt(const double* A, const double* B, double* C, int n,

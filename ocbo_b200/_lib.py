@@ -55,6 +55,7 @@ _PROTOS = {
     'ocbo_probe_dmma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dfma': (_I, [_VP, _I, _I, _VP]),
     'ocbo_probe_dgemm_nt': (_I, [_VP, _VP, _VP, _I, _VP]),
+    'ocbo_probe_kern_se': (_I, [_VP, ctypes.c_double, _L, _VP, _VP, _VP]),
     'ocbo_probe_igemm_nt': (_I, [_VP, _L, _VP, _L, _VP, _L, _I, _I, _I, _VP]),
     'ocbo_ozaki_ws_bytes': (_L, [_I, _I, _I]),
     'ocbo_ozaki_slice_pairs': (_I, []),

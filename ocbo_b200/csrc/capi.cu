@@ -996,6 +996,13 @@ int ocbo_probe_dfma(double* sink, int blocks, int iters, ocbo_stream_t stream) {
   CK(launch_probe_dfma(sink, blocks, iters, (cudaStream_t)stream), "ocbo_probe_dfma");
   return 0;
 }
+int ocbo_probe_kern_se(const double* d2, double scale, int64_t n, double* lockstep, double* plain,
+                       ocbo_stream_t stream) {
+  if (n < 0) return fail_arg(3, "n < 0");
+  if (n > 0 && (!d2 || !lockstep || !plain)) return fail_arg(1, "null buffer");
+  CK(launch_probe_kern_se(d2, scale, n, lockstep, plain, (cudaStream_t)stream), "ocbo_probe_kern_se");
+  return 0;
+}
 int ocbo_probe_igemm_nt(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C, int64_t ldc, int m,
                         int n, int k, ocbo_stream_t stream) {
   if (!A || !B || !C) return fail_arg(1, "null");

@@ -318,13 +318,20 @@ postcov_kernel(const __grid_constant__ CUtensorMap mapV1, const __grid_constant_
           kv[mi][ni][0] = dist2_np(na[r], ncol.x, d0);
           kv[mi][ni][1] = dist2_np(na[r], ncol.y, d1);
         }
+      if constexpr (KIND == OCBO_KERNEL_SE) {  // exp chains in lockstep, one row of fragments at a time
 #pragma unroll
-      for (int mi = 0; mi < HM; ++mi)
+        for (int mi = 0; mi < HM; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < G::NI; ++ni) {
-          kv[mi][ni][0] = kern_eval(KIND, scale, kv[mi][ni][0]);
-          kv[mi][ni][1] = kern_eval(KIND, scale, kv[mi][ni][1]);
-        }
+          for (int ni = 0; ni < G::NI; ni += 2) kern_eval_se<4>(scale, &kv[mi][ni][0]);  // 8 at a time would spill (128 registers)
+      } else {
+#pragma unroll
+        for (int mi = 0; mi < HM; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < G::NI; ++ni) {
+            kv[mi][ni][0] = kern_eval(KIND, scale, kv[mi][ni][0]);
+            kv[mi][ni][1] = kern_eval(KIND, scale, kv[mi][ni][1]);
+          }
+      }
 #pragma unroll
       for (int mi = 0; mi < HM; ++mi)
 #pragma unroll

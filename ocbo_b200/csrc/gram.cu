@@ -85,10 +85,15 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs a) {
     kv[k][0] = dist2_np(n1s[r], nc.x, d0);
     kv[k][1] = dist2_np(n1s[r], nc.y, d1);
   }
+  if constexpr (KIND == OCBO_KERNEL_SE) {  // the exp chains in lockstep (common.cuh: same bits as kern_eval)
 #pragma unroll
-  for (int k = 0; k < GT / 8; ++k) {
-    kv[k][0] = kern_eval(KIND, scale, kv[k][0]);
-    kv[k][1] = kern_eval(KIND, scale, kv[k][1]);
+    for (int k = 0; k < GT / 8; k += 4) kern_eval_se<8>(scale, &kv[k][0]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < GT / 8; ++k) {
+      kv[k][0] = kern_eval(KIND, scale, kv[k][0]);
+      kv[k][1] = kern_eval(KIND, scale, kv[k][1]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < GT / 8; ++k) {
@@ -235,7 +240,13 @@ __global__ void __launch_bounds__(128) post_mean_kernel(MeanArgs a) {
 #pragma unroll
         for (int d = 0; d < MAXD; ++d)
           if (d < D) dot = fma(xi[d], xs[d][j + u], dot);
-        kv[u] = kern_eval(KIND, scale, dist2_np(ni, ns[j + u], dot));
+        kv[u] = dist2_np(ni, ns[j + u], dot);
+      }
+      if constexpr (KIND == OCBO_KERNEL_SE) {
+        kern_eval_se<4>(scale, kv);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kv[u] = kern_eval(KIND, scale, kv[u]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc = fma(kv[u], al[j + u], acc);

@@ -118,6 +118,8 @@ cudaError_t launch_joint_pick(const double* seg_max, const int32_t* seg_arg, int
                               double* out_gain, int batch, cudaStream_t st);
 cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_probe_dfma(double* sink, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_probe_kern_se(const double* d2, double scale, int64_t n, double* lockstep, double* plain,
+                                 cudaStream_t st);
 // fp64 rank-k updates through the int8 tensor cores (ozaki.cu): split a panel into int8 slices, then
 // C (region) -= P Q^T from the split workspace
 size_t ozaki_ws_bytes(int rows, int kw, int batch);

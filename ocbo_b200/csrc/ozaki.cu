@@ -370,8 +370,13 @@ ozaki_update_kernel(OzParams p) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) kv[i] = kscale - 0.5 * kv[i];
 #else
+          if (p.kind == OCBO_KERNEL_SE) {  // 16 exp chains in lockstep (common.cuh: exp_core), same bits as kern_eval
+            kern_eval_se<8>(kscale, kv);       // 8 per call: 16 would spill at the kernel's 168 registers
+            kern_eval_se<8>(kscale, kv + 8);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) kv[i] = kern_eval(p.kind, kscale, kv[i]);
+            for (int i = 0; i < 16; ++i) kv[i] = kern_eval(p.kind, kscale, kv[i]);
+          }
 #endif
 #pragma unroll
           for (int i = 0; i < 16; ++i) Cc[(size_t)(i * 2 + rr) * p.ldc] = fma(-ebuf[(i * 2 + rr) * OZ_EPI_LD + cc], sc, kv[i]);

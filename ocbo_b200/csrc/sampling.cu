@@ -225,6 +225,28 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(double* sink, int iters
   if (s == 123.456) sink[0] = s;
 }
 
+// kern_eval_se (8 exp chains in lockstep, common.cuh) next to kern_eval (libdevice's exp, one call per element)
+__global__ void __launch_bounds__(256) probe_kern_se_kernel(const double* __restrict__ d2, double scale, int64_t n,
+                                                            double* __restrict__ lockstep, double* __restrict__ plain) {
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = base + i < n ? d2[base + i] : 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (base + i < n) plain[base + i] = kern_eval(OCBO_KERNEL_SE, scale, v[i]);
+  kern_eval_se<8>(scale, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (base + i < n) lockstep[base + i] = v[i];
+}
+cudaError_t launch_probe_kern_se(const double* d2, double scale, int64_t n, double* lockstep, double* plain,
+                                 cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  probe_kern_se_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(d2, scale, n, lockstep, plain);
+  return counted(cudaGetLastError());
+}
+
 cudaError_t launch_probe_dmma(double* sink, int blocks, int iters, cudaStream_t st) {
   probe_dmma_kernel<<<blocks, 256, 0, st>>>(sink, iters);
   return counted(cudaGetLastError());
