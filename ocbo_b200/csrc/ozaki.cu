@@ -178,7 +178,10 @@ template <int MODE>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_update_kernel(OzParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the shared array: rounding the pointer through an integer loses the address
+  // space, and every epilogue access to shared memory became a generic LD / ST (ncu: the Gram epilogue's dot products
+  // waited on them)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   double* epi = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
   double* red_v = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_EPI_BYTES + OZ_BAR_BYTES);  // [2][8][32]
   int* red_r = reinterpret_cast<int*>(red_v + 2 * OZ_EPI_WARPS * 32);
