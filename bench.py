@@ -662,6 +662,11 @@ def run_b200(args):
                 # context: the measured bf16 burst figure is itself taken at the power cap, so a kernel that moves
                 # fewer operand bytes per product than the bf16 GEMM of the probe can pass 2 x that figure
                 'frac_of_nominal_4500': (tops / 4500.0) if tops else None,
+                'frac_note': 'frac > 1 is possible: MEASURED_PEAKS.json has no int8 row, the peak is 2 x its bf16 burst '
+                             'figure, which was itself taken at the power cap; this kernel issues one MMA per P slice '
+                             'against up to four stacked Q slices (fewer shared-memory operand reads per product than a '
+                             'plain GEMM), so it draws less power per operation and passes it, as it passes the cuBLASLt '
+                             'int8 GEMM measured in this run',
                 'fp64_equivalent_tflops': trailing_tflops,
                 'fp64_equivalent_over_cublas_dgemm': frac(trailing_tflops),
                 'traffic': load_traffic(B),

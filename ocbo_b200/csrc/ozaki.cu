@@ -333,12 +333,20 @@ ozaki_update_kernel(OzParams p) {
             const double* x = p.X + (size_t)b * p.sX + (size_t)((isa ? ti * OZ_BM : tj * OZ_BN) + r) * D;
             double* dst = isa ? xa + r : xb + r;
             const int ld = isa ? OZ_BM : OZ_BN;
-            double nrm = 0.0;
-            for (int d = 0; d < D; ++d) {
-              const double v = x[d] / th[TH_BW + d];
-              dst[d * ld] = v;
-              nrm = sqnorm_np(nrm, v);
+            double xv[OZ_GRAM_D], bw[OZ_GRAM_D];  // all loads first: they are independent
+#pragma unroll
+            for (int d = 0; d < OZ_GRAM_D; ++d) {
+              xv[d] = d < D ? x[d] : 0.0;
+              bw[d] = d < D ? th[TH_BW + d] : 1.0;
             }
+            double nrm = 0.0;
+#pragma unroll
+            for (int d = 0; d < OZ_GRAM_D; ++d)
+              if (d < D) {
+                const double v = xv[d] / bw[d];
+                dst[d * ld] = v;
+                nrm = sqnorm_np(nrm, v);
+              }
             na[e] = nrm;
           }
         }
@@ -357,18 +365,21 @@ ozaki_update_kernel(OzParams p) {
           for (int d = 0; d < OZ_GRAM_D; ++d) xc[d] = d < D ? xb[d * OZ_BN + col] : 0.0;
           const double ncol = nb[col];
           double* Cc = Ct + c16 * 16 + cc;
+          // dimension-major: 16 independent FMAs between two dependent ones (a dependent fp64 operation costs ~35
+          // clocks here, and the eight epilogue warps are all the latency hiding there is)
           double kv[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = q * 32 + i * 2 + rr;
-            double dot = 0.0;
+          for (int i = 0; i < 16; ++i) kv[i] = 0.0;
 #ifndef OCBO_OZ_NODOT   // diagnostic variant: what do the shared-memory reads of the row points cost?
 #pragma unroll
-            for (int d = 0; d < OZ_GRAM_D; ++d)
-              if (d < D) dot = fma(xa[d * OZ_BM + r], xc[d], dot);
+          for (int d = 0; d < OZ_GRAM_D; ++d)
+            if (d < D) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) kv[i] = fma(xa[d * OZ_BM + q * 32 + i * 2 + rr], xc[d], kv[i]);
+            }
 #endif
-            kv[i] = dist2_np(na[r], ncol, dot);
-          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) kv[i] = dist2_np(na[q * 32 + i * 2 + rr], ncol, kv[i]);
 #ifdef OCBO_OZ_NOEXP  // diagnostic variant (tests/tools/oz_gram_variants.py): what does the exp chain cost?
 #pragma unroll
           for (int i = 0; i < 16; ++i) kv[i] = kscale - 0.5 * kv[i];
