@@ -79,19 +79,29 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi is started before the warm-up (it can take longer to come up than
+        a short timed region lasts), only the rows from here on are used."""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        t0, t1 = getattr(self, 't0', 0.0), time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
+        window = 'timed region'
+        if not rows and self.rows:   # region shorter than the sampling period: the warm-up ran the same load
+            rows, window = [r for _, r in self.rows[-5:]], 'warm-up (timed region shorter than one sample)'
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -102,7 +112,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(max(mx)) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'window': window}
 
 
 def cpu_threads():
@@ -431,9 +441,10 @@ def run_b200(args):
         barrier()
         return start.elapsed_time(end)
 
-    run_resident(args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
+    run_resident(args.warmup)
+    sampler.mark()
     from ocbo_b200._lib import LIB
     launches0 = int(LIB.ocbo_launch_count())
     ms_resident = run_resident(args.steps)
