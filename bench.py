@@ -138,6 +138,10 @@ def load_traffic(batch):
         if 'algorithmic_bytes' in t:
             out['algorithmic_bytes'] = t['algorithmic_bytes'] * batch
             out['dram_over_algorithmic'] = t['dram_bytes'] / t['algorithmic_bytes']
+        # per launch (the capture is at batch 1; a launch of `batch` problems moves `batch` times as much)
+        out['dram_bytes_per_launch'] = t['dram_bytes'] * batch / max(1, t['launches'])
+        if 'algorithmic_bytes' in t:
+            out['algorithmic_bytes_per_launch'] = t['algorithmic_bytes'] * batch / max(1, t['launches'])
         return out
     except Exception:
         return None
